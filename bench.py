@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- RX throughput of the 802.11a/g baseband on B200 (BASELINE.json metric:
+"RX Msamples/s and decoded Mb/s per GPU, 64-QAM 3/4").
+
+Workload (BASELINE.json configs[2], SURVEY.md 8d "C3"): synthetic 20 MHz baseband, 64-QAM 3/4,
+1528-byte PSDUs (57 OFDM symbols, 4961 samples) back to back with 1100-sample idle gaps,
+AWGN at 30 dB, LMS equalizer, hard-decision Viterbi.  The capture is generated on the GPU by
+the library's own TX chain and Philox channel and is far larger than L2 (no flush needed).
+
+One "step" = one wifi_b200_rx_batch_dev pass over the whole resident capture (all links).
+`value` = complex samples consumed per second, all ranks (device-resident input).
+`e2e`   = the same pass through wifi_b200_rx_batch with pinned HOST input and host results.
+`--impl reference` times the CPU oracle (a port of the reference algorithm; the real
+gr-ieee802-11 flowgraph cannot be built here) on a bounded sample with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENC = 7
+PSDU_LEN = 1528
+GAP = 1100
+SNR_DB = 30.0
+ALGO = 1          # LMS
+LEAD = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--links", type=int, default=64, help="independent links per GPU")
+    ap.add_argument("--frames-per-link", type=int, default=512)
+    ap.add_argument("--algo", type=int, default=ALGO)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=1536, help="frames of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def frame_samples():
+    n_sym = -(-(16 + 8 * PSDU_LEN + 6) // 216)
+    return 80 * (5 + n_sym) + 1
+
+
+def make_psdus(n, seed):
+    import zlib
+    rng = np.random.default_rng(seed)
+    out = []
+    hdr = bytes([0x08, 0, 0, 0]) + b"\x42" * 6 + b"\x23" * 6 + b"\xff" * 6
+    pay = rng.integers(0, 256, (n, PSDU_LEN - 28), dtype=np.uint8)
+    for i in range(n):
+        body = hdr + int((i & 0xfff) << 4).to_bytes(2, "little") + pay[i].tobytes()
+        out.append(body + zlib.crc32(body).to_bytes(4, "little"))
+    return out
+
+
+def build_capture(h, W, torch, n_links, fpl, seed):
+    """TX + channel on the GPU.  Returns (capture tensor [2*N] f32, link_off, psdus)."""
+    n = n_links * fpl
+    flen = frame_samples()
+    stride = flen + GAP
+    link_len = LEAD + fpl * stride
+    psdus = make_psdus(n, seed)
+    tx = torch.empty(2 * n * flen, dtype=torch.float32, device="cuda")
+    tot, off = h.tx_dev(psdus, tx.data_ptr(), n * flen, enc=ENC)
+    assert tot == n * flen
+    cap = torch.zeros(2 * n_links * link_len, dtype=torch.float32, device="cuda")
+    rng = np.random.default_rng(seed + 1)
+    seg = np.zeros(n + n_links, W.wifi_b200.CHANSEG_DTYPE)
+    f = np.arange(n)
+    seg["in_off"][:n] = off[:-1]
+    seg["in_len"][:n] = flen
+    seg["out_off"][:n] = (f // fpl) * link_len + LEAD + (f % fpl) * stride
+    seg["n"][:n] = stride
+    # noise-only lead-in of every link
+    seg["in_len"][n:] = 0
+    seg["out_off"][n:] = np.arange(n_links) * link_len
+    seg["n"][n:] = LEAD
+    seg["n0"] = seg["out_off"]
+    seg["gain"] = 0.6
+    seg["noise_sigma"] = 0.6 * 10 ** (-SNR_DB / 20)
+    seg["cfo"][:n] = rng.uniform(-0.0025 * 2 * np.pi, 0.0025 * 2 * np.pi, n)   # |eps| <= 50 kHz at 20 Msps
+    seg["phase0"][:n] = rng.uniform(-np.pi, np.pi, n)
+    seg["n_taps"] = 1
+    seg["tap_re"][:, 0] = 1.0
+    seg["seed"] = seed
+    seg["stream"] = 0
+    h.channel_dev(tx.data_ptr(), cap.data_ptr(), seg)
+    del tx
+    link_off = (np.arange(n_links + 1) * link_len).astype(np.uint64)
+    return cap, link_off, psdus
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def config_dict(args, n_links, fpl):
+    return {"workload": "BASELINE configs[2]: 54 Mb/s 64-QAM 3/4 batched RX, 1528-byte PSDUs (57 symbols, 4961 samples) + 1100-sample gaps, AWGN 30 dB",
+            "equalizer": ["LS", "LMS", "COMB", "STA"][args.algo], "links_per_gpu": n_links, "frames_per_link": fpl,
+            "samples_per_gpu": int(n_links * (LEAD + fpl * (frame_samples() + GAP))),
+            "l2_policy": "input (%.2f GB per GPU) larger than L2, no flush" % (n_links * (LEAD + fpl * (frame_samples() + GAP)) * 8 / 1e9),
+            "parallelism": "links sharded across GPUs, no data-path collective"}
+
+
+def run_reference(args):
+    """CPU arm: the oracle (port of the reference algorithm) on all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    flen = frame_samples()
+    fpl = 48
+    n_links = max(threads, 1)
+    rng = np.random.default_rng(0)
+    # one link built with the oracle TX + channel, replicated with different noise per link
+    psdus = make_psdus(fpl, 0)
+    parts = [np.zeros(LEAD, np.complex64)]
+    for i, p in enumerate(psdus):
+        parts += [O.tx_frame(p, ENC, 1 + i % 127), np.zeros(GAP, np.complex64)]
+    clean = np.concatenate(parts).astype(np.complex64)
+    links = [O.channel(clean, gain=0.6, cfo=float(rng.uniform(-0.015, 0.015)), noise_sigma=0.6 * 10 ** (-SNR_DB / 20), seed=l) for l in range(n_links)]
+    x = np.concatenate(links)
+    off = np.arange(n_links) * clean.size
+    ln = np.full(n_links, clean.size)
+    times = []
+    ok = 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = O.rx_links(x, off, ln, n_threads=threads, algo=args.algo, want_carrier=False)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            ok = int(r.frames["crc_ok"].sum())
+    t = float(np.sum(times))
+    msps = x.size * len(times) / t / 1e6
+    line = {"impl": "reference", "metric": "rx_msamples_per_s", "value": msps, "unit": "Msamples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "config": config_dict(args, n_links, fpl),
+            "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                             "sample": "%d links x %d frames (%d samples) per step, one link per host thread" % (n_links, fpl, x.size)},
+            "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    line["decoded_mbps"] = ok * (PSDU_LEN - 4) * 8 / (t / len(times)) / 1e6
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import wifi_b200 as pkg
+    W = pkg
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_links, fpl = args.links, args.frames_per_link
+    n = n_links * fpl
+    flen = frame_samples()
+    n_samples = n_links * (LEAD + fpl * (flen + GAP))
+    h = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=n_samples + 1024, max_frames=n + n_links + 1024)
+    cap, link_off, psdus = build_capture(h, W, torch, n_links, fpl, seed=1000 + rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        h.rx_batch_dev(cap.data_ptr(), link_off, final=True, fetch=False)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    stage_acc = {}
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()                      # synchronises its own stream before returning
+        for k, v in h.stage_times().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    # the library times every stage with CUDA events on its own stream; the step time on the device is
+    # their sum, the host wall clock adds launch/sync gaps -- report the larger (honest) one
+    dev_ms = sum(stage_acc.values())
+    elapsed = max(wall, dev_ms / 1e3)
+    clocks = sampler.stop() if sampler else None
+    res = h.results()
+    st_frames = len(res.frames)
+    st_ok = int(res.frames["crc_ok"].sum())
+    # parity property at full size: every CRC-ok PDU is one of the PSDUs that were sent
+    sent = {p[:-4] for p in psdus}
+    pd = res.pdus()
+    assert all(p in sent for p in pd[:2000]), "decoded PDU not among the transmitted ones"
+    tvec = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([n_samples, st_frames, st_ok, st_ok * (PSDU_LEN - 4)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tvec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)     # the only collective: counters over NCCL
+    elapsed_max = float(tvec.item())
+    tot_samples, tot_frames, tot_ok, tot_bytes = [int(v) for v in cnt.tolist()]
+    value = tot_samples * args.steps / elapsed_max / 1e6
+    mbps = tot_bytes * 8 * args.steps / elapsed_max / 1e6
+
+    # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(cap.numel(), dtype=torch.float32, pin_memory=True)
+        host.copy_(cap)
+        torch.cuda.synchronize()
+        hn = host.numpy().view(np.complex64)
+        for _ in range(2):
+            h.rx_batch(hn, link_off, final=True, fetch=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            h.rx_batch(hn, link_off, final=True, fetch=False)   # frames + PSDU store land in pinned host memory
+        barrier()
+        te = time.perf_counter() - t0
+        tv = torch.tensor([te], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        c = h.counts()
+        e2e = {"value": tot_samples * args.steps / float(tv.item()) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(n_samples * 8), "d2h_bytes_per_step": int(c["n_frames"] * 104 + c["psdu_store_bytes"]),
+               "decoded_mbps": tot_bytes * 8 * args.steps / float(tv.item()) / 1e6}
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    n_jobs = st_ok if st_ok else n
+    # algorithmic bytes per launch of the dominant kernel (Viterbi): N_CBPS coded bits in + PSDU bytes out per frame
+    vit_alg = n * (57 * 288 / 8 + PSDU_LEN)
+    vit_ms = stage_ms.get("viterbi", 0.0)
+    achieved = vit_alg / (vit_ms * 1e-3) / 1e9 if vit_ms > 0 else 0.0
+    # integer work of the kernel: 64 ACS x 4 int-ops per decoded bit
+    dec_bits = n * (PSDU_LEN + 2) * 8
+    roof = {"kernel": "k_viterbi", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": vit_alg, "ms_per_launch": vit_ms,
+            "note": "ALU-bound kernel: %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % (dec_bits * 256 / (vit_ms * 1e-3) / 1e12 if vit_ms else 0.0)}
+    path_alg = n_samples * 8 + n * PSDU_LEN
+    step_ms = 1e3 * elapsed_max / args.steps
+    line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
+            "decoded_mbps": mbps, "frames_per_step": tot_frames, "crc_ok_per_step": tot_ok,
+            "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * args.steps,
+            "roofline": roof, "stage_ms": stage_ms,
+            "path_hbm": {"algorithmic_GBps": path_alg / (step_ms * 1e-3) / 1e9, "frac_of_peak": path_alg / (step_ms * 1e-3) / 1e9 / hbm_peak}}
+    if not args.no_cpu and world == 1:
+        from oracle import oracle as O
+        nf = min(args.cpu_frames, fpl * n_links)
+        nl = max(1, nf // fpl)
+        sl = int(link_off[nl])
+        xs = cap[:2 * sl].cpu().numpy().view(np.complex64)
+        t0 = time.perf_counter()
+        r = O.rx_links(xs, link_off[:nl].astype(np.int64), np.diff(link_off[:nl + 1]).astype(np.int64), n_threads=1, algo=args.algo, want_carrier=False)
+        dt = time.perf_counter() - t0
+        # same inputs, same answers: the GPU frame table of these links equals the oracle's
+        g = res.frames[np.isin(res.frames["link"], np.arange(nl))]
+        g = g[np.lexsort((g["trigger"], g["link"]))]
+        same = len(g) == len(r.frames) and all(np.array_equal(g[k], r.frames[k]) for k in ("trigger", "frame_start", "encoding", "length", "crc_ok"))
+        line["cpu_baseline"] = {"value": sl / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+                                "sample": "first %d links (%d frames, %d samples) of the same capture, oracle single thread, %.1f s" % (nl, nl * fpl, sl, dt),
+                                "matches_gpu_frame_table": bool(same)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

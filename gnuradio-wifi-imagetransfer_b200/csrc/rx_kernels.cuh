@@ -1,0 +1,730 @@
+// rx_kernels.cuh -- receive chain of wifi_phy_hier as batch kernels over many frames.
+// Reference stages (gnu_radio/wifi_phy_hier.grc):
+//   k_detect      R1  autocorrelation front-end (:100-260) + threshold compare of sync_short (:716-734)
+//   k_select      R2  sync_short plateau / MIN_GAP / MAX_SAMPLES state machine over the flag bitmap
+//   k_sync_long   R2+R3  coarse CFO, derotation, 64-tap LTS matched filter, top-4 peak pairing (:698-715)
+//   k_demod       R3 COPY + R4 FFT (:480-500) + R5 frame_equalizer (:550-569), one warp per frame
+//   k_signal      R5f SIGNAL deinterleave + Viterbi + parse
+//   k_plan        R6 decode_mac tag / symbol collection state machine (:533-549)
+//   k_pack        R6 unpack bits, deinterleave, depuncture -> 2-bit symbols, 8 trellis steps per word
+//   k_viterbi     R6a-c Viterbi, descramble, CRC-32 -> PSDU bytes
+#pragma once
+#include "viterbi.cuh"
+
+// ------------------------------------------------------------------ R1 front-end
+__device__ __forceinline__ cf fe_prod(const cf *x, int64_t j, int hist)
+{
+    if (j - 16 < -(int64_t)hist) return {0.f, 0.f};
+    cf a = x[j], d = x[j - 16];
+    return {a.re * d.re + a.im * d.im, a.im * d.re - a.re * d.im};
+}
+__device__ __forceinline__ float fe_pw(const cf *x, int64_t j, int hist)
+{
+    if (j < -(int64_t)hist) return 0.f;
+    cf a = x[j];
+    return a.re * a.re + a.im * a.im;
+}
+
+__device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int64_t chunk)
+{
+    int lo = 0, hi = n_links - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (links[mid].chunk_base <= chunk) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// One thread per FE_CHUNK samples of one link: re-seed the two running sums exactly as the
+// oracle does at every multiple of FE_CHUNK, run them over the chunk, emit bit n = (c[n] > thr).
+__global__ void __launch_bounds__(128) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
+                                                 int64_t total_chunks, float thr_f, uint32_t *__restrict__ flags)
+{
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total_chunks) return;
+    int l = find_link(links, n_links, gid);
+    const LinkDesc L = links[l];
+    const cf *x = iq + L.x_off;
+    const int hist = L.hist;
+    int64_t i0 = (gid - L.chunk_base) * FE_CHUNK;
+    float sar = 0.f, sai = 0.f, sp = 0.f;
+    for (int64_t j = i0 - 47; j < i0; ++j) {
+        if (j < -(int64_t)hist) continue;
+        cf p = fe_prod(x, j, hist);
+        sar += p.re;
+        sai += p.im;
+    }
+    for (int64_t j = i0 - 63; j < i0; ++j) {
+        if (j < -(int64_t)hist) continue;
+        sp += fe_pw(x, j, hist);
+    }
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    int64_t end = i0 + FE_CHUNK < L.len ? i0 + FE_CHUNK : L.len;
+#pragma unroll 4
+    for (int64_t i = i0; i < end; ++i) {
+        cf pr = fe_prod(x, i, hist);
+        sar += pr.re;
+        sai += pr.im;
+        float ar = sar, ai = sai;
+        if (i - 47 >= -(int64_t)hist) {
+            cf po = fe_prod(x, i - 47, hist);
+            sar -= po.re;
+            sai -= po.im;
+        }
+        sp += fe_pw(x, i, hist);
+        float p = sp;
+        if (i - 63 >= -(int64_t)hist) sp -= fe_pw(x, i - 63, hist);
+        float c = sqrtf(ar * ar + ai * ai) / p;
+        int k = (int)(i - i0);
+        if (c > thr_f) w[k >> 5] |= 1u << (k & 31);
+    }
+    reinterpret_cast<uint4 *>(flags)[gid] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------ R2 sync_short selection
+// One warp per link.  cand(m) = flag[m] & flag[m-1] & flag[m-2] (plateau counter reached
+// min_plateau = 2 before m); triggers are the greedy chain "first candidate more than
+// MIN_GAP after the previous trigger" (COPY-state retrigger and SEARCH-state trigger
+// coincide).  Pass 0 counts, pass 1 writes the frame records.
+__device__ __forceinline__ int64_t next_candidate(const uint32_t *fw, int64_t n_words, int64_t pos, int lane, int min_plateau)
+{
+    int64_t wbase = (pos >> 5) & ~31ll;
+    for (; wbase < n_words; wbase += 32) {
+        int64_t wi = wbase + lane;
+        uint32_t w = (wi < n_words) ? fw[wi] : 0u;
+        uint32_t pw = (wi >= 1 && wi - 1 < n_words) ? fw[wi - 1] : 0u;
+        uint32_t cand = w;
+        for (int k = 1; k <= min_plateau; ++k) cand &= (w << k) | (pw >> (32 - k));
+        int64_t first = wi * 32;
+        if (first < pos) {
+            int64_t d = pos - first;
+            cand = d >= 32 ? 0u : (cand & (0xffffffffu << d));
+        }
+        uint32_t any = __ballot_sync(0xffffffffu, cand != 0u);
+        if (any) {
+            int src = __ffs((int)any) - 1;
+            uint32_t c = __shfl_sync(0xffffffffu, cand, src);
+            return (wbase + src) * 32 + (__ffs((int)c) - 1);
+        }
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ flags, LinkDesc *links, int n_links, wifi_b200_frame *frames,
+                                                 int *counters /* [0]=frames [1]=rows(lo) */, unsigned long long *row_counter,
+                                                 int64_t max_frames, int min_plateau, int *err)
+{
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_links) return;
+    LinkDesc L = links[warp];
+    const uint32_t *fw = flags + L.chunk_base * (FE_CHUNK / 32);
+    int64_t n_words = (L.len + 31) >> 5;
+    int count = 0;
+    int64_t rows = 0;
+    int base = 0;
+    long long row_base = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int64_t pos = L.min_pos > 0 ? L.min_pos : 0, prev = -1;
+        int k = 0;
+        long long racc = 0;
+        for (;;) {
+            int64_t m = next_candidate(fw, n_words, pos, lane, min_plateau);
+            if (m >= L.len) m = -1;
+            if (prev >= 0) {
+                int64_t endp = (m >= 0) ? m : L.len;
+                int blen = (int)((endp - prev) < SS_MAX_SAMPLES ? (endp - prev) : SS_MAX_SAMPLES);
+                if (pass == 1 && lane == 0 && base + k - 1 < max_frames) {
+                    wifi_b200_frame f;
+                    f.trigger = prev; f.link = warp; f.burst_len = blen; f.freq_short = 0.f; f.freq_long = 0.f;
+                    f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
+                    f.frame_symbols = 0; f.n_rows = 0; f.accepted = 0; f.decoded = 0; f.crc_ok = 0; f.snr = 0.0;
+                    f.row_off = row_base + racc; f.psdu_off = -1;
+                    frames[base + k - 1] = f;
+                }
+                racc += blen / 80 + 1;
+            }
+            if (m < 0) break;
+            prev = m;
+            ++k;
+            pos = m + SS_MIN_GAP + 1;
+        }
+        if (pass == 0) {
+            count = k;
+            rows = racc;
+            if (lane == 0) {
+                base = atomicAdd(&counters[0], count);
+                row_base = (long long)atomicAdd(row_counter, (unsigned long long)rows);
+                if ((int64_t)base + count > max_frames) atomicExch(err, WIFI_E_OVERFLOW);
+                links[warp].frame_first = base;
+                links[warp].frame_count = ((int64_t)base + count > max_frames) ? 0 : count;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            row_base = __shfl_sync(0xffffffffu, row_base, 0);
+            if ((int64_t)base + count > max_frames) return;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ R2/R3 sync_long search
+// One block (128 threads) per frame.
+__global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames)
+{
+    __shared__ cf sb[SYNC_LENGTH + 64];
+    __shared__ cf scorr[SYNC_LENGTH];
+    __shared__ float smag[SYNC_LENGTH];
+    __shared__ float s_freq;
+    __shared__ float rmax[4];
+    __shared__ int ridx[4];
+    __shared__ int top[4];
+    int f = blockIdx.x;
+    if (f >= n_frames) return;
+    wifi_b200_frame F = frames[f];
+    const LinkDesc L = links[F.link];
+    const cf *x = iq + L.x_off;
+    const int tid = threadIdx.x;
+    const int hist = L.hist;
+    int64_t t = F.trigger;
+    if (tid == 0) {
+        // a[t]: the moving_average_cc value sync_short sees on its port 1 at the trigger
+        int64_t i0 = t & ~(int64_t)(FE_CHUNK - 1);
+        float sar = 0.f, sai = 0.f;
+        for (int64_t j = i0 - 47; j < i0; ++j) {
+            if (j < -(int64_t)hist) continue;
+            cf p = fe_prod(x, j, hist);
+            sar += p.re;
+            sai += p.im;
+        }
+        for (int64_t i = i0; i <= t; ++i) {
+            cf pr = fe_prod(x, i, hist);
+            sar += pr.re;
+            sai += pr.im;
+            if (i < t && i - 47 >= -(int64_t)hist) {
+                cf po = fe_prod(x, i - 47, hist);
+                sar -= po.re;
+                sai -= po.im;
+            }
+        }
+        s_freq = wdm_atan2f(sai, sar) / 16;
+    }
+    __syncthreads();
+    const float freq = s_freq;
+    if (tid == 0) frames[f].freq_short = freq;
+    if (F.burst_len < SYNC_LENGTH + 63) return;   // SYNC never completes (end of stream)
+    for (int j = tid; j < SYNC_LENGTH + 63; j += blockDim.x) {
+        int64_t src = t + j - 16;
+        cf s = src >= -(int64_t)hist ? x[src] : cf{0.f, 0.f};
+        sb[j] = cmul(s, crot(-freq * (float)j));
+    }
+    __syncthreads();
+    for (int i = tid; i < SYNC_LENGTH; i += blockDim.x) {
+        cf acc = {0.f, 0.f};
+#pragma unroll 8
+        for (int m = 0; m < 64; ++m) acc = cadd(acc, cmul(c_tab.long_taps[63 - m], sb[i + m]));
+        scorr[i] = acc;
+        smag[i] = acc.re * acc.re + acc.im * acc.im;
+    }
+    __syncthreads();
+    // four largest |corr|^2, earlier index first on ties (stable descending sort)
+    for (int r = 0; r < 4; ++r) {
+        float bm = -1.f;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < SYNC_LENGTH; i += blockDim.x) {
+            float v = smag[i];
+            if (v > bm) { bm = v; bi = i; }   // ascending i per thread: first max kept
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            float om = __shfl_xor_sync(0xffffffffu, bm, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+        }
+        if ((tid & 31) == 0) { rmax[tid >> 5] = bm; ridx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 4; ++w)
+                if (rmax[w] > bm || (rmax[w] == bm && ridx[w] < bi)) { bm = rmax[w]; bi = ridx[w]; }
+            top[r] = bi;
+            smag[bi] = -2.f;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int found = 0, fs = SYNC_LENGTH;
+        float fo = 0.f;
+        for (int i = 0; i < 3 && found != 64; ++i)
+            for (int k = i + 1; k < 4; ++k) {
+                int lo = min(top[i], top[k]), hi = max(top[i], top[k]);
+                int diff = hi - lo;
+                if (diff == 63 || diff == 64 || diff == 65) {
+                    cf first = scorr[lo], second = scorr[hi];
+                    cf pr = cmul(first, cf{second.re, -second.im});
+                    fs = lo;
+                    fo = wdm_atan2f(pr.im, pr.re) / (float)diff;
+                    found = diff;
+                    if (diff == 64) break;
+                }
+            }
+        frames[f].found = found;
+        frames[f].frame_start = fs;
+        frames[f].freq_long = fo;   // provisional: resolved against the carry in k_demod
+    }
+}
+
+// ------------------------------------------------------------------ R3 COPY + R4 + R5
+struct DemodParams {
+    double bw, freq;
+    int algo;
+    int want_carrier;
+};
+
+__device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
+{
+    int R = avail - fs;
+    if (R <= 0) return 0;
+    int E = R <= 128 ? R : 128 + 64 * ((R - 128) / 80) + max(0, ((R - 128) % 80) - 16);
+    return last ? E / 64 : (E + 63) / 64;
+}
+
+// phase 0: symbols 0..2 (LTS1, LTS2, SIGNAL) -> EqState ; phase 1: data symbols -> rows
+__global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
+                                                EqState *states, uint8_t *rows, cf *carrier, DemodParams prm, int phase)
+{
+    __shared__ cf s_hu[4][64];
+    __shared__ double s_md[4][64], s_ms[4][64];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * 4 + wib;
+    if (f >= n_frames) return;
+    const wifi_b200_frame F = frames[f];
+    if (F.burst_len < SYNC_LENGTH + 63) return;
+    const LinkDesc L = links[F.link];
+    const cf *x = iq + L.x_off;
+    const bool last = L.is_final && (f == L.frame_first + L.frame_count - 1);
+    float fo = F.freq_long;
+    if (phase == 0) {
+        if (!F.found) {   // sync_long keeps d_freq_offset of the last burst that matched
+            fo = L.fo_carry;
+            for (int g = f - 1; g >= L.frame_first; --g)
+                if (frames[g].found) { fo = frames[g].freq_long; break; }
+        }
+    }
+    const int avail = F.burst_len - SYNC_LENGTH;
+    const int fs = F.frame_start;
+    const int n_syms = emitted_symbols(avail, fs, last);
+    const float fshort = F.freq_short;
+    const int64_t t = F.trigger;
+    const int hist = L.hist;
+
+    const int iA = lane + 32, iB = lane;      // shifted bin of FFT outputs a (X[lane]) and b (X[lane+32])
+    const bool usedA = (iA <= 58), usedB = (iB >= 6);   // iA in 32..63 (32 = DC), iB in 0..31
+    const bool dcA = (iA == 32);
+    const int carA = c_tab.carrier_of[iA], carB = c_tab.carrier_of[iB];
+    const float ltsA = c_tab.lts[iA], ltsB = c_tab.lts[iB];
+    const int q0 = 2 * dev_bitrev5(lane);
+
+    cf HA = {0.f, 0.f}, HB = {0.f, 0.f};
+    cf pp[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    double d_er = 0.0, eps0, snr = 0.0;
+    int frame_symbols = 0, enc = 0, nb = 1;
+    int n_begin, n_end;
+    EqState *st = states + f;
+    if (phase == 0) {
+        eps0 = ((double)fshort - (double)fo) * prm.bw / (2 * M_PI * prm.freq);
+        n_begin = 0;
+        n_end = n_syms < 3 ? n_syms : 3;
+        if (lane == 0) { frames[f].freq_long = fo; frames[f].n_syms = n_syms; }
+    } else {
+        if (!F.sig_ok) return;
+        frame_symbols = F.frame_symbols;
+        enc = F.encoding;
+        nb = c_tab.mcs[enc].n_bpsc;
+        HA = st->H[iA]; HB = st->H[iB];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pp[q] = st->prev_pil[q];
+        d_er = st->d_er; eps0 = st->eps0;
+        n_begin = 3;
+        n_end = n_syms < frame_symbols + 3 ? n_syms : frame_symbols + 3;
+    }
+    int n_rows = 0;
+    for (int n = n_begin; n < n_end; ++n) {
+        // ---- sync_long COPY: fetch the symbol's samples, both derotations ----
+        cf a, b;
+        {
+            int rel0 = (n < 2) ? 64 * n + q0 : 128 + 80 * (n - 2) + 16 + q0;
+            cf v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                int j = fs + rel0 + u;
+                if (j < avail) {
+                    int64_t src = t + j - 16;
+                    cf s = src >= -(int64_t)hist ? x[src] : cf{0.f, 0.f};
+                    cf bj = cmul(s, crot(-fshort * (float)j));
+                    v[u] = cmul(bj, crot((float)j * fo));
+                } else {
+                    v[u] = {0.f, 0.f};
+                }
+            }
+            a = v[0]; b = v[1];
+        }
+        warp_fft64(a, b, lane, false);
+        // a = cur[iA], b = cur[iB] (fftshift)
+        {
+            double k = 2 * M_PI * n * 80 * (eps0 + d_er);
+            double phA = k * (iA - 32) / 64, phB = k * (iB - 32) / 64;
+            a = cmul(a, crot((float)phA));
+            b = cmul(b, crot((float)phB));
+        }
+        cf c11 = cshfl(b, 11), c25 = cshfl(b, 25), c39 = cshfl(a, 7), c53 = cshfl(a, 21);
+        const float p = (n >= 2) ? c_tab.polarity[(n - 2) % 127] : 1.f;
+        cf pil[4];
+        double beta;
+        if (n < 2) {
+            cf s = cadd(cadd(csub(c11, c25), c39), c53);
+            beta = (double)wdm_atan2f(s.im, s.re);
+            pil[0] = c11; pil[1] = cf{-c25.re, -c25.im}; pil[2] = c39; pil[3] = c53;
+        } else {
+            pil[0] = cscale(c11, p); pil[1] = cscale(c25, p); pil[2] = cscale(c39, p); pil[3] = cscale(c53, -p);
+            cf s = cadd(cadd(cadd(pil[0], pil[2]), pil[1]), pil[3]);
+            beta = (double)wdm_atan2f(s.im, s.re);
+        }
+        double er = 0.0;
+        if (n >= 2) {
+            cf s = {0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s = cadd(s, cmul(cf{pp[q].re, -pp[q].im}, pil[q]));
+            er = (double)wdm_atan2f(s.im, s.re);
+            er *= prm.bw / (2 * M_PI * prm.freq * 80);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pp[q] = pil[q];
+        const cf wb = crot((float)(-beta));
+        a = cmul(a, wb);
+        b = cmul(b, wb);
+        if (n >= 2) d_er = (1 - 0.1) * d_er + 0.1 * er;
+
+        // ---- equalizer::equalize ----
+        if (prm.algo == WIFI_EQ_COMB) {
+            cf r11 = cmul(c11, wb), r25 = cmul(c25, wb), r39 = cmul(c39, wb), r53 = cmul(c53, wb);
+            cf cp[4];
+            if (n < 2) { cp[0] = r11; cp[1] = cf{-r25.re, -r25.im}; cp[2] = r39; cp[3] = r53; }
+            else { cp[0] = cscale(r11, p); cp[1] = cscale(r25, p); cp[2] = cscale(r39, p); cp[3] = cscale(r53, -p); }
+            cf avg = cscale(cadd(cadd(cadd(cp[0], cp[1]), cp[2]), cp[3]), 0.25f);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                int i = u ? iB : iA;
+                cf G;
+                if (i <= 11) G = cadd(cscale(avg, (float)(11 - i) / 11.0f), cscale(cp[0], (float)i / 11.0f));
+                else if (i <= 25) G = cadd(cscale(cp[0], (float)(25 - i) / 14.0f), cscale(cp[1], (float)(i - 11) / 14.0f));
+                else if (i <= 39) G = cadd(cscale(cp[1], (float)(39 - i) / 14.0f), cscale(cp[2], (float)(i - 25) / 14.0f));
+                else if (i <= 53) G = cadd(cscale(cp[2], (float)(53 - i) / 14.0f), cscale(cp[3], (float)(i - 39) / 14.0f));
+                else G = cadd(cscale(cp[3], (float)(64 - i) / 11.0f), cscale(avg, (float)(i - 53) / 11.0f));
+                if (u) b = cdiv(b, G); else a = cdiv(a, G);
+            }
+        }
+        if (n == 0) {
+            HA = a; HB = b;
+        } else if (n == 1) {
+            {
+                cf d = csub(HA, a), s = cadd(HA, a);
+                float md = sqrtf(d.re * d.re + d.im * d.im), ms = sqrtf(s.re * s.re + s.im * s.im);
+                s_md[wib][iA] = (double)md * (double)md; s_ms[wib][iA] = (double)ms * (double)ms;
+                if (usedA && !dcA) HA = cdiv(s, cf{ltsA * 2.0f, 0.f});
+                d = csub(HB, b); s = cadd(HB, b);
+                md = sqrtf(d.re * d.re + d.im * d.im); ms = sqrtf(s.re * s.re + s.im * s.im);
+                s_md[wib][iB] = (double)md * (double)md; s_ms[wib][iB] = (double)ms * (double)ms;
+                if (usedB) HB = cdiv(s, cf{ltsB * 2.0f, 0.f});
+            }
+            __syncwarp();
+            if (lane == 0) {
+                double signal = 0, noise = 0;
+                for (int i = 6; i <= 58; ++i) {
+                    if (i == 32) continue;
+                    noise += s_md[wib][i];
+                    signal += s_ms[wib][i];
+                }
+                snr = 10 * log10(signal / noise / 2);
+            }
+            __syncwarp();
+        } else {
+            cf symA = {0.f, 0.f}, symB = {0.f, 0.f};
+            int bitsA = 0, bitsB = 0;
+            cf huA = {0.f, 0.f}, huB = {0.f, 0.f};
+            if (carA >= 0) {
+                symA = cdiv(a, HA);
+                bitsA = dev_decide(nb, symA);
+                if (prm.algo == WIFI_EQ_LMS) {
+                    cf q = cdiv(a, c_tab.cons[enc][bitsA]);
+                    HA = cadd(cscale(HA, 0.5f), cscale(q, 0.5f));
+                } else if (prm.algo == WIFI_EQ_STA) huA = cdiv(a, c_tab.cons[enc][bitsA]);
+            } else if (iA == 39) huA = cscale(a, p);
+            else if (iA == 53) huA = cscale(a, -p);
+            if (carB >= 0) {
+                symB = cdiv(b, HB);
+                bitsB = dev_decide(nb, symB);
+                if (prm.algo == WIFI_EQ_LMS) {
+                    cf q = cdiv(b, c_tab.cons[enc][bitsB]);
+                    HB = cadd(cscale(HB, 0.5f), cscale(q, 0.5f));
+                } else if (prm.algo == WIFI_EQ_STA) huB = cdiv(b, c_tab.cons[enc][bitsB]);
+            } else if (iB == 11 || iB == 25) huB = cscale(b, p);
+            if (prm.algo == WIFI_EQ_STA) {
+                s_hu[wib][iA] = huA; s_hu[wib][iB] = huB;
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    int i = u ? iB : iA;
+                    if (i < 6 || i > 58 || i == 32) continue;
+                    cf sum = {0.f, 0.f};
+                    int cnt = 0;
+                    for (int k = i - 2; k <= i + 2; ++k) {
+                        if (k == 32 || k < 6 || k > 58) continue;
+                        sum = cadd(sum, s_hu[wib][k]);
+                        ++cnt;
+                    }
+                    cf avg = {sum.re / (float)cnt, sum.im / (float)cnt};
+                    if (u) HB = cadd(cscale(HB, 0.5f), cscale(avg, 0.5f));
+                    else HA = cadd(cscale(HA, 0.5f), cscale(avg, 0.5f));
+                }
+                __syncwarp();
+            }
+            if (n == 2) {
+                if (carA >= 0) st->sig_bits[carA] = (uint8_t)bitsA;
+                if (carB >= 0) st->sig_bits[carB] = (uint8_t)bitsB;
+            } else {
+                int64_t row = F.row_off + (n - 3);
+                if (carA >= 0) rows[row * 48 + carA] = (uint8_t)bitsA;
+                if (carB >= 0) rows[row * 48 + carB] = (uint8_t)bitsB;
+                if (prm.want_carrier) {
+                    if (carA >= 0) carrier[row * 48 + carA] = symA;
+                    if (carB >= 0) carrier[row * 48 + carB] = symB;
+                }
+                ++n_rows;
+            }
+        }
+    }
+    if (phase == 0) {
+        st->H[iA] = HA; st->H[iB] = HB;
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st->prev_pil[q] = pp[q];
+            st->d_er = d_er; st->eps0 = eps0; st->snr = snr;
+        }
+    } else if (lane == 0) {
+        frames[f].n_rows = n_rows;
+    }
+}
+
+// ------------------------------------------------------------------ R5f SIGNAL field
+// One thread per frame: deinterleave 48 hard bits, 62-step Viterbi (ntb 5), parse_signal.
+__global__ void __launch_bounds__(VIT_BLOCK) k_signal(wifi_b200_frame *frames, int n_frames, const EqState *states)
+{
+    __shared__ uint32_t ring[5 * 16 * VIT_BLOCK];
+    const int tid = threadIdx.x;
+    int f = blockIdx.x * VIT_BLOCK + tid;
+    if (f >= n_frames) return;
+    if (frames[f].n_syms < 3) return;
+    const EqState *st = states + f;
+    // 48 deinterleaved bits as 24 nibbles: step t uses deint[2t], deint[2t+1]; deint[i] = bits[(i%16)*3 + i/16]
+    uint64_t lo = 0, hi = 0;   // nibble t at bits 4t (t < 16 in lo, else hi)
+    for (int tstep = 0; tstep < 24; ++tstep) {
+        int i0 = 2 * tstep, i1 = i0 + 1;
+        uint32_t s0 = st->sig_bits[(i0 % 16) * 3 + i0 / 16] & 1u, s1 = st->sig_bits[(i1 % 16) * 3 + i1 / 16] & 1u;
+        uint64_t nib = s0 | (s1 << 2);
+        if (tstep < 16) lo |= nib << (4 * tstep); else hi |= nib << (4 * (tstep - 16));
+    }
+    VitCore v;
+    v.init();
+    uint32_t dec = 0;   // decoded bit i at bit i
+    int step = 0;
+    for (int chunk = 0; chunk < 8; ++chunk) {
+        int ns = chunk == 0 ? 6 : 8;
+        for (int k = 0; k < ns; ++k, ++step) {
+            uint32_t nib = step < 16 ? (uint32_t)(lo >> (4 * step)) & 0xfu : (step < 24 ? (uint32_t)(hi >> (4 * (step - 16))) & 0xfu : 0u);
+            v.step(nib);
+        }
+        uint32_t c = v.end_chunk(ring, (chunk + 1) % 5, 5, tid);
+        if (chunk >= 5) {
+            int m = chunk - 5;
+            dec |= (__brev(c) >> 24) << (8 * m);
+        }
+    }
+    int r = 0, len = 0;
+    bool parity = false;
+    for (int i = 0; i < 17; ++i) {
+        bool bit = (dec >> i) & 1u;
+        parity ^= bit;
+        if (i < 4 && bit) r |= 1 << i;
+        if (bit && i > 4) len |= 1 << (i - 5);
+    }
+    if (parity != (bool)((dec >> 17) & 1u)) return;
+    int enc;
+    switch (r) {
+    case 11: enc = 0; break;
+    case 15: enc = 1; break;
+    case 10: enc = 2; break;
+    case 14: enc = 3; break;
+    case 9: enc = 4; break;
+    case 13: enc = 5; break;
+    case 8: enc = 6; break;
+    case 12: enc = 7; break;
+    default: return;
+    }
+    int ndbps = c_tab.mcs[enc].n_dbps;
+    frames[f].sig_ok = 1;
+    frames[f].encoding = enc;
+    frames[f].length = len;
+    frames[f].frame_symbols = (16 + 8 * len + 6 + ndbps - 1) / ndbps;
+    frames[f].snr = st->snr;
+}
+
+// ------------------------------------------------------------------ R6 decode_mac planning
+// One thread per link, sequential over the link's frames (see oracle rx_link, decode_mac part).
+__global__ void k_plan(const LinkDesc *__restrict__ links, int n_links, wifi_b200_frame *frames, JobDesc *jobs, int *n_jobs, int *err)
+{
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_links) return;
+    const LinkDesc L = links[l];
+    int cur = -1, copied = 0, pending = -1, need = 0;
+    JobDesc J;
+    J.n_seg = 0;
+    bool bad = false;
+    for (int fi = L.frame_first; fi < L.frame_first + L.frame_count; ++fi) {
+        wifi_b200_frame F = frames[fi];
+        if (!F.sig_ok) continue;
+        if (F.n_rows == 0) {
+            if (pending < 0) pending = fi;
+            continue;
+        }
+        int tagf = pending >= 0 ? pending : fi;
+        pending = -1;
+        int t_sym = frames[tagf].frame_symbols, t_len = frames[tagf].length;
+        if (t_sym <= WIFI_MAX_SYM && t_len <= WIFI_MAX_PSDU) {
+            frames[tagf].accepted = 1;
+            cur = tagf;
+            copied = 0;
+            need = t_sym;
+            J.frame = tagf; J.enc = frames[tagf].encoding; J.len = t_len; J.n_sym = t_sym; J.n_seg = 0; J.pad = 0;
+            bad = false;
+        }
+        if (cur < 0 || copied >= need) continue;
+        int take = F.n_rows < need - copied ? F.n_rows : need - copied;
+        if (J.n_seg < 4) {
+            J.seg_row[J.n_seg] = (int32_t)F.row_off;
+            J.seg_cnt[J.n_seg] = take;
+            J.n_seg++;
+        } else {
+            bad = true;
+        }
+        copied += take;
+        if (copied == need) {
+            if (bad) { atomicExch(err, WIFI_E_OVERFLOW); continue; }
+            int j = atomicAdd(n_jobs, 1);
+            for (int s = J.n_seg; s < 4; ++s) { J.seg_row[s] = 0; J.seg_cnt[s] = 0; }
+            jobs[j] = J;
+            frames[cur].decoded = 1;
+            frames[cur].psdu_off = (int64_t)j * PSDU_STRIDE;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ R6 unpack/deinterleave/depuncture
+// depunct_lut[enc][q] for q in [0, 2*n_dbps): 0xffff = erasure, else (carrier << 3) | bit
+__global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ rows,
+                                               const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in)
+{
+    // grid.x over (group, word): blockDim = (32 lanes, 8 words)
+    const int lane = threadIdx.x, group = blockIdx.y;
+    const int w = blockIdx.x * blockDim.y + threadIdx.y;
+    const int job = group * 32 + lane;
+    if (job >= n_jobs) return;
+    const JobDesc J = jobs[job];
+    const int ntb = c_tab.mcs[J.enc].punct == 0 ? 5 : (c_tab.mcs[J.enc].punct == 1 ? 9 : 10);
+    const int n_words = J.len + 2 + ntb;   // trellis words the decoder reads
+    if (w >= n_words) return;
+    const int ndbps = c_tab.mcs[J.enc].n_dbps;
+    const int per = 2 * ndbps;
+    const int n_data = J.n_sym * ndbps;
+    const uint16_t *lut = depunct_lut + J.enc * 432;
+    int tstep = 8 * w;
+    int q = 2 * tstep;
+    int s = q / per, qi = q - s * per;
+    // row of symbol s
+    int seg = 0, sbase = 0;
+    while (seg < J.n_seg - 1 && s >= sbase + J.seg_cnt[seg]) { sbase += J.seg_cnt[seg]; ++seg; }
+    const uint8_t *rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        uint32_t sym = 0;
+        if (tstep + (k >> 1) < n_data) {
+            uint16_t e = lut[qi];
+            sym = (e == 0xffffu) ? 2u : ((rp[e >> 3] >> (e & 7)) & 1u);
+        }
+        word |= sym << (2 * k);
+        if (++qi == per) {
+            qi = 0;
+            ++s;
+            if (s - sbase >= J.seg_cnt[seg] && seg < J.n_seg - 1) { sbase += J.seg_cnt[seg]; ++seg; }
+            rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
+        }
+    }
+    vit_in[((int64_t)group * VIT_MAXW + w) * 32 + lane] = word;
+}
+
+// ------------------------------------------------------------------ R6a-c Viterbi + descramble + CRC
+__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict__ jobs, int n_jobs, const uint32_t *__restrict__ vit_in,
+                                                        uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
+{
+    extern __shared__ uint32_t vsm[];
+    uint32_t *ring = vsm;                                   // VIT_NTB_MAX*16*VIT_BLOCK words
+    uint32_t *s_crc = vsm + VIT_NTB_MAX * 16 * VIT_BLOCK;   // 256
+    uint16_t *s_scr = (uint16_t *)(s_crc + 256);            // 128
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += VIT_BLOCK) s_crc[i] = c_tab.crc_tab[i];
+    for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
+    __syncthreads();
+    const int job = blockIdx.x * VIT_BLOCK + tid;
+    if (job >= n_jobs) return;
+    const JobDesc J = jobs[job];
+    const int ntb = c_tab.mcs[J.enc].punct == 0 ? 5 : (c_tab.mcs[J.enc].punct == 1 ? 9 : 10);
+    const uint32_t *in = vit_in + ((int64_t)(job >> 5) * VIT_MAXW) * 32 + (job & 31);
+    uint32_t *out = psdu + (int64_t)job * (PSDU_STRIDE / 4);
+    const int L = J.len;
+    const int last_chunk = L + 1 + ntb;   // chunk whose traceback yields PSDU byte L-1
+    VitCore v;
+    v.init();
+    uint32_t prev = in[0];
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) v.step((prev >> (4 * k)) & 0xfu);
+    int slot = 1 % ntb;
+    v.end_chunk(ring, slot, ntb, tid);
+    uint32_t state = 0, crc = 0xffffffffu, accw = 0;
+    uint32_t next = in[32];
+#pragma unroll 1
+    for (int chunk = 1; chunk <= last_chunk; ++chunk) {
+        uint32_t bits = __funnelshift_r(prev, next, 24);
+        prev = next;
+        next = (chunk + 1 <= last_chunk) ? in[(int64_t)(chunk + 1) * 32] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.step((bits >> (4 * k)) & 0xfu);
+        slot = (slot + 1 == ntb) ? 0 : slot + 1;
+        uint32_t c = v.end_chunk(ring, slot, ntb, tid);
+        if (chunk >= ntb) {
+            int m = chunk - ntb;   // decoded byte index
+            if (m == 0) {
+                // descramble(): state from the first 7 decoded bits, bit 7 is the first data bit
+                state = c >> 1;
+                uint32_t fb = ((state >> 6) ^ (state >> 3)) & 1u;
+                state = ((state << 1) & 0x7eu) | fb;
+            } else {
+                uint32_t tabv = s_scr[state];
+                uint32_t byte = (__brev(c) >> 24) ^ (tabv & 0xffu);
+                state = tabv >> 8;
+                int pidx = m - 2;
+                if (pidx >= 0) {
+                    crc = s_crc[(crc ^ byte) & 0xffu] ^ (crc >> 8);
+                    accw |= byte << (8 * (pidx & 3));
+                    if ((pidx & 3) == 3 || pidx == L - 1) { out[pidx >> 2] = accw; accw = 0; }
+                }
+            }
+        }
+    }
+    frames[J.frame].crc_ok = ((crc ^ 0xffffffffu) == 558161692u) ? 1 : 0;
+}

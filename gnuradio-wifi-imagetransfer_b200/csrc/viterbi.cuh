@@ -1,0 +1,131 @@
+// viterbi.cuh -- K=7 (133,171) hard-decision Viterbi decoder, one trellis per thread.
+//
+// Restates [UPSTREAM] gr-ieee802-11 lib/viterbi_decoder/{base,viterbi_decoder_generic}.cc
+// (instance wifi_phy_hier.grc:533-549 decode_mac, and :550-569 frame_equalizer for SIGNAL):
+// 8-bit agreement metrics, tie -> predecessor k+32, per-state 8-bit path registers, a
+// traceback over `ntb` stored path snapshots every 8 trellis steps (first after 6).
+//
+// B200 mapping: the 64 path metrics of one frame live in 16 registers (4 states per
+// register, one byte each) and the 64 path registers in 16 more, so an add-compare-select
+// for 4 butterflies is a handful of 32-bit integer ops: IADD for the four candidate
+// metrics, one IADD3 + one PRMT (sign-replicate) for the byte-wise "m0 > m1" masks, LOP3
+// for the selects and PRMT for the state interleave.  Metrics never exceed 12+16 (spread
+// bound of the code + growth over one 8-step chunk), so bytes cannot carry into each
+// other.  Path snapshots go to shared memory, word-interleaved across the block's
+// threads (bank = thread id, conflict free).
+#pragma once
+#include "wifi_common.cuh"
+
+#define VIT_BLOCK 64
+#define VIT_NTB_MAX 10
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// branch selector for butterfly word j: byte b <- T byte (2*A_k + B_k), k = 4j + b
+__host__ __device__ constexpr uint32_t vit_par(uint32_t v) { return (v ^ (v >> 1) ^ (v >> 2) ^ (v >> 3) ^ (v >> 4) ^ (v >> 5) ^ (v >> 6)) & 1u; }
+__host__ __device__ constexpr uint32_t vit_sel(int j)
+{
+    uint32_t s = 0;
+    for (int b = 0; b < 4; ++b) {
+        uint32_t k = 4 * j + b;
+        uint32_t A = vit_par((2 * k) & 0x6d), B = vit_par((2 * k) & 0x4f);
+        s |= (2 * A + B) << (4 * b);
+    }
+    return s;
+}
+
+struct VitCore {
+    uint32_t M[16], P[16];
+
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { M[i] = 0; P[i] = 0; }
+    }
+
+    // one trellis step; nib = s0 | s1 << 2 with s in {0,1,2 = erasure}
+    __device__ __forceinline__ void step(uint32_t nib)
+    {
+        const uint32_t s0 = nib & 3u, s1 = (nib >> 2) & 3u;
+        const uint32_t t0 = (s0 == 2u) ? 0u : (s0 ? 0x00000101u : 0x01010000u);
+        const uint32_t t1 = (s1 == 2u) ? 0u : (s1 ? 0x00010001u : 0x01000100u);
+        const uint32_t T = t0 + t1;                                     // disagreements per (A,B)
+        const uint32_t E = ((s0 != 2u) ? 0x01010101u : 0u) + ((s1 != 2u) ? 0x01010101u : 0u);
+        const uint32_t T2 = E - T;                                      // agreements per (A,B)
+        uint32_t Mn[16], Pn[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t sel = vit_sel(j);
+            const uint32_t svm = prmt(T, 0u, sel), sv = prmt(T2, 0u, sel);
+            const uint32_t lo = M[j], hi = M[j + 8];
+            const uint32_t m0 = lo + sv, m1 = hi + svm, m2 = lo + svm, m3 = hi + sv;
+            const uint32_t k0 = prmt(m0 + 0x7f7f7f7fu - m1, 0u, 0xba98u); // 0xff where m0 > m1
+            const uint32_t k1 = prmt(m2 + 0x7f7f7f7fu - m3, 0u, 0xba98u);
+            const uint32_t v0 = (m0 & k0) | (m1 & ~k0);
+            const uint32_t v1 = (m2 & k1) | (m3 & ~k1);
+            const uint32_t sh0 = P[j] << 1, sh1 = (P[j + 8] << 1) | 0x01010101u;
+            const uint32_t q0 = (sh0 & k0) | (sh1 & ~k0);
+            const uint32_t q1 = (sh0 & k1) | (sh1 & ~k1);
+            Mn[2 * j] = prmt(v0, v1, 0x5140u);
+            Mn[2 * j + 1] = prmt(v0, v1, 0x7362u);
+            Pn[2 * j] = prmt(q0, q1, 0x5140u);
+            Pn[2 * j + 1] = prmt(q0, q1, 0x7362u);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { M[i] = Mn[i]; P[i] = Pn[i]; }
+    }
+
+    // byte-wise unsigned max / min of packed words (bytes < 0x80)
+    static __device__ __forceinline__ uint32_t vmax4(uint32_t a, uint32_t b)
+    {
+        uint32_t k = prmt((a | 0x80808080u) - b, 0u, 0xba98u); // 0xff where a >= b
+        return (a & k) | (b & ~k);
+    }
+    static __device__ __forceinline__ uint32_t vmin4(uint32_t a, uint32_t b)
+    {
+        uint32_t k = prmt((a | 0x80808080u) - b, 0u, 0xba98u);
+        return (b & k) | (a & ~k);
+    }
+
+    // viterbi_get_output_generic: snapshot the paths into ring slot `slot`, find the first
+    // best state, trace back ntb-1 snapshots, return that snapshot's path byte, renormalise
+    // the metrics by their minimum and clear the path registers.
+    __device__ __forceinline__ uint32_t end_chunk(uint32_t *ring, int slot, int ntb, int tid)
+    {
+#pragma unroll
+        for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = P[w];
+        uint32_t mx = M[0], mn = M[0];
+#pragma unroll
+        for (int w = 1; w < 16; ++w) { mx = vmax4(mx, M[w]); mn = vmin4(mn, M[w]); }
+        mx = vmax4(mx, mx >> 16); mx = vmax4(mx, mx >> 8);
+        mn = vmin4(mn, mn >> 16); mn = vmin4(mn, mn >> 8);
+        const uint32_t bestw = (mx & 0xffu) * 0x01010101u;
+        const uint32_t minw = (mn & 0xffu) * 0x01010101u;
+        // first state whose metric equals the maximum
+        int wsel = 0;
+        uint32_t zsel = 0;
+#pragma unroll
+        for (int w = 15; w >= 0; --w) {
+            uint32_t x = M[w] ^ bestw;
+            uint32_t z = ((x + 0x7f7f7f7fu) & 0x80808080u) ^ 0x80808080u; // bit7 set where equal
+            if (z) { wsel = w; zsel = z; }
+        }
+        int bs = wsel * 4 + ((__ffs((int)zsel) - 8) >> 3);
+        int sl = slot;
+        for (int i = 0; i < ntb - 1; ++i) {
+            uint32_t w = ring[(sl * 16 + (bs >> 2)) * VIT_BLOCK + tid];
+            bs = (int)((w >> (8 * (bs & 3))) & 0xffu) >> 2;
+            sl = (sl == 0) ? ntb - 1 : sl - 1;
+        }
+        uint32_t w = ring[(sl * 16 + (bs >> 2)) * VIT_BLOCK + tid];
+        uint32_t c = (w >> (8 * (bs & 3))) & 0xffu;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { M[i] -= minw; P[i] = 0; }
+        return c;
+    }
+};

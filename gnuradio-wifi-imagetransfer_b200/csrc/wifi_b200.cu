@@ -1,0 +1,882 @@
+// wifi_b200.cu -- host side of libwifi_b200.so: handle, workspace, C ABI (include/wifi_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -shared -Xcompiler -fPIC
+// No CPU fallback anywhere in this file: every entry point that computes launches CUDA kernels.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "rx_kernels.cuh"
+#include "tx_kernels.cuh"
+
+
+namespace {
+
+const McsDesc H_MCS[8] = {
+    {1, 48, 24, 0x0D, 0}, {1, 48, 36, 0x0F, 2}, {2, 96, 48, 0x05, 0}, {2, 96, 72, 0x07, 2},
+    {4, 192, 96, 0x09, 0}, {4, 192, 144, 0x0B, 2}, {6, 288, 192, 0x01, 1}, {6, 288, 216, 0x03, 2},
+};
+const int H_LTS53[53] = {1, 1, -1, -1, 1, 1, -1, 1, -1, 1, 1, 1, 1, 1, 1, -1, -1, 1, 1, -1, 1, -1, 1, 1, 1, 1, 0,
+                         1, -1, -1, 1, 1, -1, 1, -1, 1, -1, -1, -1, -1, -1, 1, 1, -1, -1, 1, -1, 1, -1, 1, 1, 1, 1};
+
+inline int h_n_sym(int enc, int len) { return (16 + 8 * len + 6 + H_MCS[enc].n_dbps - 1) / H_MCS[enc].n_dbps; }
+
+uint32_t h_crc_tab[256];
+void h_crc_init()
+{
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+        h_crc_tab[i] = c;
+    }
+}
+uint32_t h_crc32(const uint8_t *p, int n)
+{
+    if (!h_crc_tab[1]) h_crc_init();
+    uint32_t c = 0xffffffffu;
+    for (int i = 0; i < n; ++i) c = h_crc_tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+    return c ^ 0xffffffffu;
+}
+
+// Tables are generated from the formulas of the standard / upstream sources, never copied:
+// see the matching generator in oracle/wifi_oracle.cpp and tests/test_tables.py.
+void build_tables(DevTables &t, std::vector<uint16_t> &depunct)
+{
+    memset(&t, 0, sizeof t);
+    for (int k = -26; k <= 26; ++k) t.lts[k + 32] = (float)H_LTS53[k + 26];
+    int state = 0x7f;
+    for (int i = 0; i < 127; ++i) {
+        int fb = ((state >> 6) & 1) ^ ((state >> 3) & 1);
+        t.polarity[i] = fb ? -1.f : 1.f;
+        state = ((state << 1) & 0x7e) | fb;
+    }
+    for (int n = 0; n < 64; ++n) {
+        double re = 0, im = 0;
+        for (int k = -26; k <= 26; ++k) {
+            double ph = 2.0 * M_PI * k * n / 64.0;
+            re += H_LTS53[k + 26] * std::cos(ph);
+            im += H_LTS53[k + 26] * std::sin(ph);
+        }
+        re /= std::sqrt(52.0);
+        im /= std::sqrt(52.0);
+        t.long_taps[63 - n].re = (float)(std::round(re * 1e4) / 1e4);
+        t.long_taps[63 - n].im = (float)(std::round(-im * 1e4) / 1e4);
+    }
+    for (int k = 0; k < 32; ++k) {
+        t.tw[k].re = (float)std::cos(2.0 * M_PI * k / 64.0);
+        t.tw[k].im = (float)(-std::sin(2.0 * M_PI * k / 64.0));
+    }
+    t.tw[0] = {1.f, 0.f};
+    t.tw[16] = {0.f, -1.f};
+    t.win = (float)(1.0 / std::sqrt(52.0));
+    const float sv = (float)std::sqrt(13.0 / 6.0);
+    const int sts_k[12] = {-24, -20, -16, -12, -8, -4, 4, 8, 12, 16, 20, 24};
+    const int sts_s[12] = {1, -1, 1, -1, -1, 1, -1, -1, 1, 1, 1, 1};
+    for (int i = 0; i < 12; ++i) t.sts[sts_k[i] + 32] = {sts_s[i] * sv, sts_s[i] * sv};
+    for (int i = 0; i < 64; ++i) {
+        int k = i - 32, m = ((k % 4) + 4) % 4;
+        float v = t.lts[i];
+        t.lts_rot[i] = (m == 0) ? cf{v, 0.f} : (m == 1) ? cf{0.f, -v} : (m == 2) ? cf{-v, 0.f} : cf{0.f, v};
+    }
+    for (int e = 0; e < 8; ++e) {
+        t.mcs[e] = H_MCS[e];
+        int n_cbps = H_MCS[e].n_cbps, s = std::max(H_MCS[e].n_bpsc / 2, 1);
+        int first[288], second[288];
+        for (int j = 0; j < n_cbps; ++j) first[j] = s * (j / s) + ((j + (int)std::floor(16.0 * j / n_cbps)) % s);
+        for (int i = 0; i < n_cbps; ++i) second[i] = 16 * i - (n_cbps - 1) * (int)std::floor(16.0 * i / n_cbps);
+        for (int k = 0; k < n_cbps; ++k) {
+            t.P[e][k] = (uint16_t)second[first[k]];
+            t.Pinv[e][second[first[k]]] = (uint16_t)k;
+        }
+        int nb = H_MCS[e].n_bpsc;
+        for (int v = 0; v < (1 << nb); ++v) {
+            if (nb == 1) { t.cons[e][v] = {v ? 1.f : -1.f, 0.f}; continue; }
+            int h = nb / 2;
+            float level = (h == 1) ? sqrtf(0.5f) : (h == 2) ? sqrtf(0.1f) : sqrtf(1.0f / 42.0f);
+            auto axis = [&](int bits) -> float {
+                int b0 = bits & 1, b1 = (bits >> 1) & 1, b2 = (bits >> 2) & 1, mag;
+                if (h == 1) mag = 1;
+                else if (h == 2) mag = b1 ? 1 : 3;
+                else mag = b1 ? (b2 ? 3 : 1) : (b2 ? 5 : 7);
+                return (float)(b0 ? mag : -mag) * level;
+            };
+            t.cons[e][v] = {axis(v & ((1 << h) - 1)), axis(v >> h)};
+        }
+    }
+    h_crc_init();
+    memcpy(t.crc_tab, h_crc_tab, sizeof h_crc_tab);
+    for (int s0 = 0; s0 < 128; ++s0) {
+        int st = s0, fbits = 0;
+        for (int i = 0; i < 8; ++i) {
+            int fb = ((st >> 6) & 1) ^ ((st >> 3) & 1);
+            fbits |= fb << i;
+            st = ((st << 1) & 0x7e) | fb;
+        }
+        t.scr_tab[s0] = (uint16_t)(fbits | (st << 8));
+    }
+    int c = 0;
+    for (int i = 0; i < 64; ++i) {
+        if (i < 6 || i > 58 || i == 32 || i == 11 || i == 25 || i == 39 || i == 53) t.carrier_of[i] = -1;
+        else t.carrier_of[i] = (int8_t)c++;
+    }
+    // depuncture + deinterleave + bit-unpack lookup, per symbol: position q of the rate-1/2
+    // stream -> (carrier << 3 | bit) of the equalizer's 48-byte row, or 0xffff for an erasure
+    depunct.assign(8 * 432, 0xffff);
+    for (int e = 0; e < 8; ++e) {
+        const McsDesc &m = H_MCS[e];
+        int per = 2 * m.n_dbps, cb = 0;
+        for (int q = 0; q < per; ++q) {
+            bool keep = true;
+            if (m.punct == 1) keep = (q % 4) != 3;
+            else if (m.punct == 2) keep = !((q % 6) == 3 || (q % 6) == 4);
+            if (!keep) continue;
+            int k = t.Pinv[e][cb];    // deint[d] = bits[Pinv[d]]
+            depunct[e * 432 + q] = (uint16_t)(((k / m.n_bpsc) << 3) | (k % m.n_bpsc));
+            ++cb;
+        }
+    }
+}
+
+enum { ST_H2D = 0, ST_DETECT, ST_SELECT, ST_SYNC_LONG, ST_DEMOD_HEAD, ST_SIGNAL, ST_DEMOD_DATA, ST_PLAN, ST_PACK, ST_VITERBI, ST_D2H, ST_COUNT };
+const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "demod_head", "signal", "demod_data", "plan", "pack", "viterbi", "d2h"};
+
+#define MAX_LINKS 65536
+
+} // namespace
+
+struct wifi_b200 {
+    wifi_b200_cfg cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    // device workspace
+    cf *d_iq = nullptr;            // staging for host input (max_samples + history)
+    uint32_t *d_flags = nullptr;
+    LinkDesc *d_links = nullptr;
+    wifi_b200_frame *d_frames = nullptr;
+    EqState *d_states = nullptr;
+    uint8_t *d_rows = nullptr;
+    cf *d_carrier = nullptr;
+    JobDesc *d_jobs = nullptr;
+    uint32_t *d_vit_in = nullptr;
+    uint32_t *d_psdu = nullptr;
+    uint16_t *d_depunct = nullptr;
+    int *d_counters = nullptr;     // [0] frames [1] jobs [2] err ; +8 bytes: row counter (u64)
+    int *h_counters = nullptr;     // pinned mirror
+    int64_t row_cap = 0;
+    // tx workspace
+    uint8_t *d_txblob = nullptr;
+    TxFrameDesc *d_txdesc = nullptr;
+    uint8_t *d_txsym = nullptr;
+    cf *d_txiq = nullptr;
+    size_t txblob_cap = 0, txiq_cap = 0, txsym_cap = 0;
+    int64_t tx_sym_bytes = 0;
+    int tx_seed = 1;               // [UPSTREAM] mapper.cc d_scrambler: 1, ++ per frame, wraps after 127
+    wifi_b200_chan_seg *d_segs = nullptr;
+    int segs_cap = 0;
+    // last rx call
+    const cf *cur_iq = nullptr;
+    std::vector<LinkDesc> h_links;
+    int64_t n_frames = 0, n_jobs = 0, n_rows = 0, n_samples = 0, n_triggers = 0;
+    bool host_mirror = false;      // frames/psdu already copied to host
+    wifi_b200_frame *h_frames = nullptr;   // pinned
+    uint8_t *h_psdu = nullptr;             // pinned
+    float *h_iq = nullptr;                 // pinned staging for host input
+    cudaEvent_t ev[ST_COUNT + 1];
+    bool ev_used[ST_COUNT + 1];
+    float stage_ms[ST_COUNT];
+    wifi_b200_stats stats;
+    // streaming
+    std::vector<float> sbuf;       // pending samples (interleaved), sbuf[0] is absolute index s_abs0 - s_hist
+    int64_t s_abs0 = 0;            // absolute index of the first non-history sample in sbuf
+    int s_hist = 0;
+    int64_t s_prev_trigger = -1;   // absolute
+    float s_fo_carry = 0.f;
+    std::vector<wifi_b200_frame> s_meta;
+    std::vector<uint8_t> s_bytes;
+};
+
+namespace {
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return WIFI_E_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+
+std::mutex g_tab_mu;
+bool g_tab_done[64];
+
+int upload_tables(wifi_b200 *h)
+{
+    std::lock_guard<std::mutex> g(g_tab_mu);
+    static DevTables t;
+    static std::vector<uint16_t> dep;
+    if (dep.empty()) build_tables(t, dep);
+    if (!g_tab_done[h->device & 63]) {
+        CK(cudaMemcpyToSymbol(c_tab, &t, sizeof t));
+        g_tab_done[h->device & 63] = true;
+    }
+    CK(cudaMalloc(&h->d_depunct, dep.size() * sizeof(uint16_t)));
+    CK(cudaMemcpy(h->d_depunct, dep.data(), dep.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return WIFI_OK;
+}
+
+void free_all(wifi_b200 *h)
+{
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
+                    h->d_psdu, h->d_depunct, h->d_counters, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->h_frames) cudaFreeHost(h->h_frames);
+    if (h->h_psdu) cudaFreeHost(h->h_psdu);
+    if (h->h_iq) cudaFreeHost(h->h_iq);
+    for (int i = 0; i <= ST_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+int ensure_iq_staging(wifi_b200 *h)
+{
+    if (!h->d_iq) CK(cudaMalloc(&h->d_iq, (size_t)(h->cfg.max_samples + 512) * sizeof(cf)));
+    return WIFI_OK;
+}
+
+void mark(wifi_b200 *h, int i)
+{
+    cudaEventRecord(h->ev[i], h->stream);
+    h->ev_used[i] = true;
+}
+
+// the receive pipeline over device-resident samples; links already in h->h_links
+int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming: newest burst not complete yet */)
+{
+    const int n_links = (int)h->h_links.size();
+    int64_t total_chunks = 0, total = 0;
+    for (auto &L : h->h_links) {
+        L.chunk_base = total_chunks;
+        total_chunks += (L.len + FE_CHUNK - 1) / FE_CHUNK;
+        total += L.len;
+    }
+    h->cur_iq = iq;
+    h->n_frames = h->n_jobs = h->n_rows = 0;
+    h->n_samples = total;
+    h->host_mirror = false;
+    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
+    memset(h->stage_ms, 0, sizeof h->stage_ms);
+    const double thr = h->cfg.sensitivity;
+    float thr_f = (float)thr;   // (double)c > thr  <=>  c > largest float <= thr
+    if ((double)thr_f > thr) thr_f = nextafterf(thr_f, -INFINITY);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->d_links, h->h_links.data(), n_links * sizeof(LinkDesc), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->d_counters, 0, 64, s));
+    mark(h, ST_DETECT);
+    if (total_chunks > 0)
+        k_detect<<<(unsigned)((total_chunks + 127) / 128), 128, 0, s>>>(iq, h->d_links, n_links, total_chunks, thr_f, h->d_flags);
+    mark(h, ST_SELECT);
+    k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_links, n_links, h->d_frames, h->d_counters,
+                                                        (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
+                                                        h->cfg.min_plateau, h->d_counters + 2);
+    mark(h, ST_SYNC_LONG);
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->h_counters[2] != 0 || h->h_counters[0] > h->cfg.max_frames) {
+        h->err = "more sync_short triggers than max_frames";
+        return WIFI_E_OVERFLOW;
+    }
+    int64_t nf = h->h_counters[0];
+    int64_t rows_needed = *(int64_t *)(h->h_counters + 8);
+    if (rows_needed > h->row_cap) {
+        h->err = "row capacity exceeded";
+        return WIFI_E_OVERFLOW;
+    }
+    h->n_triggers = nf;
+    if (hold_last && nf > 0) {
+        // streaming: the newest burst is not complete yet; single link
+        nf = nf - 1;
+        h->h_links[0].frame_first = 0;
+        h->h_links[0].frame_count = (int)nf;
+        LinkDesc tmp;
+        CK(cudaMemcpy(&tmp, h->d_links, sizeof tmp, cudaMemcpyDeviceToHost));
+        tmp.frame_count = (int)nf;
+        CK(cudaMemcpyAsync(h->d_links, &tmp, sizeof tmp, cudaMemcpyHostToDevice, s));
+    }
+    h->n_frames = nf;
+    h->n_rows = rows_needed;
+    if (nf > 0) {
+        DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier};
+        k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf);
+        mark(h, ST_DEMOD_HEAD);
+        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 0);
+        mark(h, ST_SIGNAL);
+        k_signal<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, 0, s>>>(h->d_frames, (int)nf, h->d_states);
+        mark(h, ST_DEMOD_DATA);
+        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1);
+        mark(h, ST_PLAN);
+        k_plan<<<(n_links + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_counters + 1, h->d_counters + 2);
+        mark(h, ST_PACK);
+        CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h->h_counters[2] != 0) {
+            h->err = "decode_mac symbol collection spans more than 4 bursts";
+            return WIFI_E_OVERFLOW;
+        }
+        int64_t nj = h->h_counters[1];
+        h->n_jobs = nj;
+        if (nj > 0) {
+            int groups = (int)((nj + 31) / 32);
+            dim3 pb(32, 8), pg((WIFI_MAX_PSDU + 2 + VIT_NTB_MAX + 7) / 8, groups);
+            k_pack<<<pg, pb, 0, s>>>(h->d_jobs, (int)nj, h->d_rows, h->d_depunct, h->d_vit_in);
+            mark(h, ST_VITERBI);
+            size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256;
+            k_viterbi<<<(unsigned)((nj + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nj, h->d_vit_in, h->d_psdu, h->d_frames);
+        }
+    }
+    mark(h, ST_D2H);
+    if (mirror && h->n_triggers > 0) {
+        CK(cudaMemcpyAsync(h->h_frames, h->d_frames, h->n_triggers * sizeof(wifi_b200_frame), cudaMemcpyDeviceToHost, s));
+        if (h->n_jobs > 0) CK(cudaMemcpyAsync(h->h_psdu, h->d_psdu, (size_t)h->n_jobs * PSDU_STRIDE, cudaMemcpyDeviceToHost, s));
+    }
+    mark(h, ST_COUNT);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    h->host_mirror = mirror;
+    // stage times: difference between consecutive recorded events
+    int prev = -1;
+    for (int i = 0; i <= ST_COUNT; ++i) {
+        if (!h->ev_used[i]) continue;
+        if (prev >= 0) cudaEventElapsedTime(&h->stage_ms[prev], h->ev[prev], h->ev[i]);
+        prev = i;
+    }
+    return WIFI_OK;
+}
+
+int fetch_frames(wifi_b200 *h)
+{
+    if (h->host_mirror || h->n_frames == 0) return WIFI_OK;
+    CK(cudaMemcpyAsync(h->h_frames, h->d_frames, h->n_frames * sizeof(wifi_b200_frame), cudaMemcpyDeviceToHost, h->stream));
+    if (h->n_jobs > 0) CK(cudaMemcpyAsync(h->h_psdu, h->d_psdu, (size_t)h->n_jobs * PSDU_STRIDE, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->host_mirror = true;
+    return WIFI_OK;
+}
+
+void update_stats(wifi_b200 *h)
+{
+    h->stats.samples += h->n_samples;
+    h->stats.frames_detected += h->n_frames;
+    for (int64_t i = 0; i < h->n_frames; ++i) {
+        const wifi_b200_frame &f = h->h_frames[i];
+        h->stats.signal_ok += f.sig_ok;
+        h->stats.decoded += f.decoded;
+        if (f.crc_ok) {
+            h->stats.crc_ok++;
+            h->stats.pdu_bytes += f.length - 4;
+            h->stats.per_mcs_crc_ok[f.encoding & 7]++;
+        }
+    }
+}
+
+int set_links(wifi_b200 *h, const uint64_t *link_off, int n_links, int final)
+{
+    if (!link_off || n_links <= 0 || n_links > MAX_LINKS) { h->err = "bad link table"; return WIFI_E_ARG; }
+    int64_t total = (int64_t)(link_off[n_links] - link_off[0]);
+    if (total > h->cfg.max_samples) { h->err = "more samples than max_samples"; return WIFI_E_OVERFLOW; }
+    h->h_links.resize(n_links);
+    for (int l = 0; l < n_links; ++l) {
+        LinkDesc &L = h->h_links[l];
+        memset(&L, 0, sizeof L);
+        if (link_off[l + 1] < link_off[l]) { h->err = "link offsets not ascending"; return WIFI_E_ARG; }
+        L.x_off = (int64_t)link_off[l];
+        L.len = (int64_t)(link_off[l + 1] - link_off[l]);
+        L.is_final = final ? 1 : 0;
+    }
+    return WIFI_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int wifi_b200_abi_version(void) { return WIFI_B200_ABI_VERSION; }
+
+int wifi_b200_device_count(void)
+{
+    int n = 0, ok = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+const char *wifi_b200_strerror(int code)
+{
+    switch (code) {
+    case WIFI_OK: return "ok";
+    case WIFI_E_ARG: return "bad argument";
+    case WIFI_E_TOO_LARGE: return "PSDU too large (max 1528 bytes / 511 symbols)";
+    case WIFI_E_CUDA: return "CUDA error";
+    case WIFI_E_NOMEM: return "out of memory";
+    case WIFI_E_OVERFLOW: return "capacity exceeded";
+    case WIFI_E_NODEVICE: return "no sm_100 device";
+    default: return "unknown";
+    }
+}
+
+int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
+{
+    if (!cfg_in || !out) return WIFI_E_ARG;
+    *out = nullptr;
+    wifi_b200_cfg cfg = *cfg_in;
+    if (cfg.bandwidth <= 0) cfg.bandwidth = 10e6;
+    if (cfg.frequency <= 0) cfg.frequency = 5.89e9;
+    if (cfg.sensitivity <= 0) cfg.sensitivity = 0.56;
+    if (cfg.min_plateau <= 0) cfg.min_plateau = 2;
+    if (cfg.max_samples <= 0) cfg.max_samples = 1 << 22;
+    if (cfg.max_frames <= 0) cfg.max_frames = cfg.max_samples / 1000 + 64;
+    if (cfg.chan_est < 0 || cfg.chan_est > 3 || cfg.encoding < 0 || cfg.encoding > 7 || cfg.min_plateau > 16) return WIFI_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg.device < 0 || cfg.device >= ndev) return WIFI_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg.device) != cudaSuccess || prop.major != 10) return WIFI_E_NODEVICE;
+    wifi_b200 *h = new wifi_b200;
+    h->cfg = cfg;
+    h->device = cfg.device;
+    memset(h->ev, 0, sizeof h->ev);
+    memset(&h->stats, 0, sizeof h->stats);
+    memset(h->stage_ms, 0, sizeof h->stage_ms);
+    auto fail = [&](int code) { free_all(h); delete h; return code; };
+    if (cudaSetDevice(h->device) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
+    for (int i = 0; i <= ST_COUNT; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (upload_tables(h) != WIFI_OK) return fail(WIFI_E_CUDA);
+    const int64_t S = cfg.max_samples, Fm = cfg.max_frames;
+    h->row_cap = S / 80 + Fm + 64;
+    bool ok = true;
+    auto A = [&](void **p, size_t bytes) { if (ok && cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) ok = false; };
+    A((void **)&h->d_flags, (size_t)(S / FE_CHUNK + MAX_LINKS + 1) * 16);
+    A((void **)&h->d_links, (size_t)MAX_LINKS * sizeof(LinkDesc));
+    A((void **)&h->d_frames, (size_t)Fm * sizeof(wifi_b200_frame));
+    A((void **)&h->d_states, (size_t)Fm * sizeof(EqState));
+    A((void **)&h->d_rows, (size_t)h->row_cap * 48);
+    if (cfg.want_carrier) A((void **)&h->d_carrier, (size_t)h->row_cap * 48 * sizeof(cf));
+    A((void **)&h->d_jobs, (size_t)Fm * sizeof(JobDesc));
+    A((void **)&h->d_vit_in, (size_t)((Fm + 31) / 32) * VIT_MAXW * 32 * 4);
+    A((void **)&h->d_psdu, (size_t)Fm * PSDU_STRIDE);
+    A((void **)&h->d_counters, 64);
+    if (!ok) return fail(WIFI_E_NOMEM);
+    if (cudaMallocHost(&h->h_counters, 64) != cudaSuccess) return fail(WIFI_E_NOMEM);
+    if (cudaMallocHost(&h->h_frames, (size_t)Fm * sizeof(wifi_b200_frame)) != cudaSuccess) return fail(WIFI_E_NOMEM);
+    if (cudaMallocHost(&h->h_psdu, (size_t)Fm * PSDU_STRIDE) != cudaSuccess) return fail(WIFI_E_NOMEM);
+    *out = h;
+    return WIFI_OK;
+}
+
+void wifi_b200_destroy(wifi_b200_t *h)
+{
+    if (!h) return;
+    free_all(h);
+    delete h;
+}
+
+int wifi_b200_set_param(wifi_b200_t *h, int id, double v)
+{
+    if (!h) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    switch (id) {
+    case WIFI_P_BANDWIDTH: if (v <= 0) return WIFI_E_ARG; h->cfg.bandwidth = v; break;
+    case WIFI_P_FREQUENCY: if (v <= 0) return WIFI_E_ARG; h->cfg.frequency = v; break;
+    case WIFI_P_SENSITIVITY: h->cfg.sensitivity = v; break;
+    case WIFI_P_CHAN_EST: if (v < 0 || v > 3) return WIFI_E_ARG; h->cfg.chan_est = (int)v; break;
+    case WIFI_P_ENCODING: if (v < 0 || v > 7) return WIFI_E_ARG; h->cfg.encoding = (int)v; break;
+    case WIFI_P_MIN_PLATEAU: if (v < 1 || v > 16) return WIFI_E_ARG; h->cfg.min_plateau = (int)v; break;
+    case WIFI_P_WANT_CARRIER:
+        if (v != 0 && !h->d_carrier) {
+            cudaSetDevice(h->device);
+            if (cudaMalloc(&h->d_carrier, (size_t)h->row_cap * 48 * sizeof(cf)) != cudaSuccess) return WIFI_E_NOMEM;
+        }
+        h->cfg.want_carrier = v != 0;
+        break;
+    default: return WIFI_E_ARG;
+    }
+    return WIFI_OK;
+}
+
+double wifi_b200_get_param(wifi_b200_t *h, int id)
+{
+    if (!h) return NAN;
+    std::lock_guard<std::mutex> g(h->mu);
+    switch (id) {
+    case WIFI_P_BANDWIDTH: return h->cfg.bandwidth;
+    case WIFI_P_FREQUENCY: return h->cfg.frequency;
+    case WIFI_P_SENSITIVITY: return h->cfg.sensitivity;
+    case WIFI_P_CHAN_EST: return h->cfg.chan_est;
+    case WIFI_P_ENCODING: return h->cfg.encoding;
+    case WIFI_P_MIN_PLATEAU: return h->cfg.min_plateau;
+    case WIFI_P_WANT_CARRIER: return h->cfg.want_carrier;
+    default: return NAN;
+    }
+}
+
+const char *wifi_b200_last_error(wifi_b200_t *h) { return h ? h->err.c_str() : "null handle"; }
+void *wifi_b200_stream(wifi_b200_t *h) { return h ? (void *)h->stream : nullptr; }
+int wifi_b200_sync(wifi_b200_t *h)
+{
+    if (!h) return WIFI_E_ARG;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    return WIFI_OK;
+}
+
+int wifi_b200_mac_frame(const uint8_t *payload, int n, int seq, const uint8_t src[6], const uint8_t dst[6], const uint8_t bss[6], uint8_t *o)
+{
+    // [UPSTREAM] mac.cc: fc 0x0008, duration 0, addr1 = dst, addr2 = src, addr3 = bss, seq_ctl = (seq & 0xfff) << 4, FCS
+    if (!payload && n > 0) return WIFI_E_ARG;
+    if (n < 0 || !o || !src || !dst || !bss) return WIFI_E_ARG;
+    if (n > 1500) return WIFI_E_TOO_LARGE;
+    o[0] = 0x08; o[1] = 0x00; o[2] = 0x00; o[3] = 0x00;
+    memcpy(o + 4, dst, 6);
+    memcpy(o + 10, src, 6);
+    memcpy(o + 16, bss, 6);
+    uint16_t sc = (uint16_t)((seq & 0xfff) << 4);
+    o[22] = sc & 0xff; o[23] = sc >> 8;
+    if (n) memcpy(o + 24, payload, n);
+    uint32_t c = h_crc32(o, 24 + n);
+    o[24 + n] = c & 0xff; o[25 + n] = (c >> 8) & 0xff; o[26 + n] = (c >> 16) & 0xff; o[27 + n] = (c >> 24) & 0xff;
+    return 28 + n;
+}
+
+int wifi_b200_n_sym(int enc, int len) { return (enc < 0 || enc > 7 || len < 0) ? WIFI_E_ARG : h_n_sym(enc, len); }
+int wifi_b200_frame_samples(int enc, int len) { return (enc < 0 || enc > 7 || len < 0) ? WIFI_E_ARG : 80 * (5 + h_n_sym(enc, len)) + 1; }
+
+static int64_t tx_common(wifi_b200_t *h, const uint8_t *blob, const uint32_t *off, const uint32_t *len, const uint8_t *enc,
+                         const uint8_t *seed, int n, float *iq_out, size_t cap, uint64_t *burst_off, bool out_is_dev)
+{
+    if (!h || !blob || !off || !len || n <= 0 || !iq_out) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (n > h->cfg.max_frames) { h->err = "more PSDUs than max_frames"; return WIFI_E_OVERFLOW; }
+    std::vector<TxFrameDesc> descs(n);
+    uint64_t pos = 0, spos = 0;
+    size_t blob_bytes = 0;
+    int seedc = h->tx_seed;
+    for (int i = 0; i < n; ++i) {
+        int e = enc ? enc[i] : h->cfg.encoding;
+        if (e < 0 || e > 7) { h->err = "bad encoding"; return WIFI_E_ARG; }
+        int ns = h_n_sym(e, (int)len[i]);
+        if (len[i] > WIFI_MAX_PSDU || ns > WIFI_MAX_SYM) { h->err = "PSDU too large"; return WIFI_E_TOO_LARGE; }
+        int sd;
+        if (seed) { sd = seed[i] & 0x7f; if (sd == 0) { h->err = "scrambler seed 0"; return WIFI_E_ARG; } }
+        else { sd = seedc; seedc = seedc >= 127 ? 1 : seedc + 1; }
+        descs[i] = {off[i], len[i], (uint32_t)e, (uint32_t)sd, pos, spos};
+        if (burst_off) burst_off[i] = pos;
+        pos += (uint64_t)(80 * (5 + ns) + 1);
+        spos += (uint64_t)ns * 48;
+        blob_bytes = std::max(blob_bytes, (size_t)off[i] + len[i]);
+    }
+    if (burst_off) burst_off[n] = pos;
+    if (pos > cap) { h->err = "iq_out too small"; return WIFI_E_OVERFLOW; }
+    if (!seed) h->tx_seed = seedc;
+    if (blob_bytes > h->txblob_cap) {
+        if (h->d_txblob) cudaFree(h->d_txblob);
+        h->d_txblob = nullptr;
+        CK(cudaMalloc(&h->d_txblob, blob_bytes + 1024));
+        h->txblob_cap = blob_bytes + 1024;
+    }
+    if (!h->d_txdesc) CK(cudaMalloc(&h->d_txdesc, (size_t)h->cfg.max_frames * sizeof(TxFrameDesc)));
+    if (spos > h->txsym_cap) {
+        if (h->d_txsym) cudaFree(h->d_txsym);
+        h->d_txsym = nullptr;
+        CK(cudaMalloc(&h->d_txsym, spos + 1024));
+        h->txsym_cap = spos + 1024;
+    }
+    cf *dst = (cf *)iq_out;
+    if (!out_is_dev) {
+        if (pos > h->txiq_cap) {
+            if (h->d_txiq) cudaFree(h->d_txiq);
+            h->d_txiq = nullptr;
+            CK(cudaMalloc(&h->d_txiq, (pos + 1024) * sizeof(cf)));
+            h->txiq_cap = pos + 1024;
+        }
+        dst = h->d_txiq;
+    }
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->d_txblob, blob, blob_bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_txdesc, descs.data(), n * sizeof(TxFrameDesc), cudaMemcpyHostToDevice, s));
+    k_tx<<<n, 128, 0, s>>>(h->d_txblob, h->d_txdesc, n, dst, h->d_txsym);
+    CK(cudaGetLastError());
+    if (!out_is_dev) CK(cudaMemcpyAsync(iq_out, dst, pos * sizeof(cf), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->tx_sym_bytes = (int64_t)spos;
+    return (int64_t)pos;
+}
+
+int64_t wifi_b200_tx(wifi_b200_t *h, const uint8_t *blob, const uint32_t *off, const uint32_t *len, const uint8_t *enc,
+                     const uint8_t *seed, int n, float *iq_out, size_t cap, uint64_t *burst_off)
+{
+    return tx_common(h, blob, off, len, enc, seed, n, iq_out, cap, burst_off, false);
+}
+int64_t wifi_b200_tx_dev(wifi_b200_t *h, const uint8_t *blob, const uint32_t *off, const uint32_t *len, const uint8_t *enc,
+                         const uint8_t *seed, int n, float *iq_out_dev, size_t cap, uint64_t *burst_off)
+{
+    return tx_common(h, blob, off, len, enc, seed, n, iq_out_dev, cap, burst_off, true);
+}
+int64_t wifi_b200_tx_symbols(wifi_b200_t *h, uint8_t *out, size_t cap)
+{
+    if (!h || !out) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if ((size_t)h->tx_sym_bytes > cap) return WIFI_E_OVERFLOW;
+    if (h->tx_sym_bytes) CK(cudaMemcpy(out, h->d_txsym, h->tx_sym_bytes, cudaMemcpyDeviceToHost));
+    return h->tx_sym_bytes;
+}
+
+int wifi_b200_channel_dev(wifi_b200_t *h, const float *in_dev, float *out_dev, const wifi_b200_chan_seg *segs, int n_segs)
+{
+    if (!h || !in_dev || !out_dev || !segs || n_segs <= 0) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    int64_t maxn = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        if (segs[i].n_taps < 0 || segs[i].n_taps > 8 || segs[i].n < 0) { h->err = "bad channel segment"; return WIFI_E_ARG; }
+        maxn = std::max(maxn, segs[i].n);
+    }
+    if (n_segs > h->segs_cap) {
+        if (h->d_segs) cudaFree(h->d_segs);
+        h->d_segs = nullptr;
+        CK(cudaMalloc(&h->d_segs, (size_t)(n_segs + 64) * sizeof(wifi_b200_chan_seg)));
+        h->segs_cap = n_segs + 64;
+    }
+    CK(cudaMemcpyAsync(h->d_segs, segs, (size_t)n_segs * sizeof(wifi_b200_chan_seg), cudaMemcpyHostToDevice, h->stream));
+    for (int base = 0; base < n_segs; base += 65535) {
+        int cnt = std::min(65535, n_segs - base);
+        dim3 grid((unsigned)std::min<int64_t>((maxn + 255) / 256, 4096), cnt);
+        if (grid.x == 0) grid.x = 1;
+        k_channel<<<grid, 256, 0, h->stream>>>((const cf *)in_dev, (cf *)out_dev, h->d_segs + base, cnt);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_batch_dev(wifi_b200_t *h, const float *iq_dev, const uint64_t *link_off, int n_links, int final)
+{
+    if (!h || !iq_dev) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    int rc = set_links(h, link_off, n_links, final);
+    if (rc) return rc;
+    rc = run_rx(h, (const cf *)iq_dev, false, false);
+    return rc;
+}
+
+int wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int final)
+{
+    if (!h || !iq_host) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    int rc = set_links(h, link_off, n_links, final);
+    if (rc) return rc;
+    rc = ensure_iq_staging(h);
+    if (rc) return rc;
+    // rebase the links onto the staging buffer
+    uint64_t base = link_off[0];
+    int64_t total = (int64_t)(link_off[n_links] - base);
+    for (auto &L : h->h_links) L.x_off -= (int64_t)base;
+    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
+    cudaEventRecord(h->ev[ST_H2D], h->stream);
+    CK(cudaMemcpyAsync(h->d_iq, iq_host + 2 * base, (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
+    rc = run_rx(h, h->d_iq, true, false);
+    if (rc) return rc;
+    update_stats(h);
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_counts(wifi_b200_t *h, int64_t *n_frames, int64_t *n_rows, int64_t *n_pdus, int64_t *psdu_store_bytes)
+{
+    if (!h) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    int rc = fetch_frames(h);
+    if (rc) return rc;
+    int64_t np = 0;
+    for (int64_t i = 0; i < h->n_frames; ++i) np += h->h_frames[i].crc_ok;
+    if (n_frames) *n_frames = h->n_frames;
+    if (n_rows) *n_rows = h->n_rows;
+    if (n_pdus) *n_pdus = np;
+    if (psdu_store_bytes) *psdu_store_bytes = h->n_jobs * PSDU_STRIDE;
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_frames(wifi_b200_t *h, wifi_b200_frame *out, int64_t cap)
+{
+    if (!h || !out) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (cap < h->n_frames) return WIFI_E_OVERFLOW;
+    int rc = fetch_frames(h);
+    if (rc) return rc;
+    memcpy(out, h->h_frames, h->n_frames * sizeof(wifi_b200_frame));
+    return (int)h->n_frames;
+}
+
+int wifi_b200_rx_rows(wifi_b200_t *h, uint8_t *rows, float *carrier, int64_t cap_rows)
+{
+    if (!h) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (cap_rows < h->n_rows) return WIFI_E_OVERFLOW;
+    if (rows && h->n_rows) CK(cudaMemcpy(rows, h->d_rows, (size_t)h->n_rows * 48, cudaMemcpyDeviceToHost));
+    if (carrier) {
+        if (!h->d_carrier || !h->cfg.want_carrier) { h->err = "carrier output not enabled"; return WIFI_E_ARG; }
+        if (h->n_rows) CK(cudaMemcpy(carrier, h->d_carrier, (size_t)h->n_rows * 48 * sizeof(cf), cudaMemcpyDeviceToHost));
+    }
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_psdus(wifi_b200_t *h, uint8_t *store, size_t cap)
+{
+    if (!h || !store) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (cap < (size_t)h->n_jobs * PSDU_STRIDE) return WIFI_E_OVERFLOW;
+    int rc = fetch_frames(h);
+    if (rc) return rc;
+    memcpy(store, h->h_psdu, (size_t)h->n_jobs * PSDU_STRIDE);
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_flags(wifi_b200_t *h, int link, uint32_t *flags, int64_t cap_words)
+{
+    if (!h || !flags || link < 0 || link >= (int)h->h_links.size()) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    const LinkDesc &L = h->h_links[link];
+    int64_t words = (L.len + 31) / 32;
+    if (cap_words < words) return WIFI_E_OVERFLOW;
+    CK(cudaMemcpy(flags, h->d_flags + L.chunk_base * (FE_CHUNK / 32), words * 4, cudaMemcpyDeviceToHost));
+    return (int)words;
+}
+
+// ---- streaming: one continuous stream, arbitrary chunking (samp_in) ----
+int wifi_b200_rx_reset(wifi_b200_t *h)
+{
+    if (!h) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    h->sbuf.clear();
+    h->s_abs0 = 0; h->s_hist = 0; h->s_prev_trigger = -1; h->s_fo_carry = 0.f;
+    h->s_meta.clear(); h->s_bytes.clear();
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_push(wifi_b200_t *h, const float *iq, size_t n, int flush)
+{
+    if (!h || (!iq && n)) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (n) h->sbuf.insert(h->sbuf.end(), iq, iq + 2 * n);
+    const int64_t have = (int64_t)(h->sbuf.size() / 2) - h->s_hist;   // samples from s_abs0 on
+    if (have <= 0) return WIFI_OK;
+    if (have + h->s_hist > h->cfg.max_samples) { h->err = "stream backlog exceeds max_samples"; return WIFI_E_OVERFLOW; }
+    int rc = ensure_iq_staging(h);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_iq, h->sbuf.data(), h->sbuf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    h->h_links.resize(1);
+    LinkDesc &L = h->h_links[0];
+    memset(&L, 0, sizeof L);
+    L.x_off = h->s_hist;
+    L.len = have;
+    L.is_final = flush ? 1 : 0;
+    L.hist = h->s_hist;
+    L.fo_carry = h->s_fo_carry;
+    L.min_pos = h->s_prev_trigger >= 0 ? h->s_prev_trigger + SS_MIN_GAP + 1 - h->s_abs0 : 0;
+    // the newest burst is held back unless flushing: its end is not known before the next
+    // trigger arrives (sync_short retrigger / sync_long RESET decide its length)
+    rc = run_rx(h, h->d_iq, true, flush == 0);
+    if (rc) return rc;
+    update_stats(h);
+    const int64_t nf = h->n_frames;
+    for (int64_t i = 0; i < nf; ++i) {
+        wifi_b200_frame f = h->h_frames[i];
+        if (!f.crc_ok) continue;
+        const uint8_t *p = h->h_psdu + f.psdu_off;
+        h->s_bytes.insert(h->s_bytes.end(), p, p + (f.length - 4));
+        f.trigger += h->s_abs0;
+        h->s_meta.push_back(f);
+    }
+    if (nf > 0) {
+        h->s_prev_trigger = h->h_frames[nf - 1].trigger + h->s_abs0;
+        h->s_fo_carry = h->h_frames[nf - 1].freq_long;
+    }
+    const int64_t buf_abs = h->s_abs0 - h->s_hist;   // absolute index of sbuf[0]
+    const int64_t end_abs = h->s_abs0 + have;
+    int64_t new_abs0;
+    if (flush) {
+        new_abs0 = (end_abs + FE_CHUNK - 1) / FE_CHUNK * FE_CHUNK;   // stream ended: nothing is kept
+        h->sbuf.clear();
+        h->s_abs0 = new_abs0; h->s_hist = 0; h->s_prev_trigger = -1; h->s_fo_carry = 0.f;
+        return WIFI_OK;
+    }
+    int64_t keep = (h->n_triggers > nf) ? h->h_frames[nf].trigger + h->s_abs0 : end_abs;
+    new_abs0 = (keep - FE_CHUNK) / FE_CHUNK * FE_CHUNK;
+    if (new_abs0 < h->s_abs0) new_abs0 = h->s_abs0;
+    int64_t new_hist = new_abs0 - buf_abs;
+    if (new_hist > 256) new_hist = 256;
+    int64_t drop = (new_abs0 - new_hist) - buf_abs;   // samples to erase from the front
+    if (drop > 0) h->sbuf.erase(h->sbuf.begin(), h->sbuf.begin() + 2 * drop);
+    h->s_abs0 = new_abs0;
+    h->s_hist = (int)new_hist;
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *psdu_buf, size_t psdu_cap, int *n_out)
+{
+    if (!h || !n_out) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    int k = 0;
+    size_t used = 0, consumed_bytes = 0;
+    while (k < (int)h->s_meta.size() && k < cap) {
+        wifi_b200_frame f = h->s_meta[k];
+        size_t nb = (size_t)(f.length - 4);
+        if (used + nb > psdu_cap) break;
+        if (psdu_buf) memcpy(psdu_buf + used, h->s_bytes.data() + consumed_bytes, nb);
+        f.psdu_off = (int64_t)used;
+        if (meta) meta[k] = f;
+        used += nb;
+        consumed_bytes += nb;
+        ++k;
+    }
+    h->s_meta.erase(h->s_meta.begin(), h->s_meta.begin() + k);
+    h->s_bytes.erase(h->s_bytes.begin(), h->s_bytes.begin() + consumed_bytes);
+    *n_out = k;
+    return WIFI_OK;
+}
+
+int wifi_b200_get_stats(wifi_b200_t *h, wifi_b200_stats *out)
+{
+    if (!h || !out) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    *out = h->stats;
+    return WIFI_OK;
+}
+
+int wifi_b200_stage_times(wifi_b200_t *h, float *ms, int cap)
+{
+    if (!h || !ms) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    int n = cap < ST_COUNT ? cap : ST_COUNT;
+    for (int i = 0; i < n; ++i) ms[i] = h->stage_ms[i];
+    return n;
+}
+const char *wifi_b200_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? STAGE_NAMES[i] : ""; }
+
+} // extern "C"

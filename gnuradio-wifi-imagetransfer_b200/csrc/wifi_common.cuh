@@ -1,0 +1,142 @@
+// wifi_common.cuh -- shared device types, constant tables and the fp32 helper
+// ops of libwifi_b200.so.  Numerical contract: every float expression here and
+// in the kernels is written in the same order as oracle/wifi_oracle.cpp and the
+// translation unit is compiled with -fmad=false, so results are bit-identical
+// to the oracle (see include/wifi_detmath.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/wifi_b200.h"
+#include "../../include/wifi_detmath.h"
+
+#define WIFI_MAX_SYM 511        // [UPSTREAM] utils.h MAX_SYM
+#define WIFI_MAX_PSDU 1528      // [UPSTREAM] utils.h MAX_PSDU_SIZE
+#define SS_MIN_GAP 480          // [UPSTREAM] sync_short.cc MIN_GAP
+#define SS_MAX_SAMPLES 43200    // [UPSTREAM] sync_short.cc MAX_SAMPLES = 540*80
+#define SYNC_LENGTH 320         // wifi_phy_hier.grc:698-715 sync_length
+#define FE_CHUNK 128            // running-sum re-seed period of the front-end
+#define PSDU_STRIDE 1536        // bytes reserved per decode job in the psdu store
+#define VIT_MAXW 1560           // 32-bit words (8 trellis steps each) reserved per decode job
+
+struct cf { float re, im; };
+__device__ __forceinline__ cf cadd(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cf csub(cf a, cf b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ cf cmul(cf a, cf b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cf cdiv(cf a, cf b)
+{
+    float den = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
+}
+__device__ __forceinline__ cf cscale(cf a, float s) { return {a.re * s, a.im * s}; }
+__device__ __forceinline__ cf crot(float phase)
+{
+    cf w;
+    wdm_sincosf(phase, &w.im, &w.re);
+    return w;
+}
+__device__ __forceinline__ cf cshfl(cf v, int lane) { return {__shfl_sync(0xffffffffu, v.re, lane), __shfl_sync(0xffffffffu, v.im, lane)}; }
+__device__ __forceinline__ cf cshfl_xor(cf v, int m) { return {__shfl_xor_sync(0xffffffffu, v.re, m), __shfl_xor_sync(0xffffffffu, v.im, m)}; }
+
+struct McsDesc { int n_bpsc, n_cbps, n_dbps, rate_field, punct; };
+
+struct DevTables {
+    float lts[64];            // LTS, shifted order (index = subcarrier + 32)
+    float polarity[127];      // pilot polarity, wifi_phy_hier.grc:350-376
+    cf long_taps[64];         // sync_long matched filter LONG[]
+    cf tw[32];                // exp(-j 2 pi k/64)
+    cf sts[64];               // sync word 1/2
+    cf lts_rot[64];           // sync word 3
+    float win;                // 1/sqrt(52)
+    uint16_t P[8][288];       // interleaver: out[k] = in[P[k]]
+    uint16_t Pinv[8][288];    // Pinv[P[k]] = k
+    cf cons[8][64];           // constellations
+    McsDesc mcs[8];
+    uint32_t crc_tab[256];
+    uint16_t scr_tab[128];    // descrambler, 8 steps: low byte = 8 feedback bits (LSB first), high byte = next state
+    int8_t carrier_of[64];    // shifted bin -> data carrier 0..47, -1 for pilots/null
+};
+__constant__ DevTables c_tab;   // single translation unit (wifi_b200.cu)
+
+// per-link descriptor (device)
+struct LinkDesc {
+    int64_t x_off;        // first sample of the link in the iq buffer
+    int64_t len;          // samples
+    int64_t chunk_base;   // first FE_CHUNK chunk (prefix sum over links)
+    int32_t frame_first;  // first frame record of the link
+    int32_t frame_count;
+    float fo_carry;       // sync_long d_freq_offset entering this buffer
+    int32_t is_final;
+    int32_t hist;         // valid samples stored before x_off (streaming history); older samples read as 0
+    int32_t pad0;
+    int64_t min_pos;      // first sample index sync_short may trigger on (previous trigger + MIN_GAP + 1)
+};
+
+// per-frame equalizer state handed from the SIGNAL phase to the data phase
+struct EqState {
+    cf H[64];
+    cf prev_pil[4];
+    double d_er;
+    double eps0;
+    double snr;
+    uint8_t sig_bits[48];
+};
+
+struct JobDesc {
+    int32_t frame;        // owner (tag) frame
+    int32_t enc, len, n_sym;
+    int32_t n_seg;
+    int32_t seg_row[4];   // first row of each segment
+    int32_t seg_cnt[4];   // rows in each segment
+    int32_t pad;
+};
+
+__device__ __forceinline__ int dev_decide(int nb, cf s)
+{
+    if (nb == 1) return s.re > 0;
+    if (nb == 2) return (s.re > 0) | ((s.im > 0) << 1);
+    if (nb == 4) {
+        const float level = sqrtf(0.1f);
+        int r = s.re > 0;
+        r |= (fabsf(s.re) < (2 * level)) << 1;
+        r |= (s.im > 0) << 2;
+        r |= (fabsf(s.im) < (2 * level)) << 3;
+        return r;
+    }
+    const float level = sqrtf(1.0f / 42.0f);
+    float ar = fabsf(s.re), ai = fabsf(s.im);
+    int r = s.re > 0;
+    r |= (ar < (4 * level)) << 1;
+    r |= ((ar < (6 * level)) && (ar > (2 * level))) << 2;
+    r |= (s.im > 0) << 3;
+    r |= (ai < (4 * level)) << 4;
+    r |= ((ai < (6 * level)) && (ai > (2 * level))) << 5;
+    return r;
+}
+
+__device__ __forceinline__ int dev_bitrev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
+
+// 64-point FFT across one warp.  On entry lane l holds in[2*bitrev5(l)] (a) and
+// in[2*bitrev5(l)+1] (b) -- i.e. DIT positions l and l+32 after bit reversal.  On
+// exit a = X[l], b = X[l+32].  Same butterfly network and rounding as oracle fft64().
+__device__ __forceinline__ void warp_fft64(cf &a, cf &b, int lane, bool inverse)
+{
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int half = 1 << s;
+        cf w = c_tab.tw[(lane & (half - 1)) * (32 >> s)];
+        if (inverse) w.im = -w.im;
+        const bool hi = (lane & half) != 0;
+        cf ta = hi ? cmul(w, a) : a;
+        cf tb = hi ? cmul(w, b) : b;
+        cf ra = cshfl_xor(ta, half);
+        cf rb = cshfl_xor(tb, half);
+        a = hi ? csub(ra, ta) : cadd(a, ra);
+        b = hi ? csub(rb, tb) : cadd(b, rb);
+    }
+    cf w = c_tab.tw[lane];
+    if (inverse) w.im = -w.im;
+    cf t = cmul(w, b);
+    cf u = a;
+    a = cadd(u, t);
+    b = csub(u, t);
+}

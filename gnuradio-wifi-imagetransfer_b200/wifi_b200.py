@@ -1,0 +1,297 @@
+"""ctypes binding of libwifi_b200.so (include/wifi_b200.h).  There is no CPU path in this
+module: every compute call goes to the CUDA library and raises WifiB200Error if it fails."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+FRAME_DTYPE = np.dtype([
+    ("trigger", "<i8"), ("link", "<i4"), ("burst_len", "<i4"), ("freq_short", "<f4"), ("freq_long", "<f4"),
+    ("found", "<i4"), ("frame_start", "<i4"), ("n_syms", "<i4"), ("sig_ok", "<i4"), ("encoding", "<i4"),
+    ("length", "<i4"), ("frame_symbols", "<i4"), ("n_rows", "<i4"), ("accepted", "<i4"), ("decoded", "<i4"),
+    ("crc_ok", "<i4"), ("snr", "<f8"), ("row_off", "<i8"), ("psdu_off", "<i8"),
+], align=True)
+PSDU_STRIDE = 1536
+
+ENCODINGS = ("BPSK_1_2", "BPSK_3_4", "QPSK_1_2", "QPSK_3_4", "QAM16_1_2", "QAM16_3_4", "QAM64_2_3", "QAM64_3_4")
+EQUALIZERS = ("LS", "LMS", "COMB", "STA")
+P_BANDWIDTH, P_FREQUENCY, P_SENSITIVITY, P_CHAN_EST, P_ENCODING, P_MIN_PLATEAU, P_WANT_CARRIER = range(7)
+E_ARG, E_TOO_LARGE, E_CUDA, E_NOMEM, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4, -5, -6
+
+
+class Cfg(C.Structure):
+    _fields_ = [("bandwidth", C.c_double), ("frequency", C.c_double), ("sensitivity", C.c_double),
+                ("chan_est", C.c_int32), ("encoding", C.c_int32), ("min_plateau", C.c_int32), ("device", C.c_int32),
+                ("want_carrier", C.c_int32), ("reserved", C.c_int32), ("max_samples", C.c_int64), ("max_frames", C.c_int64)]
+
+
+class ChanSeg(C.Structure):
+    _fields_ = [("in_off", C.c_int64), ("in_len", C.c_int64), ("out_off", C.c_int64), ("n", C.c_int64), ("n0", C.c_int64),
+                ("gain", C.c_float), ("cfo", C.c_float), ("phase0", C.c_float), ("noise_sigma", C.c_float),
+                ("n_taps", C.c_int32), ("delay", C.c_int32 * 8), ("tap_re", C.c_float * 8), ("tap_im", C.c_float * 8),
+                ("seed", C.c_uint64), ("stream", C.c_uint64)]
+
+
+CHANSEG_DTYPE = np.dtype([
+    ("in_off", "<i8"), ("in_len", "<i8"), ("out_off", "<i8"), ("n", "<i8"), ("n0", "<i8"),
+    ("gain", "<f4"), ("cfo", "<f4"), ("phase0", "<f4"), ("noise_sigma", "<f4"), ("n_taps", "<i4"),
+    ("delay", "<i4", (8,)), ("tap_re", "<f4", (8,)), ("tap_im", "<f4", (8,)), ("seed", "<u8"), ("stream", "<u8")], align=True)
+assert CHANSEG_DTYPE.itemsize == C.sizeof(ChanSeg), (CHANSEG_DTYPE.itemsize, C.sizeof(ChanSeg))
+
+
+class Stats(C.Structure):
+    _fields_ = [("samples", C.c_int64), ("frames_detected", C.c_int64), ("signal_ok", C.c_int64), ("decoded", C.c_int64),
+                ("crc_ok", C.c_int64), ("pdu_bytes", C.c_int64), ("per_mcs_crc_ok", C.c_int64 * 8)]
+
+
+class WifiB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libwifi_b200: %s (code %d)" % (msg, code))
+        self.code = code
+
+
+EXPORTS = [
+    "wifi_b200_abi_version", "wifi_b200_device_count", "wifi_b200_create", "wifi_b200_destroy", "wifi_b200_set_param",
+    "wifi_b200_get_param", "wifi_b200_last_error", "wifi_b200_strerror", "wifi_b200_stream", "wifi_b200_sync",
+    "wifi_b200_mac_frame", "wifi_b200_n_sym", "wifi_b200_frame_samples", "wifi_b200_tx", "wifi_b200_tx_dev",
+    "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_counts",
+    "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_flags", "wifi_b200_rx_push",
+    "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
+]
+
+_LIB = None
+
+
+def lib():
+    """Loads (building if stale) the CUDA library.  Raises if it cannot be built or loaded."""
+    global _LIB
+    if _LIB is None:
+        so = _build.build()
+        L = C.CDLL(so)
+        vp, i64, u64p = C.c_void_p, C.c_int64, C.POINTER(C.c_uint64)
+        L.wifi_b200_create.argtypes = [C.POINTER(Cfg), C.POINTER(vp)]
+        L.wifi_b200_destroy.argtypes = [vp]
+        L.wifi_b200_destroy.restype = None
+        L.wifi_b200_set_param.argtypes = [vp, C.c_int, C.c_double]
+        L.wifi_b200_get_param.argtypes = [vp, C.c_int]
+        L.wifi_b200_get_param.restype = C.c_double
+        L.wifi_b200_last_error.argtypes = [vp]
+        L.wifi_b200_last_error.restype = C.c_char_p
+        L.wifi_b200_strerror.restype = C.c_char_p
+        L.wifi_b200_stream.argtypes = [vp]
+        L.wifi_b200_stream.restype = vp
+        L.wifi_b200_sync.argtypes = [vp]
+        L.wifi_b200_mac_frame.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, vp]
+        for f in ("wifi_b200_tx", "wifi_b200_tx_dev"):
+            getattr(L, f).argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_size_t, vp]
+            getattr(L, f).restype = i64
+        L.wifi_b200_tx_symbols.argtypes = [vp, vp, C.c_size_t]
+        L.wifi_b200_tx_symbols.restype = i64
+        L.wifi_b200_channel_dev.argtypes = [vp, vp, vp, vp, C.c_int]
+        for f in ("wifi_b200_rx_batch", "wifi_b200_rx_batch_dev"):
+            getattr(L, f).argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.wifi_b200_rx_counts.argtypes = [vp, vp, vp, vp, vp]
+        L.wifi_b200_rx_frames.argtypes = [vp, vp, i64]
+        L.wifi_b200_rx_rows.argtypes = [vp, vp, vp, i64]
+        L.wifi_b200_rx_psdus.argtypes = [vp, vp, C.c_size_t]
+        L.wifi_b200_rx_flags.argtypes = [vp, C.c_int, vp, i64]
+        L.wifi_b200_rx_push.argtypes = [vp, vp, C.c_size_t, C.c_int]
+        L.wifi_b200_rx_pop.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_int)]
+        L.wifi_b200_rx_reset.argtypes = [vp]
+        L.wifi_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.wifi_b200_stage_times.argtypes = [vp, vp, C.c_int]
+        L.wifi_b200_stage_name.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count():
+    return lib().wifi_b200_device_count()
+
+
+def mac_frame(payload, seq, src=b"\x23" * 6, dst=b"\x42" * 6, bss=b"\xff" * 6):
+    """[UPSTREAM] ieee802_11.mac framing; defaults are the addresses of IRS_tranceiver.py:271."""
+    pl = np.frombuffer(bytes(payload), np.uint8)
+    o = np.empty(pl.size + 28, np.uint8)
+    n = lib().wifi_b200_mac_frame(_p(pl) if pl.size else None, pl.size, seq, bytes(src), bytes(dst), bytes(bss), _p(o))
+    if n < 0:
+        raise WifiB200Error(n, lib().wifi_b200_strerror(n).decode())
+    return o[:n].tobytes()
+
+
+def n_sym(enc, psdu_len):
+    return lib().wifi_b200_n_sym(enc, psdu_len)
+
+
+def frame_samples(enc, psdu_len):
+    return lib().wifi_b200_frame_samples(enc, psdu_len)
+
+
+class RxResult:
+    """All sync_short triggers of one rx call plus the decoded PSDU store."""
+
+    def __init__(self, frames, store):
+        self.frames, self.store = frames, store
+
+    def psdu(self, i):
+        f = self.frames[i]
+        if f["psdu_off"] < 0:
+            return None
+        return self.store[f["psdu_off"]:f["psdu_off"] + f["length"]].tobytes()
+
+    def pdus(self):
+        """What mac_out carries: PSDU without FCS for every CRC-ok frame, in frame-table order."""
+        return [self.psdu(i)[:-4] for i in range(len(self.frames)) if self.frames[i]["crc_ok"]]
+
+
+class Handle:
+    def __init__(self, bandwidth=10e6, frequency=5.89e9, sensitivity=0.56, chan_est=0, encoding=0, min_plateau=2,
+                 device=0, want_carrier=False, max_samples=1 << 22, max_frames=0):
+        self._L = lib()
+        cfg = Cfg(bandwidth, frequency, sensitivity, int(chan_est), int(encoding), min_plateau, device, int(want_carrier), 0,
+                  int(max_samples), int(max_frames))
+        h = C.c_void_p()
+        rc = self._L.wifi_b200_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise WifiB200Error(rc, self._L.wifi_b200_strerror(rc).decode())
+        self._h = h
+        self.max_frames = int(max_frames) if max_frames else int(max_samples) // 1000 + 64
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.wifi_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise WifiB200Error(rc, self._L.wifi_b200_last_error(self._h).decode() or self._L.wifi_b200_strerror(rc).decode())
+        return rc
+
+    def set_param(self, pid, value):
+        self._ck(self._L.wifi_b200_set_param(self._h, pid, float(value)))
+
+    def get_param(self, pid):
+        return self._L.wifi_b200_get_param(self._h, pid)
+
+    @property
+    def stream(self):
+        return self._L.wifi_b200_stream(self._h)
+
+    # ---- TX ----
+    def _tx_args(self, psdus, enc, seed):
+        n = len(psdus)
+        blob = np.frombuffer(b"".join(psdus), np.uint8) if n else np.zeros(0, np.uint8)
+        lens = np.array([len(p) for p in psdus], np.uint32)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint32) if n else np.zeros(0, np.uint32)
+        e = None if enc is None else np.broadcast_to(np.asarray(enc, np.uint8), (n,)).copy()
+        s = None if seed is None else np.broadcast_to(np.asarray(seed, np.uint8), (n,)).copy()
+        return n, blob, offs, lens, e, s
+
+    def tx(self, psdus, enc=None, seed=None):
+        """mac_in -> samp_out: list of PSDUs (bytes, FCS included) -> (iq complex64, burst offsets)."""
+        n, blob, offs, lens, e, s = self._tx_args(psdus, enc, seed)
+        encs = e if e is not None else np.full(n, int(self.get_param(P_ENCODING)), np.uint8)
+        for ln in lens:
+            if ln > 1528:
+                raise WifiB200Error(E_TOO_LARGE, "PSDU too large")
+        cap = int(sum(frame_samples(int(encs[i]), int(lens[i])) for i in range(n)))
+        iq = np.empty(cap, np.complex64)
+        boff = np.zeros(n + 1, np.uint64)
+        tot = self._ck(self._L.wifi_b200_tx(self._h, _p(blob), _p(offs), _p(lens), _p(e), _p(s), n, _p(iq), cap, _p(boff)))
+        return iq[:tot], boff
+
+    def tx_dev(self, psdus, out_ptr, cap_samples, enc=None, seed=None):
+        n, blob, offs, lens, e, s = self._tx_args(psdus, enc, seed)
+        boff = np.zeros(n + 1, np.uint64)
+        tot = self._ck(self._L.wifi_b200_tx_dev(self._h, _p(blob), _p(offs), _p(lens), _p(e), _p(s), n, C.c_void_p(out_ptr), cap_samples, _p(boff)))
+        return tot, boff
+
+    def tx_symbols(self):
+        buf = np.empty(self.max_frames * 511 * 48 if self.max_frames < 64 else 64 * 511 * 48, np.uint8)
+        n = self._ck(self._L.wifi_b200_tx_symbols(self._h, _p(buf), buf.size))
+        return buf[:n].copy()
+
+    def channel_dev(self, in_ptr, out_ptr, segs):
+        segs = np.ascontiguousarray(segs, CHANSEG_DTYPE)
+        self._ck(self._L.wifi_b200_channel_dev(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), _p(segs), segs.size))
+
+    # ---- RX ----
+    def rx_batch(self, iq, link_off=None, final=True, fetch=True):
+        a = np.ascontiguousarray(iq, np.complex64)
+        lo = np.array([0, a.size], np.uint64) if link_off is None else np.ascontiguousarray(link_off, np.uint64)
+        self._ck(self._L.wifi_b200_rx_batch(self._h, _p(a), _p(lo), lo.size - 1, int(final)))
+        return self.results() if fetch else None
+
+    def rx_batch_dev(self, iq_ptr, link_off, final=True, fetch=False):
+        lo = np.ascontiguousarray(link_off, np.uint64)
+        self._ck(self._L.wifi_b200_rx_batch_dev(self._h, C.c_void_p(iq_ptr), _p(lo), lo.size - 1, int(final)))
+        return self.results() if fetch else None
+
+    def counts(self):
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(self._L.wifi_b200_rx_counts(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("n_frames", "n_rows", "n_pdus", "psdu_store_bytes"), [x.value for x in v]))
+
+    def results(self):
+        c = self.counts()
+        frames = np.zeros(c["n_frames"], FRAME_DTYPE)
+        store = np.zeros(c["psdu_store_bytes"], np.uint8)
+        if c["n_frames"]:
+            self._ck(self._L.wifi_b200_rx_frames(self._h, _p(frames), frames.size))
+        if c["psdu_store_bytes"]:
+            self._ck(self._L.wifi_b200_rx_psdus(self._h, _p(store), store.size))
+        return RxResult(frames, store)
+
+    def rows(self, carrier=False):
+        c = self.counts()
+        rows = np.zeros((c["n_rows"], 48), np.uint8)
+        car = np.zeros((c["n_rows"], 48), np.complex64) if carrier else None
+        self._ck(self._L.wifi_b200_rx_rows(self._h, _p(rows), _p(car), c["n_rows"]))
+        return (rows, car) if carrier else rows
+
+    def flags(self, link, n_samples):
+        w = np.zeros((n_samples + 31) // 32, np.uint32)
+        self._ck(self._L.wifi_b200_rx_flags(self._h, link, _p(w), w.size))
+        return np.unpackbits(w.view(np.uint8), bitorder="little")[:n_samples].astype(bool)
+
+    def rx_push(self, iq, flush=False):
+        a = np.ascontiguousarray(iq, np.complex64)
+        self._ck(self._L.wifi_b200_rx_push(self._h, _p(a) if a.size else None, a.size, int(flush)))
+
+    def rx_pop(self, cap=256):
+        meta = np.zeros(cap, FRAME_DTYPE)
+        buf = np.zeros(cap * 1528, np.uint8)
+        n = C.c_int()
+        self._ck(self._L.wifi_b200_rx_pop(self._h, _p(meta), cap, _p(buf), buf.size, C.byref(n)))
+        out = []
+        for i in range(n.value):
+            f = meta[i]
+            out.append((f.copy(), buf[f["psdu_off"]:f["psdu_off"] + f["length"] - 4].tobytes()))
+        return out
+
+    def rx_reset(self):
+        self._ck(self._L.wifi_b200_rx_reset(self._h))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._L.wifi_b200_get_stats(self._h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k != "per_mcs_crc_ok"}
+        d["per_mcs_crc_ok"] = list(s.per_mcs_crc_ok)
+        return d
+
+    def stage_times(self):
+        ms = np.zeros(16, np.float32)
+        n = self._ck(self._L.wifi_b200_stage_times(self._h, _p(ms), 16))
+        return {self._L.wifi_b200_stage_name(i).decode(): float(ms[i]) for i in range(n)}

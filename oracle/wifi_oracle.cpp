@@ -762,8 +762,9 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
             if (rel >= 0 && (rel < 128 || ((rel - 128) % 80) > 15)) sy.push_back(cmul(b[j], crot((float)j * F.freq_long)));
         }
         /* a later tag sends sync_long through RESET, which zero-pads the open symbol; the
-         * last burst of the stream never sees that tag, its partial symbol is never emitted */
-        int n_syms = last ? (int)(sy.size() / 64) : (int)((sy.size() + 63) / 64);
+         * last burst of a finished stream never sees that tag, its partial symbol is never
+         * emitted.  final == 0 means "a later tag will come". */
+        int n_syms = (last && cfg.final) ? (int)(sy.size() / 64) : (int)((sy.size() + 63) / 64);
         sy.resize((size_t)n_syms * 64, cf{0.f, 0.f}); /* RESET zero padding */
         F.n_syms = n_syms;
 
