@@ -18,12 +18,6 @@ __device__ __forceinline__ cf fe_prod(const cf *x, int64_t j, int hist)
     cf a = x[j], d = x[j - 16];
     return {a.re * d.re + a.im * d.im, a.im * d.re - a.re * d.im};
 }
-__device__ __forceinline__ float fe_pw(const cf *x, int64_t j, int hist)
-{
-    if (j < -(int64_t)hist) return 0.f;
-    cf a = x[j];
-    return a.re * a.re + a.im * a.im;
-}
 
 __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int64_t chunk)
 {
@@ -35,133 +29,181 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
     return lo;
 }
 
-// One thread per FE_CHUNK samples of one link: re-seed the two running sums exactly as the
-// oracle does at every multiple of FE_CHUNK, run them over the chunk, emit bit n = (c[n] > thr).
-__global__ void __launch_bounds__(128) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
-                                                 int64_t total_chunks, float thr_f, uint32_t *__restrict__ flags)
+// One block per tile of DET_TILE samples of one link, one thread per FE_CHUNK samples.  The tile
+// (plus two chunks of history) is staged in shared memory with coalesced loads; rows are padded
+// by one sample so that the per-thread sequential walk (stride FE_CHUNK) is bank-conflict free.
+// Each thread re-seeds the two running sums exactly as the oracle does at every multiple of
+// FE_CHUNK, runs them over its chunk and emits bit n = (c[n] > thr).  Samples before the start
+// of the stream are zeros, which makes every "index < 0" special case of the oracle an exact
+// no-op (x + 0 == x), so the inner loop is branch free.
+#define DET_ROWS (DET_THREADS + 2)
+#define DET_IDX(q) ((q) + ((q) >> 6))     // row * 65 + col
+__global__ void __launch_bounds__(DET_THREADS) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
+                                                         int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
+                                                         uint32_t *__restrict__ summary)
 {
-    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total_chunks) return;
-    int l = find_link(links, n_links, gid);
+    extern __shared__ cf sx[];   // DET_ROWS * 65
+    const int64_t tile = blockIdx.x;
+    if (tile >= total_tiles) return;
+    const int tid = threadIdx.x;
+    int l = find_link(links, n_links, tile * DET_THREADS);
     const LinkDesc L = links[l];
     const cf *x = iq + L.x_off;
-    const int hist = L.hist;
-    int64_t i0 = (gid - L.chunk_base) * FE_CHUNK;
-    float sar = 0.f, sai = 0.f, sp = 0.f;
-    for (int64_t j = i0 - 47; j < i0; ++j) {
-        if (j < -(int64_t)hist) continue;
-        cf p = fe_prod(x, j, hist);
-        sar += p.re;
-        sai += p.im;
+    const int64_t T0 = (tile * DET_THREADS - L.chunk_base) * FE_CHUNK;   // first sample of the tile in the link
+    const int64_t lo = -(int64_t)L.hist, hi = L.len;
+    for (int q = tid; q < DET_ROWS * FE_CHUNK; q += DET_THREADS) {
+        int64_t g = T0 - 2 * FE_CHUNK + q;
+        cf v = {0.f, 0.f};
+        if (g >= lo && g < hi) v = x[g];
+        sx[DET_IDX(q)] = v;
     }
-    for (int64_t j = i0 - 63; j < i0; ++j) {
-        if (j < -(int64_t)hist) continue;
-        sp += fe_pw(x, j, hist);
-    }
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    int64_t end = i0 + FE_CHUNK < L.len ? i0 + FE_CHUNK : L.len;
-#pragma unroll 4
-    for (int64_t i = i0; i < end; ++i) {
-        cf pr = fe_prod(x, i, hist);
-        sar += pr.re;
-        sai += pr.im;
-        float ar = sar, ai = sai;
-        if (i - 47 >= -(int64_t)hist) {
-            cf po = fe_prod(x, i - 47, hist);
-            sar -= po.re;
-            sai -= po.im;
+    __syncthreads();
+    const int q0 = (tid + 2) * FE_CHUNK;   // tile-local index of this thread's first sample
+    uint32_t w0 = 0u, w1 = 0u;
+    if (T0 + (int64_t)tid * FE_CHUNK < hi) {
+        float sar = 0.f, sai = 0.f, sp = 0.f;
+#pragma unroll 1
+        for (int k = 47; k >= 1; --k) {
+            cf a = sx[DET_IDX(q0 - k)], d = sx[DET_IDX(q0 - k - 16)];
+            sar += a.re * d.re + a.im * d.im;
+            sai += a.im * d.re - a.re * d.im;
         }
-        sp += fe_pw(x, i, hist);
-        float p = sp;
-        if (i - 63 >= -(int64_t)hist) sp -= fe_pw(x, i - 63, hist);
-        float c = sqrtf(ar * ar + ai * ai) / p;
-        int k = (int)(i - i0);
-        if (c > thr_f) w[k >> 5] |= 1u << (k & 31);
+#pragma unroll 1
+        for (int k = 63; k >= 1; --k) {
+            cf a = sx[DET_IDX(q0 - k)];
+            sp += a.re * a.re + a.im * a.im;
+        }
+        const float thr2 = thr_f * thr_f;
+#pragma unroll 4
+        for (int i = 0; i < FE_CHUNK; ++i) {
+            const int q = q0 + i;
+            cf xn = sx[DET_IDX(q)], xd = sx[DET_IDX(q - 16)], xo = sx[DET_IDX(q - 47)], xod = sx[DET_IDX(q - 63)];
+            sar += xn.re * xd.re + xn.im * xd.im;
+            sai += xn.im * xd.re - xn.re * xd.im;
+            const float ar = sar, ai = sai;
+            sar -= xo.re * xod.re + xo.im * xod.im;
+            sai -= xo.im * xod.re - xo.re * xod.im;
+            sp += xn.re * xn.re + xn.im * xn.im;
+            const float p = sp;
+            sp -= xod.re * xod.re + xod.im * xod.im;
+            const float m2 = ar * ar + ai * ai;
+            // c = sqrt(m2)/p > thr.  Decide from the squares when the margin (1e-4) dwarfs the rounding
+            // of the exact expression (< 3e-7); evaluate the oracle's expression only inside the margin.
+            const float t2 = thr2 * (p * p);
+            bool over;
+            if (p > 0.f && t2 > 1e-30f && t2 < 1e30f && m2 > 1e-30f && (m2 > t2 * 1.0001f || m2 < t2 * 0.9999f)) over = m2 > t2;
+            else over = (sqrtf(m2) / p) > thr_f;
+            if (over) { if (i < 32) w0 |= 1u << i; else w1 |= 1u << (i - 32); }
+        }
     }
-    reinterpret_cast<uint4 *>(flags)[gid] = make_uint4(w[0], w[1], w[2], w[3]);
+    const int64_t chunk = tile * DET_THREADS + tid;
+    reinterpret_cast<uint2 *>(flags)[chunk] = make_uint2(w0, w1);
+    uint32_t any = __ballot_sync(0xffffffffu, (w0 | w1) != 0u);
+    if ((tid & 31) == 0) summary[chunk >> 5] = any;
 }
 
 // ------------------------------------------------------------------ R2 sync_short selection
-// One warp per link.  cand(m) = flag[m] & flag[m-1] & flag[m-2] (plateau counter reached
-// min_plateau = 2 before m); triggers are the greedy chain "first candidate more than
-// MIN_GAP after the previous trigger" (COPY-state retrigger and SEARCH-state trigger
-// coincide).  Pass 0 counts, pass 1 writes the frame records.
-__device__ __forceinline__ int64_t next_candidate(const uint32_t *fw, int64_t n_words, int64_t pos, int lane, int min_plateau)
+// One warp per link.  cand(m) = flag[m] & flag[m-1] & .. & flag[m-min_plateau] (plateau counter
+// reached min_plateau before m); triggers are the greedy chain "first candidate more than MIN_GAP
+// after the previous trigger" (the COPY-state retrigger and the SEARCH-state trigger coincide, see
+// DESIGN.md).  The scan walks the one-bit-per-chunk summary and opens only chunks that hold a flag.
+__device__ __forceinline__ int64_t next_candidate(const uint32_t *__restrict__ fw, const uint32_t *__restrict__ sm, int64_t chunk_base,
+                                                  int64_t n_chunks, int64_t pos, int lane, int min_plateau)
 {
-    int64_t wbase = (pos >> 5) & ~31ll;
-    for (; wbase < n_words; wbase += 32) {
+    int64_t c = pos >> 6;
+    while (c < n_chunks) {
+        // next chunk >= c with any flag: 32 summary words (1024 chunks) per iteration
+        int64_t gb = chunk_base + c;                 // global chunk index = summary bit index
+        int64_t wbase = gb >> 5;
         int64_t wi = wbase + lane;
-        uint32_t w = (wi < n_words) ? fw[wi] : 0u;
-        uint32_t pw = (wi >= 1 && wi - 1 < n_words) ? fw[wi - 1] : 0u;
-        uint32_t cand = w;
-        for (int k = 1; k <= min_plateau; ++k) cand &= (w << k) | (pw >> (32 - k));
-        int64_t first = wi * 32;
+        uint32_t sw = (wi * 32 < chunk_base + n_chunks) ? sm[wi] : 0u;
+        if (lane == 0) sw &= 0xffffffffu << (gb & 31);
+        uint32_t any = __ballot_sync(0xffffffffu, sw != 0u);
+        if (!any) { c = (wbase + 32) * 32 - chunk_base; continue; }
+        int src = __ffs((int)any) - 1;
+        uint32_t hit = __shfl_sync(0xffffffffu, sw, src);
+        int64_t ch = (wbase + src) * 32 + (__ffs((int)hit) - 1) - chunk_base;
+        if (ch >= n_chunks) return -1;
+        // open chunk ch: 64 flags + the last bits of the previous chunk
+        uint2 w = reinterpret_cast<const uint2 *>(fw)[ch];
+        uint32_t pw = ch > 0 ? fw[2 * ch - 1] : 0u;
+        unsigned long long f64 = ((unsigned long long)w.y << 32) | w.x, cand = f64;
+        for (int k = 1; k <= min_plateau; ++k) cand &= (f64 << k) | ((unsigned long long)pw >> (32 - k));
+        int64_t first = ch * 64;
         if (first < pos) {
             int64_t d = pos - first;
-            cand = d >= 32 ? 0u : (cand & (0xffffffffu << d));
+            cand = d >= 64 ? 0ull : (cand & (~0ull << d));
         }
-        uint32_t any = __ballot_sync(0xffffffffu, cand != 0u);
-        if (any) {
-            int src = __ffs((int)any) - 1;
-            uint32_t c = __shfl_sync(0xffffffffu, cand, src);
-            return (wbase + src) * 32 + (__ffs((int)c) - 1);
-        }
+        if (cand) return first + (__ffsll((long long)cand) - 1);
+        c = ch + 1;
     }
     return -1;
 }
 
-__global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ flags, LinkDesc *links, int n_links, wifi_b200_frame *frames,
-                                                 int *counters /* [0]=frames [1]=rows(lo) */, unsigned long long *row_counter,
-                                                 int64_t max_frames, int min_plateau, int *err)
+__global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary, LinkDesc *links,
+                                                 int n_links, wifi_b200_frame *frames, int *counters, unsigned long long *row_counter,
+                                                 int64_t max_frames, int min_plateau, int *err, int2 *trig_tmp)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_links) return;
     LinkDesc L = links[warp];
-    const uint32_t *fw = flags + L.chunk_base * (FE_CHUNK / 32);
-    int64_t n_words = (L.len + 31) >> 5;
-    int count = 0;
-    int64_t rows = 0;
+    const uint32_t *fw = flags + L.chunk_base * 2;
+    const int64_t n_chunks = (L.len + FE_CHUNK - 1) / FE_CHUNK;
+    int2 *tmp = trig_tmp + L.chunk_base / 4;   // triggers are > 480 samples apart: at most one per 7 chunks
+    int64_t pos = L.min_pos > 0 ? L.min_pos : 0, prev = -1;
+    int k = 0;
+    for (;;) {
+        int64_t m = next_candidate(fw, summary, L.chunk_base, n_chunks, pos, lane, min_plateau);
+        if (m >= L.len) m = -1;
+        if (prev >= 0) {
+            int64_t endp = (m >= 0) ? m : L.len;
+            int blen = (int)((endp - prev) < SS_MAX_SAMPLES ? (endp - prev) : SS_MAX_SAMPLES);
+            if (lane == 0) tmp[k - 1] = make_int2((int)prev, blen);
+        }
+        if (m < 0) break;
+        prev = m;
+        ++k;
+        pos = m + SS_MIN_GAP + 1;
+    }
+    __syncwarp();
+    // rows reserved per burst: blen/80 + 1 ; exclusive prefix over the link's bursts
+    long long rows = 0;
+    for (int b0 = 0; b0 < k; b0 += 32) {
+        int i = b0 + lane;
+        if (i < k) rows += tmp[i].y / 80 + 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
     int base = 0;
     long long row_base = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        int64_t pos = L.min_pos > 0 ? L.min_pos : 0, prev = -1;
-        int k = 0;
-        long long racc = 0;
-        for (;;) {
-            int64_t m = next_candidate(fw, n_words, pos, lane, min_plateau);
-            if (m >= L.len) m = -1;
-            if (prev >= 0) {
-                int64_t endp = (m >= 0) ? m : L.len;
-                int blen = (int)((endp - prev) < SS_MAX_SAMPLES ? (endp - prev) : SS_MAX_SAMPLES);
-                if (pass == 1 && lane == 0 && base + k - 1 < max_frames) {
-                    wifi_b200_frame f;
-                    f.trigger = prev; f.link = warp; f.burst_len = blen; f.freq_short = 0.f; f.freq_long = 0.f;
-                    f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
-                    f.frame_symbols = 0; f.n_rows = 0; f.accepted = 0; f.decoded = 0; f.crc_ok = 0; f.snr = 0.0;
-                    f.row_off = row_base + racc; f.psdu_off = -1;
-                    frames[base + k - 1] = f;
-                }
-                racc += blen / 80 + 1;
-            }
-            if (m < 0) break;
-            prev = m;
-            ++k;
-            pos = m + SS_MIN_GAP + 1;
+    if (lane == 0) {
+        base = atomicAdd(&counters[0], k);
+        row_base = (long long)atomicAdd(row_counter, (unsigned long long)rows);
+        bool ovf = (int64_t)base + k > max_frames;
+        if (ovf) atomicExch(err, WIFI_E_OVERFLOW);
+        links[warp].frame_first = base;
+        links[warp].frame_count = ovf ? 0 : k;
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    row_base = __shfl_sync(0xffffffffu, row_base, 0);
+    if ((int64_t)base + k > max_frames) return;
+    long long carry = 0;
+    for (int b0 = 0; b0 < k; b0 += 32) {
+        int i = b0 + lane;
+        int2 tb = i < k ? tmp[i] : make_int2(0, 0);
+        long long mine = i < k ? tb.y / 80 + 1 : 0, incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        if (pass == 0) {
-            count = k;
-            rows = racc;
-            if (lane == 0) {
-                base = atomicAdd(&counters[0], count);
-                row_base = (long long)atomicAdd(row_counter, (unsigned long long)rows);
-                if ((int64_t)base + count > max_frames) atomicExch(err, WIFI_E_OVERFLOW);
-                links[warp].frame_first = base;
-                links[warp].frame_count = ((int64_t)base + count > max_frames) ? 0 : count;
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            row_base = __shfl_sync(0xffffffffu, row_base, 0);
-            if ((int64_t)base + count > max_frames) return;
+        if (i < k) {
+            wifi_b200_frame f;
+            f.trigger = tb.x; f.link = warp; f.burst_len = tb.y; f.freq_short = 0.f; f.freq_long = 0.f;
+            f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
+            f.frame_symbols = 0; f.n_rows = 0; f.accepted = 0; f.decoded = 0; f.crc_ok = 0; f.snr = 0.0;
+            f.row_off = row_base + carry + incl - mine; f.psdu_off = -1;
+            frames[base + i] = f;
         }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -286,10 +328,13 @@ __device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
 
 // phase 0: symbols 0..2 (LTS1, LTS2, SIGNAL) -> EqState ; phase 1: data symbols -> rows
 __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
-                                                EqState *states, uint8_t *rows, cf *carrier, DemodParams prm, int phase)
+                                                EqState *states, uint8_t *rows, cf *carrier, DemodParams prm, int phase,
+                                                const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in)
 {
     __shared__ cf s_hu[4][64];
     __shared__ double s_md[4][64], s_ms[4][64];
+    __shared__ uint16_t s_lut[4][432];
+    __shared__ uint8_t s_bits[4][48];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * 4 + wib;
     if (f >= n_frames) return;
@@ -343,6 +388,16 @@ __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const 
         n_begin = 3;
         n_end = n_syms < frame_symbols + 3 ? n_syms : frame_symbols + 3;
     }
+    // data phase: the warp also depunctures each symbol into the decoder's trellis words (R6
+    // unpack + deinterleave + depuncture), 8 steps per 32-bit word, words_per_sym = N_DBPS/8.
+    // BPSK 3/4 (N_DBPS 36) does not fill whole words per symbol and goes through k_pack.
+    const int ndbps = c_tab.mcs[enc].n_dbps;
+    const int wps = (phase == 1 && (ndbps & 7) == 0) ? ndbps >> 3 : 0;
+    if (wps) {
+        for (int i = lane; i < 2 * ndbps; i += 32) s_lut[wib][i] = depunct_lut[enc * 432 + i];
+        __syncwarp();
+    }
+    uint32_t *vw = vit_in + (int64_t)f * VIT_MAXW;
     int n_rows = 0;
     for (int n = n_begin; n < n_end; ++n) {
         // ---- sync_long COPY: fetch the symbol's samples, both derotations ----
@@ -495,6 +550,22 @@ __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const 
                     if (carA >= 0) carrier[row * 48 + carA] = symA;
                     if (carB >= 0) carrier[row * 48 + carB] = symB;
                 }
+                if (wps) {
+                    if (carA >= 0) s_bits[wib][carA] = (uint8_t)bitsA;
+                    if (carB >= 0) s_bits[wib][carB] = (uint8_t)bitsB;
+                    __syncwarp();
+                    if (lane < wps) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            uint32_t e = s_lut[wib][16 * lane + k];
+                            uint32_t sym = (e == 0xffffu) ? 2u : ((s_bits[wib][e >> 3] >> (e & 7)) & 1u);
+                            word |= sym << (2 * k);
+                        }
+                        vw[(n - 3) * wps + lane] = word;
+                    }
+                    __syncwarp();
+                }
                 ++n_rows;
             }
         }
@@ -575,101 +646,159 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_signal(wifi_b200_frame *frames, i
 }
 
 // ------------------------------------------------------------------ R6 decode_mac planning
-// One thread per link, sequential over the link's frames (see oracle rx_link, decode_mac part).
-__global__ void k_plan(const LinkDesc *__restrict__ links, int n_links, wifi_b200_frame *frames, JobDesc *jobs, int *n_jobs, int *err)
+// decode_mac's tag / symbol-collection state machine (see oracle rx_link).  One warp per link.
+// A frame is "regular" when its SIGNAL decoded, it passes the size check and it delivered all of
+// its symbols: then it resets the collection state whatever came before (unless an older tag is
+// still pending) and forms a job on its own.  Groups of 32 frames that are all regular or
+// SIGNAL-less are planned in parallel; any other group falls back to the sequential machine.
+struct PlanState { int cur, copied, need, pending; JobDesc J; bool bad; };
+
+__device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *frames, JobDesc *jobs, int *pack_list, int *n_pack, int *err)
 {
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_links) return;
-    const LinkDesc L = links[l];
-    int cur = -1, copied = 0, pending = -1, need = 0;
-    JobDesc J;
-    J.n_seg = 0;
-    bool bad = false;
-    for (int fi = L.frame_first; fi < L.frame_first + L.frame_count; ++fi) {
+    for (int fi = f0; fi < f1; ++fi) {
         wifi_b200_frame F = frames[fi];
         if (!F.sig_ok) continue;
         if (F.n_rows == 0) {
-            if (pending < 0) pending = fi;
+            if (S.pending < 0) S.pending = fi;
             continue;
         }
-        int tagf = pending >= 0 ? pending : fi;
-        pending = -1;
+        int tagf = S.pending >= 0 ? S.pending : fi;
+        S.pending = -1;
         int t_sym = frames[tagf].frame_symbols, t_len = frames[tagf].length;
         if (t_sym <= WIFI_MAX_SYM && t_len <= WIFI_MAX_PSDU) {
             frames[tagf].accepted = 1;
-            cur = tagf;
-            copied = 0;
-            need = t_sym;
-            J.frame = tagf; J.enc = frames[tagf].encoding; J.len = t_len; J.n_sym = t_sym; J.n_seg = 0; J.pad = 0;
-            bad = false;
+            S.cur = tagf;
+            S.copied = 0;
+            S.need = t_sym;
+            S.J.frame = tagf; S.J.enc = frames[tagf].encoding; S.J.len = t_len; S.J.n_sym = t_sym; S.J.n_seg = 0; S.J.need_pack = 0;
+            S.bad = false;
         }
-        if (cur < 0 || copied >= need) continue;
-        int take = F.n_rows < need - copied ? F.n_rows : need - copied;
-        if (J.n_seg < 4) {
-            J.seg_row[J.n_seg] = (int32_t)F.row_off;
-            J.seg_cnt[J.n_seg] = take;
-            J.n_seg++;
+        if (S.cur < 0 || S.copied >= S.need) continue;
+        int take = F.n_rows < S.need - S.copied ? F.n_rows : S.need - S.copied;
+        if (S.J.n_seg < 4) {
+            S.J.seg_row[S.J.n_seg] = (int32_t)F.row_off;
+            S.J.seg_cnt[S.J.n_seg] = take;
+            S.J.n_seg++;
         } else {
-            bad = true;
+            S.bad = true;
         }
-        copied += take;
-        if (copied == need) {
-            if (bad) { atomicExch(err, WIFI_E_OVERFLOW); continue; }
-            int j = atomicAdd(n_jobs, 1);
-            for (int s = J.n_seg; s < 4; ++s) { J.seg_row[s] = 0; J.seg_cnt[s] = 0; }
-            jobs[j] = J;
-            frames[cur].decoded = 1;
-            frames[cur].psdu_off = (int64_t)j * PSDU_STRIDE;
+        S.copied += take;
+        if (S.copied == S.need) {
+            if (S.bad) { atomicExch(err, WIFI_E_OVERFLOW); continue; }
+            for (int s = S.J.n_seg; s < 4; ++s) { S.J.seg_row[s] = 0; S.J.seg_cnt[s] = 0; }
+            bool own = (S.J.n_seg == 1 && fi == S.cur);
+            S.J.need_pack = (!own || (c_tab.mcs[S.J.enc].n_dbps & 7) != 0) ? 1 : 0;
+            jobs[S.cur] = S.J;
+            if (S.J.need_pack) pack_list[atomicAdd(n_pack, 1)] = S.cur;
+            frames[S.cur].decoded = 1;
+            frames[S.cur].psdu_off = (int64_t)S.cur * PSDU_STRIDE;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links, int n_links, wifi_b200_frame *frames, JobDesc *jobs,
+                                               int *pack_list, int *n_pack, int *err)
+{
+    int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (l >= n_links) return;
+    const LinkDesc L = links[l];
+    PlanState S;
+    S.cur = -1; S.copied = 0; S.need = 0; S.pending = -1; S.bad = false; S.J.n_seg = 0;
+    const int fend = L.frame_first + L.frame_count;
+    for (int f0 = L.frame_first; f0 < fend; f0 += 32) {
+        int fi = f0 + lane;
+        bool valid = fi < fend;
+        int sig = 0, nrows = 0, fsym = 0, len = 0, enc = 0;
+        long long row_off = 0;
+        if (valid) {
+            const wifi_b200_frame *F = frames + fi;
+            sig = F->sig_ok; nrows = F->n_rows; fsym = F->frame_symbols; len = F->length; enc = F->encoding; row_off = F->row_off;
+            jobs[fi].n_sym = 0;
+        }
+        bool regular = valid && sig && nrows > 0 && fsym <= WIFI_MAX_SYM && len <= WIFI_MAX_PSDU && nrows >= fsym;
+        bool quiet = !valid || !sig;
+        bool all_simple = __all_sync(0xffffffffu, regular || quiet);
+        if (all_simple && S.pending < 0) {
+            if (regular) {
+                JobDesc J;
+                J.frame = fi; J.enc = enc; J.len = len; J.n_sym = fsym; J.n_seg = 1;
+                J.seg_row[0] = (int32_t)row_off; J.seg_cnt[0] = fsym;
+                for (int s = 1; s < 4; ++s) { J.seg_row[s] = 0; J.seg_cnt[s] = 0; }
+                J.need_pack = (c_tab.mcs[enc].n_dbps & 7) != 0 ? 1 : 0;
+                jobs[fi] = J;
+                if (J.need_pack) pack_list[atomicAdd(n_pack, 1)] = fi;
+                frames[fi].accepted = 1;
+                frames[fi].decoded = 1;
+                frames[fi].psdu_off = (int64_t)fi * PSDU_STRIDE;
+            }
+            unsigned reg = __ballot_sync(0xffffffffu, regular);
+            if (reg) {   // state after the last regular frame: its collection is complete
+                int lastl = 31 - __clz((int)reg);
+                S.cur = f0 + lastl;
+                S.need = __shfl_sync(0xffffffffu, fsym, lastl);
+                S.copied = S.need;
+                S.J.n_seg = 0;
+                S.bad = false;
+            }
+        } else {
+            __syncwarp();   // the jobs[].n_sym = 0 defaults above must land before the sequential writes
+            if (lane == 0) plan_sequential(S, f0, f0 + 32 < fend ? f0 + 32 : fend, frames, jobs, pack_list, n_pack, err);
+            S.cur = __shfl_sync(0xffffffffu, S.cur, 0);
+            S.copied = __shfl_sync(0xffffffffu, S.copied, 0);
+            S.need = __shfl_sync(0xffffffffu, S.need, 0);
+            S.pending = __shfl_sync(0xffffffffu, S.pending, 0);
+            // S.J / S.bad of an open collection live in lane 0 only; lane 0 is the one that continues it
         }
     }
 }
 
 // ------------------------------------------------------------------ R6 unpack/deinterleave/depuncture
+// Only for the jobs k_demod could not pack itself (pack_list): gathered rows, BPSK 3/4.
 // depunct_lut[enc][q] for q in [0, 2*n_dbps): 0xffff = erasure, else (carrier << 3) | bit
-__global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ rows,
-                                               const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in)
+__global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, const int *__restrict__ pack_list, const int *__restrict__ n_pack,
+                                               const uint8_t *__restrict__ rows, const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in)
 {
-    // grid.x over (group, word): blockDim = (32 lanes, 8 words)
-    const int lane = threadIdx.x, group = blockIdx.y;
-    const int w = blockIdx.x * blockDim.y + threadIdx.y;
-    const int job = group * 32 + lane;
-    if (job >= n_jobs) return;
-    const JobDesc J = jobs[job];
-    const int ntb = c_tab.mcs[J.enc].punct == 0 ? 5 : (c_tab.mcs[J.enc].punct == 1 ? 9 : 10);
-    const int n_words = J.len + 2 + ntb;   // trellis words the decoder reads
-    if (w >= n_words) return;
-    const int ndbps = c_tab.mcs[J.enc].n_dbps;
-    const int per = 2 * ndbps;
-    const int n_data = J.n_sym * ndbps;
-    const uint16_t *lut = depunct_lut + J.enc * 432;
-    int tstep = 8 * w;
-    int q = 2 * tstep;
-    int s = q / per, qi = q - s * per;
-    // row of symbol s
-    int seg = 0, sbase = 0;
-    while (seg < J.n_seg - 1 && s >= sbase + J.seg_cnt[seg]) { sbase += J.seg_cnt[seg]; ++seg; }
-    const uint8_t *rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
-    uint32_t word = 0;
+    const int np = *n_pack;
+    for (int e = blockIdx.y; e < np; e += gridDim.y) {
+        const JobDesc J = jobs[pack_list[e]];
+        const int ndbps = c_tab.mcs[J.enc].n_dbps;
+        const int per = 2 * ndbps;
+        const int n_data = J.n_sym * ndbps;
+        const int n_words = (n_data + 7) >> 3;
+        const uint16_t *lut = depunct_lut + J.enc * 432;
+        uint32_t *vw = vit_in + (int64_t)J.frame * VIT_MAXW;
+        for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+            int tstep = 8 * w;
+            int q = 2 * tstep;
+            int s = q / per, qi = q - s * per;
+            int seg = 0, sbase = 0;
+            while (seg < J.n_seg - 1 && s >= sbase + J.seg_cnt[seg]) { sbase += J.seg_cnt[seg]; ++seg; }
+            const uint8_t *rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
+            uint32_t word = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        uint32_t sym = 0;
-        if (tstep + (k >> 1) < n_data) {
-            uint16_t e = lut[qi];
-            sym = (e == 0xffffu) ? 2u : ((rp[e >> 3] >> (e & 7)) & 1u);
-        }
-        word |= sym << (2 * k);
-        if (++qi == per) {
-            qi = 0;
-            ++s;
-            if (s - sbase >= J.seg_cnt[seg] && seg < J.n_seg - 1) { sbase += J.seg_cnt[seg]; ++seg; }
-            rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
+            for (int k = 0; k < 16; ++k) {
+                uint32_t sym = 0;
+                if (tstep + (k >> 1) < n_data) {
+                    uint16_t en = lut[qi];
+                    sym = (en == 0xffffu) ? 2u : ((rp[en >> 3] >> (en & 7)) & 1u);
+                }
+                word |= sym << (2 * k);
+                if (++qi == per) {
+                    qi = 0;
+                    ++s;
+                    if (s - sbase >= J.seg_cnt[seg] && seg < J.n_seg - 1) { sbase += J.seg_cnt[seg]; ++seg; }
+                    rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
+                }
+            }
+            vw[w] = word;
         }
     }
-    vit_in[((int64_t)group * VIT_MAXW + w) * 32 + lane] = word;
 }
 
 // ------------------------------------------------------------------ R6a-c Viterbi + descramble + CRC
-__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict__ jobs, int n_jobs, const uint32_t *__restrict__ vit_in,
+// One thread per frame slot; jobs[frame].n_sym == 0 means nothing to decode.  Trellis words of the
+// frame are contiguous (vit_in[frame][w]); words past the coded data read as 0 (oracle note 2).
+__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict__ jobs, int n_frames, const uint32_t *__restrict__ vit_in,
                                                         uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
 {
     extern __shared__ uint32_t vsm[];
@@ -681,10 +810,13 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
     __syncthreads();
     const int job = blockIdx.x * VIT_BLOCK + tid;
-    if (job >= n_jobs) return;
+    if (job >= n_frames) return;
     const JobDesc J = jobs[job];
-    const int ntb = c_tab.mcs[J.enc].punct == 0 ? 5 : (c_tab.mcs[J.enc].punct == 1 ? 9 : 10);
-    const uint32_t *in = vit_in + ((int64_t)(job >> 5) * VIT_MAXW) * 32 + (job & 31);
+    if (J.n_sym == 0) return;
+    const int punct = c_tab.mcs[J.enc].punct;
+    const int ntb = punct == 0 ? 5 : (punct == 1 ? 9 : 10);
+    const int nw = (J.n_sym * c_tab.mcs[J.enc].n_dbps + 7) >> 3;
+    const uint32_t *in = vit_in + (int64_t)job * VIT_MAXW;
     uint32_t *out = psdu + (int64_t)job * (PSDU_STRIDE / 4);
     const int L = J.len;
     const int last_chunk = L + 1 + ntb;   // chunk whose traceback yields PSDU byte L-1
@@ -696,12 +828,12 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     int slot = 1 % ntb;
     v.end_chunk(ring, slot, ntb, tid);
     uint32_t state = 0, crc = 0xffffffffu, accw = 0;
-    uint32_t next = in[32];
+    uint32_t next = 1 < nw ? in[1] : 0u;
 #pragma unroll 1
     for (int chunk = 1; chunk <= last_chunk; ++chunk) {
         uint32_t bits = __funnelshift_r(prev, next, 24);
         prev = next;
-        next = (chunk + 1 <= last_chunk) ? in[(int64_t)(chunk + 1) * 32] : 0u;
+        next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k) v.step((bits >> (4 * k)) & 0xfu);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;

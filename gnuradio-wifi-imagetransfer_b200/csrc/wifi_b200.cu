@@ -143,7 +143,8 @@ void build_tables(DevTables &t, std::vector<uint16_t> &depunct)
 enum { ST_H2D = 0, ST_DETECT, ST_SELECT, ST_SYNC_LONG, ST_DEMOD_HEAD, ST_SIGNAL, ST_DEMOD_DATA, ST_PLAN, ST_PACK, ST_VITERBI, ST_D2H, ST_COUNT };
 const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "demod_head", "signal", "demod_data", "plan", "pack", "viterbi", "d2h"};
 
-#define MAX_LINKS 65536
+#define MAX_LINKS 16384
+#define DET_SMEM (DET_ROWS * 65 * (int)sizeof(cf))
 
 } // namespace
 
@@ -155,7 +156,11 @@ struct wifi_b200 {
     std::string err;
     // device workspace
     cf *d_iq = nullptr;            // staging for host input (max_samples + history)
-    uint32_t *d_flags = nullptr;
+    uint32_t *d_flags = nullptr;      // 1 bit per sample: c[n] > threshold
+    uint32_t *d_summary = nullptr;    // 1 bit per FE_CHUNK chunk: any flag set
+    int2 *d_trig_tmp = nullptr;       // k_select scratch: (trigger, burst_len) per link
+    int *d_pack_list = nullptr;       // frames whose trellis words k_pack must build
+    int64_t tile_cap = 0;
     LinkDesc *d_links = nullptr;
     wifi_b200_frame *d_frames = nullptr;
     EqState *d_states = nullptr;
@@ -165,7 +170,7 @@ struct wifi_b200 {
     uint32_t *d_vit_in = nullptr;
     uint32_t *d_psdu = nullptr;
     uint16_t *d_depunct = nullptr;
-    int *d_counters = nullptr;     // [0] frames [1] jobs [2] err ; +8 bytes: row counter (u64)
+    int *d_counters = nullptr;     // [0] frames [1] pack-list length [2] err ; ints 8..9: row counter (u64)
     int *h_counters = nullptr;     // pinned mirror
     int64_t row_cap = 0;
     // tx workspace
@@ -233,7 +238,7 @@ void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
-                    h->d_psdu, h->d_depunct, h->d_counters, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
+                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_frames) cudaFreeHost(h->h_frames);
@@ -259,17 +264,20 @@ void mark(wifi_b200 *h, int i)
 int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming: newest burst not complete yet */)
 {
     const int n_links = (int)h->h_links.size();
-    int64_t total_chunks = 0, total = 0;
+    int64_t total_tiles = 0, total = 0;
     for (auto &L : h->h_links) {
-        L.chunk_base = total_chunks;
-        total_chunks += (L.len + FE_CHUNK - 1) / FE_CHUNK;
+        L.chunk_base = total_tiles * DET_THREADS;
+        total_tiles += (L.len + DET_TILE - 1) / DET_TILE;
         total += L.len;
     }
+    if (total_tiles > h->tile_cap) { h->err = "tile capacity exceeded (too many short links)"; return WIFI_E_OVERFLOW; }
     h->cur_iq = iq;
     h->n_frames = h->n_jobs = h->n_rows = 0;
     h->n_samples = total;
     h->host_mirror = false;
+    bool h2d_marked = h->ev_used[ST_H2D];
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
+    h->ev_used[ST_H2D] = h2d_marked;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     const double thr = h->cfg.sensitivity;
     float thr_f = (float)thr;   // (double)c > thr  <=>  c > largest float <= thr
@@ -278,12 +286,12 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
     CK(cudaMemcpyAsync(h->d_links, h->h_links.data(), n_links * sizeof(LinkDesc), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(h->d_counters, 0, 64, s));
     mark(h, ST_DETECT);
-    if (total_chunks > 0)
-        k_detect<<<(unsigned)((total_chunks + 127) / 128), 128, 0, s>>>(iq, h->d_links, n_links, total_chunks, thr_f, h->d_flags);
+    if (total_tiles > 0)
+        k_detect<<<(unsigned)total_tiles, DET_THREADS, DET_SMEM, s>>>(iq, h->d_links, n_links, total_tiles, thr_f, h->d_flags, h->d_summary);
     mark(h, ST_SELECT);
-    k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_links, n_links, h->d_frames, h->d_counters,
+    k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->d_frames, h->d_counters,
                                                         (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
-                                                        h->cfg.min_plateau, h->d_counters + 2);
+                                                        h->cfg.min_plateau, h->d_counters + 2, h->d_trig_tmp);
     mark(h, ST_SYNC_LONG);
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -309,35 +317,27 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
         CK(cudaMemcpyAsync(h->d_links, &tmp, sizeof tmp, cudaMemcpyHostToDevice, s));
     }
     h->n_frames = nf;
+    h->n_jobs = nf;       // decode jobs live at the index of their owner frame
     h->n_rows = rows_needed;
     if (nf > 0) {
         DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier};
         k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf);
         mark(h, ST_DEMOD_HEAD);
-        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 0);
+        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 0,
+                                                          h->d_depunct, h->d_vit_in);
         mark(h, ST_SIGNAL);
         k_signal<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, 0, s>>>(h->d_frames, (int)nf, h->d_states);
         mark(h, ST_DEMOD_DATA);
-        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1);
+        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1,
+                                                          h->d_depunct, h->d_vit_in);
         mark(h, ST_PLAN);
-        k_plan<<<(n_links + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_counters + 1, h->d_counters + 2);
+        k_plan<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_pack_list, h->d_counters + 1,
+                                                          h->d_counters + 2);
         mark(h, ST_PACK);
-        CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (h->h_counters[2] != 0) {
-            h->err = "decode_mac symbol collection spans more than 4 bursts";
-            return WIFI_E_OVERFLOW;
-        }
-        int64_t nj = h->h_counters[1];
-        h->n_jobs = nj;
-        if (nj > 0) {
-            int groups = (int)((nj + 31) / 32);
-            dim3 pb(32, 8), pg((WIFI_MAX_PSDU + 2 + VIT_NTB_MAX + 7) / 8, groups);
-            k_pack<<<pg, pb, 0, s>>>(h->d_jobs, (int)nj, h->d_rows, h->d_depunct, h->d_vit_in);
-            mark(h, ST_VITERBI);
-            size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256;
-            k_viterbi<<<(unsigned)((nj + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nj, h->d_vit_in, h->d_psdu, h->d_frames);
-        }
+        k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in);
+        mark(h, ST_VITERBI);
+        size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256;
+        k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
     }
     mark(h, ST_D2H);
     if (mirror && h->n_triggers > 0) {
@@ -345,8 +345,13 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
         if (h->n_jobs > 0) CK(cudaMemcpyAsync(h->h_psdu, h->d_psdu, (size_t)h->n_jobs * PSDU_STRIDE, cudaMemcpyDeviceToHost, s));
     }
     mark(h, ST_COUNT);
+    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    if (h->h_counters[2] != 0) {
+        h->err = "decode_mac symbol collection spans more than 4 bursts";
+        return WIFI_E_OVERFLOW;
+    }
     h->host_mirror = mirror;
     // stage times: difference between consecutive recorded events
     int prev = -1;
@@ -459,18 +464,23 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
     for (int i = 0; i <= ST_COUNT; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) return fail(WIFI_E_CUDA);
     if (upload_tables(h) != WIFI_OK) return fail(WIFI_E_CUDA);
+    if (cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM) != cudaSuccess) return fail(WIFI_E_CUDA);
     const int64_t S = cfg.max_samples, Fm = cfg.max_frames;
     h->row_cap = S / 80 + Fm + 64;
     bool ok = true;
     auto A = [&](void **p, size_t bytes) { if (ok && cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) ok = false; };
-    A((void **)&h->d_flags, (size_t)(S / FE_CHUNK + MAX_LINKS + 1) * 16);
+    h->tile_cap = S / DET_TILE + MAX_LINKS + 1;
+    A((void **)&h->d_flags, (size_t)h->tile_cap * DET_THREADS * 8);
+    A((void **)&h->d_summary, (size_t)h->tile_cap * (DET_THREADS / 32) * 4 + 256);
+    A((void **)&h->d_trig_tmp, (size_t)h->tile_cap * (DET_THREADS / 4) * sizeof(int2));
+    A((void **)&h->d_pack_list, (size_t)Fm * sizeof(int));
     A((void **)&h->d_links, (size_t)MAX_LINKS * sizeof(LinkDesc));
     A((void **)&h->d_frames, (size_t)Fm * sizeof(wifi_b200_frame));
     A((void **)&h->d_states, (size_t)Fm * sizeof(EqState));
     A((void **)&h->d_rows, (size_t)h->row_cap * 48);
     if (cfg.want_carrier) A((void **)&h->d_carrier, (size_t)h->row_cap * 48 * sizeof(cf));
     A((void **)&h->d_jobs, (size_t)Fm * sizeof(JobDesc));
-    A((void **)&h->d_vit_in, (size_t)((Fm + 31) / 32) * VIT_MAXW * 32 * 4);
+    A((void **)&h->d_vit_in, (size_t)Fm * VIT_MAXW * 4);
     A((void **)&h->d_psdu, (size_t)Fm * PSDU_STRIDE);
     A((void **)&h->d_counters, 64);
     if (!ok) return fail(WIFI_E_NOMEM);
@@ -675,6 +685,7 @@ int wifi_b200_rx_batch_dev(wifi_b200_t *h, const float *iq_dev, const uint64_t *
     cudaSetDevice(h->device);
     int rc = set_links(h, link_off, n_links, final);
     if (rc) return rc;
+    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
     rc = run_rx(h, (const cf *)iq_dev, false, false);
     return rc;
 }
@@ -693,7 +704,7 @@ int wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *lin
     int64_t total = (int64_t)(link_off[n_links] - base);
     for (auto &L : h->h_links) L.x_off -= (int64_t)base;
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
-    cudaEventRecord(h->ev[ST_H2D], h->stream);
+    mark(h, ST_H2D);
     CK(cudaMemcpyAsync(h->d_iq, iq_host + 2 * base, (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
     rc = run_rx(h, h->d_iq, true, false);
     if (rc) return rc;
@@ -801,6 +812,7 @@ int wifi_b200_rx_push(wifi_b200_t *h, const float *iq, size_t n, int flush)
     L.min_pos = h->s_prev_trigger >= 0 ? h->s_prev_trigger + SS_MIN_GAP + 1 - h->s_abs0 : 0;
     // the newest burst is held back unless flushing: its end is not known before the next
     // trigger arrives (sync_short retrigger / sync_long RESET decide its length)
+    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
     rc = run_rx(h, h->d_iq, true, flush == 0);
     if (rc) return rc;
     update_stats(h);

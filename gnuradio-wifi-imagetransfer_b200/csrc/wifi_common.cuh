@@ -14,7 +14,9 @@
 #define SS_MIN_GAP 480          // [UPSTREAM] sync_short.cc MIN_GAP
 #define SS_MAX_SAMPLES 43200    // [UPSTREAM] sync_short.cc MAX_SAMPLES = 540*80
 #define SYNC_LENGTH 320         // wifi_phy_hier.grc:698-715 sync_length
-#define FE_CHUNK 128            // running-sum re-seed period of the front-end
+#define FE_CHUNK 64             // running-sum re-seed period of the front-end
+#define DET_THREADS 128         // k_detect: one thread per chunk, one block per tile
+#define DET_TILE (DET_THREADS * FE_CHUNK)   // 8192 samples
 #define PSDU_STRIDE 1536        // bytes reserved per decode job in the psdu store
 #define VIT_MAXW 1560           // 32-bit words (8 trellis steps each) reserved per decode job
 
@@ -61,7 +63,7 @@ __constant__ DevTables c_tab;   // single translation unit (wifi_b200.cu)
 struct LinkDesc {
     int64_t x_off;        // first sample of the link in the iq buffer
     int64_t len;          // samples
-    int64_t chunk_base;   // first FE_CHUNK chunk (prefix sum over links)
+    int64_t chunk_base;   // first FE_CHUNK chunk of the link (links start on a DET_TILE tile: multiple of DET_THREADS)
     int32_t frame_first;  // first frame record of the link
     int32_t frame_count;
     float fo_carry;       // sync_long d_freq_offset entering this buffer
@@ -81,13 +83,14 @@ struct EqState {
     uint8_t sig_bits[48];
 };
 
+// decode job, stored at the index of its owner (tag) frame; n_sym == 0: no job
 struct JobDesc {
     int32_t frame;        // owner (tag) frame
     int32_t enc, len, n_sym;
     int32_t n_seg;
     int32_t seg_row[4];   // first row of each segment
     int32_t seg_cnt[4];   // rows in each segment
-    int32_t pad;
+    int32_t need_pack;    // trellis words not already written by k_demod (gathered rows, BPSK 3/4)
 };
 
 __device__ __forceinline__ int dev_decide(int nb, cf s)

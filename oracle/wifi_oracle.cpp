@@ -18,7 +18,7 @@
  *  (1) GNU Radio's moving_average re-seeds its running sum at every work() call
  *      (<= max_iter=4000 outputs, wifi_phy_hier.grc:210,230), so upstream output
  *      depends on scheduler chunking.  The oracle fixes the chunking: re-seed at
- *      every absolute sample index that is a multiple of 128.
+ *      every absolute sample index that is a multiple of 64.
  *  (2) viterbi_decoder::decode [UP] keeps clocking the trellis ntraceback bytes
  *      past the end of the coded frame and so reads stale bytes of its input
  *      buffers.  A freshly constructed block holds zeros there; the oracle
@@ -511,7 +511,7 @@ struct FrontEnd {
     }
     inline void step(int64_t i, cf &a, float &p, float &c)
     {
-        if ((i & 127) == 0) seed(i);
+        if ((i & 63) == 0) seed(i);
         cf pr = prod(i);
         sar += pr.re;
         sai += pr.im;
