@@ -38,7 +38,7 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
 // no-op (x + 0 == x), so the inner loop is branch free.
 #define DET_ROWS (DET_THREADS + 2)
 #define DET_IDX(q) ((q) + ((q) >> 6))     // row * 65 + col
-__global__ void __launch_bounds__(DET_THREADS) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
+__global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
                                                          int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
                                                          uint32_t *__restrict__ summary)
 {
@@ -58,26 +58,29 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const cf *__restrict__ i
         sx[DET_IDX(q)] = v;
     }
     __syncthreads();
-    const int q0 = (tid + 2) * FE_CHUNK;   // tile-local index of this thread's first sample
+    // this thread's chunk is row tid+2 of the padded tile: element c of the chunk (c may be negative,
+    // reaching into the previous rows) sits at base + c + floor(c / 64); with the loops unrolled
+    // every shared-memory address is base + an immediate
+    const cf *base = sx + (tid + 2) * (FE_CHUNK + 1);
+#define DET_AT(c) base[(c) + ((c) >> 6)]
     uint32_t w0 = 0u, w1 = 0u;
     if (T0 + (int64_t)tid * FE_CHUNK < hi) {
         float sar = 0.f, sai = 0.f, sp = 0.f;
-#pragma unroll 1
+#pragma unroll
         for (int k = 47; k >= 1; --k) {
-            cf a = sx[DET_IDX(q0 - k)], d = sx[DET_IDX(q0 - k - 16)];
+            cf a = DET_AT(-k), d = DET_AT(-k - 16);
             sar += a.re * d.re + a.im * d.im;
             sai += a.im * d.re - a.re * d.im;
         }
-#pragma unroll 1
+#pragma unroll
         for (int k = 63; k >= 1; --k) {
-            cf a = sx[DET_IDX(q0 - k)];
+            cf a = DET_AT(-k);
             sp += a.re * a.re + a.im * a.im;
         }
         const float thr2 = thr_f * thr_f;
-#pragma unroll 4
+#pragma unroll
         for (int i = 0; i < FE_CHUNK; ++i) {
-            const int q = q0 + i;
-            cf xn = sx[DET_IDX(q)], xd = sx[DET_IDX(q - 16)], xo = sx[DET_IDX(q - 47)], xod = sx[DET_IDX(q - 63)];
+            cf xn = DET_AT(i), xd = DET_AT(i - 16), xo = DET_AT(i - 47), xod = DET_AT(i - 63);
             sar += xn.re * xd.re + xn.im * xd.im;
             sai += xn.im * xd.re - xn.re * xd.im;
             const float ar = sar, ai = sai;
@@ -88,14 +91,16 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect(const cf *__restrict__ i
             sp -= xod.re * xod.re + xod.im * xod.im;
             const float m2 = ar * ar + ai * ai;
             // c = sqrt(m2)/p > thr.  Decide from the squares when the margin (1e-4) dwarfs the rounding
-            // of the exact expression (< 3e-7); evaluate the oracle's expression only inside the margin.
+            // of the exact expression (< 3e-7); evaluate the oracle's expression only inside the margin
+            // or when p is outside the range where the squares are safe.
             const float t2 = thr2 * (p * p);
-            bool over;
-            if (p > 0.f && t2 > 1e-30f && t2 < 1e30f && m2 > 1e-30f && (m2 > t2 * 1.0001f || m2 < t2 * 0.9999f)) over = m2 > t2;
-            else over = (sqrtf(m2) / p) > thr_f;
-            if (over) { if (i < 32) w0 |= 1u << i; else w1 |= 1u << (i - 32); }
+            bool over = m2 > t2;
+            const bool sure = (p > 1e-12f) && (p < 1e12f) && ((m2 > t2 * 1.0001f) || (m2 < t2 * 0.9999f));
+            if (!sure) over = (sqrtf(m2) / p) > thr_f;
+            if (over) { if (i < 32) w0 |= 1u << (i & 31); else w1 |= 1u << (i & 31); }
         }
     }
+#undef DET_AT
     const int64_t chunk = tile * DET_THREADS + tid;
     reinterpret_cast<uint2 *>(flags)[chunk] = make_uint2(w0, w1);
     uint32_t any = __ballot_sync(0xffffffffu, (w0 | w1) != 0u);
@@ -364,6 +369,7 @@ __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const 
     const int carA = c_tab.carrier_of[iA], carB = c_tab.carrier_of[iB];
     const float ltsA = c_tab.lts[iA], ltsB = c_tab.lts[iB];
     const int q0 = 2 * dev_bitrev5(lane);
+    const WarpTw tw = warp_tw(lane, false);
 
     cf HA = {0.f, 0.f}, HB = {0.f, 0.f};
     cf pp[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const 
     const int ndbps = c_tab.mcs[enc].n_dbps;
     const int wps = (phase == 1 && (ndbps & 7) == 0) ? ndbps >> 3 : 0;
     if (wps) {
-        for (int i = lane; i < 2 * ndbps; i += 32) s_lut[wib][i] = depunct_lut[enc * 432 + i];
+        for (int i = lane; i < 2 * ndbps; i += 32) s_lut[wib][(i & 15) * 27 + (i >> 4)] = depunct_lut[enc * 432 + i];   // [k][word]: conflict-free reads
         __syncwarp();
     }
     uint32_t *vw = vit_in + (int64_t)f * VIT_MAXW;
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const 
             }
             a = v[0]; b = v[1];
         }
-        warp_fft64(a, b, lane, false);
+        warp_fft64(a, b, lane, tw);
         // a = cur[iA], b = cur[iB] (fftshift)
         {
             double k = 2 * M_PI * n * 80 * (eps0 + d_er);
@@ -506,18 +512,18 @@ __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const 
                 symA = cdiv(a, HA);
                 bitsA = dev_decide(nb, symA);
                 if (prm.algo == WIFI_EQ_LMS) {
-                    cf q = cdiv(a, c_tab.cons[enc][bitsA]);
+                    cf q = cdiv(a, dev_point(nb, bitsA));
                     HA = cadd(cscale(HA, 0.5f), cscale(q, 0.5f));
-                } else if (prm.algo == WIFI_EQ_STA) huA = cdiv(a, c_tab.cons[enc][bitsA]);
+                } else if (prm.algo == WIFI_EQ_STA) huA = cdiv(a, dev_point(nb, bitsA));
             } else if (iA == 39) huA = cscale(a, p);
             else if (iA == 53) huA = cscale(a, -p);
             if (carB >= 0) {
                 symB = cdiv(b, HB);
                 bitsB = dev_decide(nb, symB);
                 if (prm.algo == WIFI_EQ_LMS) {
-                    cf q = cdiv(b, c_tab.cons[enc][bitsB]);
+                    cf q = cdiv(b, dev_point(nb, bitsB));
                     HB = cadd(cscale(HB, 0.5f), cscale(q, 0.5f));
-                } else if (prm.algo == WIFI_EQ_STA) huB = cdiv(b, c_tab.cons[enc][bitsB]);
+                } else if (prm.algo == WIFI_EQ_STA) huB = cdiv(b, dev_point(nb, bitsB));
             } else if (iB == 11 || iB == 25) huB = cscale(b, p);
             if (prm.algo == WIFI_EQ_STA) {
                 s_hu[wib][iA] = huA; s_hu[wib][iB] = huB;
@@ -558,7 +564,7 @@ __global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const 
                         uint32_t word = 0;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
-                            uint32_t e = s_lut[wib][16 * lane + k];
+                            uint32_t e = s_lut[wib][k * 27 + lane];
                             uint32_t sym = (e == 0xffffu) ? 2u : ((s_bits[wib][e >> 3] >> (e & 7)) & 1u);
                             word |= sym << (2 * k);
                         }
@@ -837,7 +843,7 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
 #pragma unroll
         for (int k = 0; k < 8; ++k) v.step((bits >> (4 * k)) & 0xfu);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
-        uint32_t c = v.end_chunk(ring, slot, ntb, tid);
+        uint32_t c = v.end_chunk(ring, slot, ntb, tid, (chunk & 3) == 0);
         if (chunk >= ntb) {
             int m = chunk - ntb;   // decoded byte index
             if (m == 0) {

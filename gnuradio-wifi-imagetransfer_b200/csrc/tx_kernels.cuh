@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(128) k_tx(const uint8_t *__restrict__ psdu_blo
     const int total_syms = 5 + n_sym;
     cf *o = out + D.burst_off;
     const int q0 = 2 * dev_bitrev5(lane);
+    const WarpTw tw = warp_tw(lane, true);
     for (int s = wib; s < total_syms; s += 4) {
         cf v[2];
 #pragma unroll
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(128) k_tx(const uint8_t *__restrict__ psdu_blo
             v[u] = cscale(X, c_tab.win);
         }
         cf a = v[0], b = v[1];
-        warp_fft64(a, b, lane, true);
+        warp_fft64(a, b, lane, tw);
         cf *os = o + (int64_t)s * 80;
         os[16 + lane] = a;
         os[48 + lane] = b;

@@ -56,12 +56,11 @@ struct VitCore {
         const uint32_t t1 = (s1 == 2u) ? 0u : (s1 ? 0x00010001u : 0x01000100u);
         const uint32_t T = t0 + t1;                                     // disagreements per (A,B)
         const uint32_t E = ((s0 != 2u) ? 0x01010101u : 0u) + ((s1 != 2u) ? 0x01010101u : 0u);
-        const uint32_t T2 = E - T;                                      // agreements per (A,B)
         uint32_t Mn[16], Pn[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint32_t sel = vit_sel(j);
-            const uint32_t svm = prmt(T, 0u, sel), sv = prmt(T2, 0u, sel);
+            const uint32_t svm = prmt(T, 0u, sel), sv = E - svm;   // agreements = available symbols - disagreements
             const uint32_t lo = M[j], hi = M[j + 8];
             const uint32_t m0 = lo + sv, m1 = hi + svm, m2 = lo + svm, m3 = hi + sv;
             const uint32_t k0 = prmt(m0 + 0x7f7f7f7fu - m1, 0u, 0xba98u); // 0xff where m0 > m1
@@ -95,17 +94,15 @@ struct VitCore {
     // viterbi_get_output_generic: snapshot the paths into ring slot `slot`, find the first
     // best state, trace back ntb-1 snapshots, return that snapshot's path byte, renormalise
     // the metrics by their minimum and clear the path registers.
-    __device__ __forceinline__ uint32_t end_chunk(uint32_t *ring, int slot, int ntb, int tid)
+    __device__ __forceinline__ uint32_t end_chunk(uint32_t *ring, int slot, int ntb, int tid, bool renorm = true)
     {
 #pragma unroll
         for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = P[w];
-        uint32_t mx = M[0], mn = M[0];
+        uint32_t mx = M[0];
 #pragma unroll
-        for (int w = 1; w < 16; ++w) { mx = vmax4(mx, M[w]); mn = vmin4(mn, M[w]); }
+        for (int w = 1; w < 16; ++w) mx = vmax4(mx, M[w]);
         mx = vmax4(mx, mx >> 16); mx = vmax4(mx, mx >> 8);
-        mn = vmin4(mn, mn >> 16); mn = vmin4(mn, mn >> 8);
         const uint32_t bestw = (mx & 0xffu) * 0x01010101u;
-        const uint32_t minw = (mn & 0xffu) * 0x01010101u;
         // first state whose metric equals the maximum
         int wsel = 0;
         uint32_t zsel = 0;
@@ -124,8 +121,19 @@ struct VitCore {
         }
         uint32_t w = ring[(sl * 16 + (bs >> 2)) * VIT_BLOCK + tid];
         uint32_t c = (w >> (8 * (bs & 3))) & 0xffu;
+        // upstream subtracts the minimum after every chunk; only metric differences matter, so the
+        // subtraction may be skipped as long as bytes stay below 0x80 (spread <= 12, +16 per chunk)
+        if (renorm) {
+            uint32_t mn = M[0];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { M[i] -= minw; P[i] = 0; }
+            for (int w = 1; w < 16; ++w) mn = vmin4(mn, M[w]);
+            mn = vmin4(mn, mn >> 16); mn = vmin4(mn, mn >> 8);
+            const uint32_t minw = (mn & 0xffu) * 0x01010101u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) M[i] -= minw;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P[i] = 0;
         return c;
     }
 };

@@ -118,16 +118,34 @@ __device__ __forceinline__ int dev_decide(int nb, cf s)
 
 __device__ __forceinline__ int dev_bitrev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
 
+// Per-lane twiddles of the warp FFT, fetched once per kernel (the table index depends on the
+// lane, so reading c_tab inside the symbol loop would serialise in the constant cache).
+struct WarpTw { cf w[6]; };
+__device__ __forceinline__ WarpTw warp_tw(int lane, bool inverse)
+{
+    WarpTw t;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int half = 1 << s;
+        t.w[s] = c_tab.tw[(lane & (half - 1)) * (32 >> s)];
+    }
+    t.w[5] = c_tab.tw[lane];
+    if (inverse) {
+#pragma unroll
+        for (int s = 0; s < 6; ++s) t.w[s].im = -t.w[s].im;
+    }
+    return t;
+}
+
 // 64-point FFT across one warp.  On entry lane l holds in[2*bitrev5(l)] (a) and
 // in[2*bitrev5(l)+1] (b) -- i.e. DIT positions l and l+32 after bit reversal.  On
 // exit a = X[l], b = X[l+32].  Same butterfly network and rounding as oracle fft64().
-__device__ __forceinline__ void warp_fft64(cf &a, cf &b, int lane, bool inverse)
+__device__ __forceinline__ void warp_fft64(cf &a, cf &b, int lane, const WarpTw &tw)
 {
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
         const int half = 1 << s;
-        cf w = c_tab.tw[(lane & (half - 1)) * (32 >> s)];
-        if (inverse) w.im = -w.im;
+        const cf w = tw.w[s];
         const bool hi = (lane & half) != 0;
         cf ta = hi ? cmul(w, a) : a;
         cf tb = hi ? cmul(w, b) : b;
@@ -136,10 +154,26 @@ __device__ __forceinline__ void warp_fft64(cf &a, cf &b, int lane, bool inverse)
         a = hi ? csub(ra, ta) : cadd(a, ra);
         b = hi ? csub(rb, tb) : cadd(b, rb);
     }
-    cf w = c_tab.tw[lane];
-    if (inverse) w.im = -w.im;
-    cf t = cmul(w, b);
+    cf t = cmul(tw.w[5], b);
     cf u = a;
     a = cadd(u, t);
     b = csub(u, t);
+}
+
+// constellation point of a decided index, computed exactly as the table is built
+// ((float)(+-magnitude) * level), so no lane-divergent constant-memory lookup is needed
+__device__ __forceinline__ cf dev_point(int nb, int v)
+{
+    if (nb == 1) return {v ? 1.f : -1.f, 0.f};
+    const int h = nb >> 1;
+    const float level = (h == 1) ? sqrtf(0.5f) : (h == 2) ? sqrtf(0.1f) : sqrtf(1.0f / 42.0f);
+    int ax[2] = {v & ((1 << h) - 1), v >> h};
+    float o[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        int b0 = ax[u] & 1, b1 = (ax[u] >> 1) & 1, b2 = (ax[u] >> 2) & 1;
+        int mag = (h == 1) ? 1 : (h == 2) ? (b1 ? 1 : 3) : (b1 ? (b2 ? 3 : 1) : (b2 ? 5 : 7));
+        o[u] = (float)(b0 ? mag : -mag) * level;
+    }
+    return {o[0], o[1]};
 }
