@@ -1,0 +1,139 @@
+"""Known-answer tests that pin the oracle: IEEE 802.11-2012 Annex L (802.11a Annex G) example
+values and the constants written in the reference's wifi_phy_hier.grc (tests/golden/)."""
+import json
+import os
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "hier_constants.json")))
+
+
+def test_signal_field_annex_g(O):
+    # 36 Mb/s, LENGTH 100 (Annex G.4): RATE 1011, interleaved SIGNAL bits
+    want = "100101001101000000010100100000110010010010010100"
+    assert "".join(map(str, O.signal_field(5, 100))) == want
+    bits = np.array([1, 0, 1, 1, 0, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0], np.uint8)
+    enc = "110100011010000100000010001111100111000000000000"
+    assert "".join(map(str, O.conv_encode(bits))) == enc
+
+
+def test_scrambler_sequences(O):
+    z = np.zeros(127, np.uint8)
+    seq = "".join(map(str, O.scramble(z, 0x7f)))
+    assert seq == ("00001110" "11110010" "11001001" "00000010" "00100110" "00101110" "10110110" "00001100"
+                   "11010100" "11100111" "10110100" "00101010" "11111010" "01010001" "10111000" "1111111")
+    assert "".join(map(str, O.scramble(z[:16], 0b1011101))) == "0110110000011001"
+    # periodicity 127 and involution
+    x = np.random.default_rng(0).integers(0, 2, 1000, dtype=np.uint8)
+    assert np.array_equal(O.scramble(O.scramble(x, 55), 55), x)
+
+
+def test_pilot_polarity_matches_reference_grc(O):
+    pol = O.polarity()
+    ref = np.array([p[0] for p in GOLD["pilot_symbols"]], np.float32)
+    assert np.array_equal(pol, ref)
+    assert all(tuple(p) == (p[0], p[0], p[0], -p[0]) for p in GOLD["pilot_symbols"])
+    assert GOLD["pilot_carriers"] == [[-21, -7, 7, 21]]
+
+
+def test_carrier_map_and_sync_words_match_reference_grc(O):
+    occ = GOLD["occupied_carriers"][0]
+    assert occ == [k for k in range(-26, 27) if k not in (-21, -7, 0, 7, 21)] and len(occ) == 48
+    sw = [np.array([complex(a, b) for a, b in w]) for w in GOLD["sync_words"]]
+    lts = O.lts_freq().astype(np.float64)
+    assert np.array_equal(sw[3].real, lts) and not sw[3].imag.any()
+    k = np.arange(64) - 32
+    assert np.allclose(sw[2], lts * (-1j) ** k, atol=1e-12)
+    assert np.array_equal(sw[0], sw[1])
+    # first four OFDM symbols of any frame = IFFT of the four sync words (window 1/sqrt(52))
+    iq = O.tx_frame(bytes(40), 0, 1).astype(np.complex128)
+    for s in range(4):
+        t = np.fft.ifft(np.fft.ifftshift(sw[s])) * 64 / np.sqrt(52)
+        assert np.allclose(iq[80 * s + 16:80 * s + 80], t, atol=2e-6), s
+
+
+def test_preamble_time_domain_annex_g(O):
+    # Annex G tables G.4 / G.6 are normalised by 1/64 where GNU Radio uses 1/sqrt(52)
+    s = O.tx_frame(bytes(100), 0, 1) * np.sqrt(52) / 64
+    sts = [0.046 + 0.046j, -0.132 + 0.002j, -0.013 - 0.079j, 0.143 - 0.013j, 0.092 + 0.000j, 0.143 - 0.013j, -0.013 - 0.079j,
+           -0.132 + 0.002j, 0.046 + 0.046j, 0.002 - 0.132j, -0.079 - 0.013j, -0.013 + 0.143j, 0.000 + 0.092j, -0.013 + 0.143j,
+           -0.079 - 0.013j, 0.002 - 0.132j]
+    assert np.abs(s[1:16] - np.array(sts[1:])).max() < 8e-4
+    assert abs(s[0] - sts[0] / 2) < 8e-4                      # windowed first sample 0.023+0.023j
+    gi2 = [0.012 - 0.098j, 0.092 - 0.106j, -0.092 - 0.115j, -0.003 - 0.054j, 0.075 + 0.074j, -0.127 + 0.021j, -0.122 + 0.017j,
+           -0.035 + 0.151j, -0.056 + 0.022j, -0.060 - 0.081j, 0.070 - 0.014j, 0.082 - 0.092j, -0.131 - 0.065j, -0.057 - 0.039j,
+           0.037 - 0.098j, 0.062 + 0.062j]
+    assert np.abs(s[161:177] - np.array(gi2)).max() < 8e-4
+    t1 = [0.156 + 0.000j, -0.005 - 0.120j, 0.040 - 0.111j, 0.097 + 0.083j, 0.021 + 0.028j, 0.060 - 0.088j, -0.115 - 0.055j,
+          -0.038 - 0.106j, 0.098 - 0.026j, 0.053 + 0.004j, 0.001 - 0.115j, -0.137 - 0.047j, 0.024 - 0.059j, 0.059 - 0.015j,
+          -0.022 + 0.161j, 0.119 - 0.004j, 0.062 - 0.062j]
+    assert np.abs(s[192:209] - np.array(t1)).max() < 8e-4
+    assert np.abs(s[256:273] - np.array(t1)).max() < 8e-4
+
+
+def test_long_taps_match_upstream_values(O):
+    # [UPSTREAM] sync_long.cc LONG[]: first eight and last two entries
+    t = O.long_taps()
+    first = [-0.0455 - 1.0679j, 0.3528 - 0.9865j, 0.8594 + 0.7348j, 0.1874 + 0.2475j, 0.5309 - 0.7784j, -1.0218 - 0.4897j,
+             -0.3401 - 0.9423j, 0.8657 - 0.2298j]
+    assert np.allclose(t[:8], first, atol=1e-6)
+    assert np.allclose(t[-2:], [-0.0455 + 1.0679j, 1.3868], atol=1e-6)
+
+
+def test_crc_residue(O):
+    data = bytes(range(200))
+    fcs = zlib.crc32(data).to_bytes(4, "little")
+    assert O.crc32(data + fcs) == 558161692 == 0x2144DF1C
+    assert O.crc32(b"123456789") == 0xCBF43926
+
+
+def test_mcs_table_and_frame_geometry(O):
+    want = {0: (1, 48, 24, 0x0D), 1: (1, 48, 36, 0x0F), 2: (2, 96, 48, 0x05), 3: (2, 96, 72, 0x07),
+            4: (4, 192, 96, 0x09), 5: (4, 192, 144, 0x0B), 6: (6, 288, 192, 0x01), 7: (6, 288, 216, 0x03)}
+    for e, w in want.items():
+        m = O.mcs(e)
+        assert (m["n_bpsc"], m["n_cbps"], m["n_dbps"], m["rate_field"]) == w
+    assert O.n_sym(7, 1528) == 57 and O.tx_frame(bytes(1528), 7, 1).size == 4961
+    assert O.n_sym(0, 1500) == 501 and O.n_sym(4, 1500) == 126 and O.n_sym(3, 296) == 34
+
+
+def test_mac_header(O):
+    p = O.mac_frame(b"hello", seq=0x123)
+    assert p[:4] == bytes([0x08, 0, 0, 0]) and p[4:10] == b"\x42" * 6 and p[10:16] == b"\x23" * 6 and p[16:22] == b"\xff" * 6
+    assert p[22:24] == ((0x123 & 0xfff) << 4).to_bytes(2, "little") and p[24:29] == b"hello"
+    assert p[29:] == zlib.crc32(p[:29]).to_bytes(4, "little") and len(p) == 33
+
+
+def test_fft64_matches_numpy(O):
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal(64) + 1j * rng.standard_normal(64)).astype(np.complex64)
+    assert np.allclose(O.fft64(x), np.fft.fft(x), atol=2e-5)
+    assert np.allclose(O.fft64(x, inverse=True), np.fft.ifft(x) * 64, atol=2e-5)
+
+
+def test_constellations_and_decisions(O):
+    import ref_model as R
+    for enc in range(8):
+        pts = O.constellation(enc)
+        nb = R.N_BPSC[enc]
+        for v in range(1 << nb):
+            bits = [(v >> k) & 1 for k in range(nb)]
+            assert abs(pts[v] - R.map_bits(bits, enc)[0]) < 1e-6
+            assert O.decide(enc, complex(pts[v]) * 1.01 + 0.001j) == v
+
+
+def test_viterbi_clean_and_erasures(O):
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2, 400, dtype=np.uint8)
+    bits[-40:] = 0
+    coded = O.conv_encode(bits)
+    assert np.array_equal(O.viterbi(coded, 400, 5)[:352], bits[:352])
+    dep = coded.copy()
+    dep[3::6] = 2
+    dep[4::6] = 2                                   # rate 3/4 erasures
+    assert np.array_equal(O.viterbi(dep, 400, 10)[:352], bits[:352])
+    noisy = coded.copy()
+    noisy[[50, 170, 290, 431]] ^= 1                 # isolated channel errors are corrected
+    assert np.array_equal(O.viterbi(noisy, 400, 5)[:352], bits[:352])
