@@ -164,7 +164,7 @@ def run_reference(args):
     from oracle import oracle as O
     threads = os.cpu_count() or 1
     flen = frame_samples()
-    fpl = 48
+    fpl = 96
     n_links = max(threads, 1)
     rng = np.random.default_rng(0)
     # one link built with the oracle TX + channel, replicated with different noise per link
@@ -191,7 +191,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "rx_msamples_per_s", "value": msps, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
-            "config": config_dict(args, n_links, fpl),
+            "config": config_dict(args, args.links, args.frames_per_link),
             "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": "port",
                              "sample": "%d links x %d frames (%d samples) per step, one link per host thread" % (n_links, fpl, x.size)},
             "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
