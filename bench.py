@@ -109,7 +109,7 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -231,10 +231,10 @@ def main():
     def step():
         h.rx_batch_dev(cap.data_ptr(), link_off, final=True, fetch=False)
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     stage_acc = {}
     barrier()
     t0 = time.perf_counter()

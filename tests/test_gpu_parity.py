@@ -214,3 +214,107 @@ def test_full_size_roundtrip_property(O, W):
     from util import assert_frames_equal as afe
     afe(sub, ref)
     h.close()
+
+
+def test_config1_shape_bpsk_1500_byte_psdus(H, O, W):
+    """BASELINE configs[0] shape: BPSK 1/2, 1500-byte PSDUs (501 symbols, 40481 samples), AWGN 20 dB."""
+    rng = np.random.default_rng(61)
+    y, psdus = make_capture(O, rng, [(0, 1500)] * 3, snr_db=20, seed=6)
+    H.set_param(W.wifi_b200.P_CHAN_EST, 0)
+    res, ref = H.rx_batch(y), O.rx(y, algo=0)
+    assert_frames_equal(res, ref)
+    assert res.pdus() == [p[:-4] for p in psdus]
+
+
+def test_config2_shape_16qam_multipath_cfo(H, O, W):
+    """BASELINE configs[1] shape at reduced length: 16-QAM 1/2, 1500-byte PSDUs, per-frame CFO,
+    3-tap channel h=[1, 0.4e^{j.}, 0, 0.2e^{j.}], 25 dB."""
+    rng = np.random.default_rng(62)
+    parts = [np.zeros(300, np.complex64)]
+    for i in range(10):
+        p = make_psdu(O, rng, 1500, seq=i)
+        iq = np.concatenate([O.tx_frame(p, 4, 1 + i), np.zeros(1100, np.complex64)])
+        taps = np.array([1.0, 0.4 * np.exp(1j * rng.uniform(0, 6.28)), 0.2 * np.exp(1j * rng.uniform(0, 6.28))])
+        taps /= np.linalg.norm(taps)
+        parts.append(O.channel(iq, n0=i * 20000, gain=0.6, cfo=float(rng.uniform(-0.0157, 0.0157)), noise_sigma=0.6 * 10 ** (-25 / 20),
+                               taps=((0, taps[0]), (1, taps[1]), (3, taps[2])), seed=62))
+    y = np.concatenate(parts)
+    for algo in (1, 2):
+        H.set_param(W.wifi_b200.P_CHAN_EST, algo)
+        res, ref = H.rx_batch(y), O.rx(y, algo=algo)
+        assert_frames_equal(res, ref)
+        assert int(ref.frames["crc_ok"].sum()) >= 8
+
+
+def test_config4_shape_many_links(O, W):
+    """BASELINE configs[3] shape at reduced length: 1024 independent links in one call."""
+    rng = np.random.default_rng(63)
+    base, _ = make_capture(O, rng, [(7, 200), (7, 120)], snr_db=30, seed=1, lead=64, gap=500, cfo=0.002)
+    n_links = 1024
+    links = []
+    for l in range(n_links):
+        links.append(O.channel(base, n0=0, gain=1.0, noise_sigma=0.02, cfo=float(rng.uniform(-0.005, 0.005)), seed=100 + l))
+    x = np.concatenate(links)
+    off = np.arange(n_links + 1, dtype=np.uint64) * base.size
+    h = W.Handle(max_samples=x.size + 1024, max_frames=4 * n_links, chan_est=1)
+    res = h.rx_batch(x, off)
+    ref = O.rx_links(x, off[:-1].astype(np.int64), np.full(n_links, base.size, np.int64), n_threads=8, algo=1, want_carrier=False)
+    order = np.lexsort((res.frames["trigger"], res.frames["link"]))
+    res.frames = res.frames[order]
+    assert_frames_equal(res, ref)
+    assert int(ref.frames["crc_ok"].sum()) >= 2 * n_links - 8
+    h.close()
+
+
+@pytest.mark.parametrize("enc", range(8))
+def test_config5_shape_per_ladder_is_identical(H, O, W, enc):
+    """BASELINE configs[4] shape: 599-byte PSDUs (571-byte feature-map patches) over an SNR ladder.
+    The frame tables are equal, so the PER curve is the oracle's by construction."""
+    H.set_param(W.wifi_b200.P_CHAN_EST, 0)
+    per = []
+    for snr in (2, 8, 14, 20, 26):
+        rng = np.random.default_rng(1000 * enc + snr)
+        y, _ = make_capture(O, rng, [(enc, 599)] * 6, snr_db=snr, seed=enc * 31 + snr, gap=600)
+        res, ref = H.rx_batch(y), O.rx(y, algo=0)
+        assert_frames_equal(res, ref)
+        per.append(1 - ref.frames["crc_ok"].sum() / 6)
+    assert per[0] >= per[-1]
+
+
+def test_setters_take_effect(O, W):
+    h = W.Handle(max_samples=1 << 18, sensitivity=0.56)
+    rng = np.random.default_rng(71)
+    y, _ = make_capture(O, rng, [(3, 100)] * 2, snr_db=12, seed=7)
+    h.set_param(W.wifi_b200.P_SENSITIVITY, 0.8)
+    h.set_param(W.wifi_b200.P_BANDWIDTH, 20e6)
+    h.set_param(W.wifi_b200.P_FREQUENCY, 2.412e9)
+    h.set_param(W.wifi_b200.P_CHAN_EST, 3)
+    assert_frames_equal(h.rx_batch(y), O.rx(y, threshold=0.8, bw=20e6, freq=2.412e9, algo=3))
+    with pytest.raises(W.WifiB200Error):
+        h.set_param(W.wifi_b200.P_CHAN_EST, 9)
+    with pytest.raises(W.WifiB200Error):
+        h.rx_batch(np.zeros((1 << 18) + 10, np.complex64))     # more samples than max_samples
+    h.close()
+
+
+def test_facade_loopback_like_irs_tranceiver(O, W):
+    """mac -> wifi_phy_hier TX -> x0.6 -> pad -> channel -> RX -> 'Extract Pics' slice, as
+    gnu_radio/IRS_tranceiver.py wires it (:271-344)."""
+    import struct
+    phy = W.wifi_phy_hier(bandwidth=20e6, chan_est=0, encoding=3, frequency=5.89e9, sensitivity=0.56, max_samples=1 << 19)
+    m = W.mac([0x23] * 6, [0x42] * 6, [0xff] * 6)
+    payloads = [struct.pack("=L", 268) + bytes(np.random.default_rng(i).integers(0, 256, 264, dtype=np.uint8)) for i in range(5)]
+    parts = []
+    for p in payloads:
+        burst = phy.mac_in(m.app_in(p))
+        parts += [np.zeros(100, np.complex64), 0.6 * burst, np.zeros(1000, np.complex64)]   # foo.packet_pad2(100, 1000)
+    x = np.concatenate(parts).astype(np.complex64)
+    y = O.channel(x, gain=float(10 ** (22 / 20)), noise_sigma=float(np.sqrt(2)), cfo=0.001, seed=3)   # snr slider 22, noise_voltage 1
+    got = []
+    phy.msg_connect_mac_out(lambda pdu: got.append(pdu))
+    for i in range(0, y.size, 4096):
+        phy.samp_in(y[i:i + 4096], flush=(i + 4096 >= y.size))
+    assert [pdu[1][24:][4:] for pdu in got] == [p[4:] for p in payloads]
+    assert all(pdu[0]["dlt"] == 105 and pdu[0]["encoding"] == 3 for pdu in got)
+    phy.set_encoding(5)
+    assert phy.get_encoding() == 5 and phy.mac_in(m.app_in(b"x" * 100)).size == W.wifi_b200.frame_samples(5, 128)
