@@ -267,27 +267,65 @@ def main():
     mbps = tot_bytes * 8 * args.steps / elapsed_max / 1e6
 
     # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----
+    # Two handles driven from two host threads, each taking alternate quarters of the links: the
+    # library serialises capture copies per GPU, so one handle's H2D overlaps the other's kernels.
     e2e = None
     if not args.no_e2e:
+        import threading
         host = torch.empty(cap.numel(), dtype=torch.float32, pin_memory=True)
         host.copy_(cap)
         torch.cuda.synchronize()
         hn = host.numpy().view(np.complex64)
+        parts = 4 if n_links >= 4 else 1
+        bounds = [n_links * i // parts for i in range(parts + 1)]
+        part_samples = max(int(link_off[bounds[i + 1]] - link_off[bounds[i]]) for i in range(parts))
+        part_frames = (max(bounds[i + 1] - bounds[i] for i in range(parts))) * (fpl + 1) + 1024
+        hs = [W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=part_samples + 1024, max_frames=part_frames) for _ in range(2)]
+        tot = {"frames": 0, "store": 0, "ok": 0}
+        lock = threading.Lock()
+
+        def worker(k, count):
+            for i in range(k, parts, 2):
+                hs[k].rx_batch(hn, link_off[bounds[i]:bounds[i + 1] + 1], final=True, fetch=False)   # frames + PSDU store land in pinned host memory
+                if count:
+                    c = hs[k].counts()
+                    with lock:
+                        tot["frames"] += c["n_frames"]
+                        tot["store"] += c["psdu_store_bytes"]
+                        tot["ok"] += c["n_pdus"]
+
+        def e2e_step(count=False):
+            th = [threading.Thread(target=worker, args=(k, count)) for k in range(2 if parts > 1 else 1)]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+
         for _ in range(2):
-            h.rx_batch(hn, link_off, final=True, fetch=False)
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            h.rx_batch(hn, link_off, final=True, fetch=False)   # frames + PSDU store land in pinned host memory
+            e2e_step()
         barrier()
         te = time.perf_counter() - t0
-        tv = torch.tensor([te], dtype=torch.float64, device="cuda")
+        e2e_step(count=True)
+        assert tot["ok"] == st_ok, (tot, st_ok)          # same answers through the host path
+        # the plain single-call form, for reference
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            h.rx_batch(hn, link_off, final=True, fetch=False)
+        t1 = (time.perf_counter() - t0) / max(1, args.steps // 2)
+        tv = torch.tensor([te, t1], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        c = h.counts()
-        e2e = {"value": tot_samples * args.steps / float(tv.item()) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(n_samples * 8), "d2h_bytes_per_step": int(c["n_frames"] * 104 + c["psdu_store_bytes"]),
-               "decoded_mbps": tot_bytes * 8 * args.steps / float(tv.item()) / 1e6}
+        e2e = {"value": tot_samples * args.steps / float(tv[0].item()) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(n_samples * 8), "d2h_bytes_per_step": int(tot["frames"] * 96 + tot["store"]),
+               "decoded_mbps": tot_bytes * 8 * args.steps / float(tv[0].item()) / 1e6,
+               "how": "wifi_b200_rx_batch on pinned host IQ, 2 handles x 2 host threads over 4 link groups (H2D of one overlaps kernels of the other); results copied to host",
+               "single_call_value": tot_samples / float(tv[1].item()) / 1e6}
+        for x_ in hs:
+            x_.close()
         del host
 
     if rank != 0:

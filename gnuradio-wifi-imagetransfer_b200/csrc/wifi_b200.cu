@@ -217,6 +217,7 @@ namespace {
     } while (0)
 
 std::mutex g_tab_mu;
+std::mutex g_h2d_mu[64];
 bool g_tab_done[64];
 
 int upload_tables(wifi_b200 *h)
@@ -678,6 +679,36 @@ int wifi_b200_channel_dev(wifi_b200_t *h, const float *in_dev, float *out_dev, c
     return WIFI_OK;
 }
 
+// host-buffer form of the test channel: stages in/out through the handle's device buffers
+int wifi_b200_channel(wifi_b200_t *h, const float *in_host, int64_t in_len, float *out_host, int64_t out_len,
+                      const wifi_b200_chan_seg *segs, int n_segs)
+{
+    if (!h || !in_host || !out_host || in_len <= 0 || out_len <= 0) return WIFI_E_ARG;
+    cf *d_in = nullptr, *d_out = nullptr;
+    {
+        std::lock_guard<std::mutex> g(h->mu);
+        cudaSetDevice(h->device);
+        CK(cudaMalloc(&d_in, (size_t)in_len * sizeof(cf)));
+        if (cudaMalloc(&d_out, (size_t)out_len * sizeof(cf)) != cudaSuccess) { cudaFree(d_in); h->err = "cudaMalloc"; return WIFI_E_NOMEM; }
+        cudaMemcpy(d_in, in_host, (size_t)in_len * sizeof(cf), cudaMemcpyHostToDevice);
+        cudaMemset(d_out, 0, (size_t)out_len * sizeof(cf));
+    }
+    for (int i = 0; i < n_segs; ++i)
+        if (segs[i].in_off < 0 || segs[i].in_off + segs[i].in_len > in_len || segs[i].out_off < 0 || segs[i].out_off + segs[i].n > out_len) {
+            cudaFree(d_in); cudaFree(d_out);
+            h->err = "channel segment outside the buffers";
+            return WIFI_E_ARG;
+        }
+    int rc = wifi_b200_channel_dev(h, (const float *)d_in, (float *)d_out, segs, n_segs);
+    if (rc == WIFI_OK) {
+        std::lock_guard<std::mutex> g(h->mu);
+        if (cudaMemcpy(out_host, d_out, (size_t)out_len * sizeof(cf), cudaMemcpyDeviceToHost) != cudaSuccess) rc = WIFI_E_CUDA;
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
 int wifi_b200_rx_batch_dev(wifi_b200_t *h, const float *iq_dev, const uint64_t *link_off, int n_links, int final)
 {
     if (!h || !iq_dev) return WIFI_E_ARG;
@@ -705,7 +736,13 @@ int wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *lin
     for (auto &L : h->h_links) L.x_off -= (int64_t)base;
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
     mark(h, ST_H2D);
-    CK(cudaMemcpyAsync(h->d_iq, iq_host + 2 * base, (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
+    {
+        // One host->device capture copy at a time per GPU: with two handles driven from two threads the
+        // copy of one batch then overlaps the kernels of the other instead of halving its PCIe share.
+        std::lock_guard<std::mutex> lk(g_h2d_mu[h->device & 63]);
+        CK(cudaMemcpyAsync(h->d_iq, iq_host + 2 * base, (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     rc = run_rx(h, h->d_iq, true, false);
     if (rc) return rc;
     update_stats(h);

@@ -56,7 +56,7 @@ EXPORTS = [
     "wifi_b200_abi_version", "wifi_b200_device_count", "wifi_b200_create", "wifi_b200_destroy", "wifi_b200_set_param",
     "wifi_b200_get_param", "wifi_b200_last_error", "wifi_b200_strerror", "wifi_b200_stream", "wifi_b200_sync",
     "wifi_b200_mac_frame", "wifi_b200_n_sym", "wifi_b200_frame_samples", "wifi_b200_tx", "wifi_b200_tx_dev",
-    "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_counts",
+    "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
 ]
@@ -90,6 +90,7 @@ def lib():
         L.wifi_b200_tx_symbols.argtypes = [vp, vp, C.c_size_t]
         L.wifi_b200_tx_symbols.restype = i64
         L.wifi_b200_channel_dev.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.wifi_b200_channel.argtypes = [vp, vp, i64, vp, i64, vp, C.c_int]
         for f in ("wifi_b200_rx_batch", "wifi_b200_rx_batch_dev"):
             getattr(L, f).argtypes = [vp, vp, vp, C.c_int, C.c_int]
         L.wifi_b200_rx_counts.argtypes = [vp, vp, vp, vp, vp]
@@ -131,6 +132,18 @@ def n_sym(enc, psdu_len):
 
 def frame_samples(enc, psdu_len):
     return lib().wifi_b200_frame_samples(enc, psdu_len)
+
+
+def chan_seg(in_off=0, in_len=0, out_off=0, n=0, n0=0, gain=1.0, cfo=0.0, phase0=0.0, noise_sigma=0.0, taps=((0, 1.0),),
+             seed=0, stream=0):
+    s = np.zeros(1, CHANSEG_DTYPE)
+    s["in_off"], s["in_len"], s["out_off"], s["n"], s["n0"] = in_off, in_len, out_off, n, n0
+    s["gain"], s["cfo"], s["phase0"], s["noise_sigma"] = gain, cfo, phase0, noise_sigma
+    s["n_taps"] = len(taps)
+    for i, (d, hh) in enumerate(taps):
+        s["delay"][0, i], s["tap_re"][0, i], s["tap_im"][0, i] = d, np.float32(complex(hh).real), np.float32(complex(hh).imag)
+    s["seed"], s["stream"] = seed, stream
+    return s
 
 
 class RxResult:
@@ -226,6 +239,15 @@ class Handle:
     def channel_dev(self, in_ptr, out_ptr, segs):
         segs = np.ascontiguousarray(segs, CHANSEG_DTYPE)
         self._ck(self._L.wifi_b200_channel_dev(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), _p(segs), segs.size))
+
+    def channel(self, x, n_out=None, **kw):
+        """One-segment convenience form of the test channel on host arrays (keywords as chan_seg())."""
+        a = np.ascontiguousarray(x, np.complex64)
+        n_out = a.size if n_out is None else int(n_out)
+        out = np.empty(n_out, np.complex64)
+        seg = chan_seg(in_len=a.size, n=n_out, **kw)
+        self._ck(self._L.wifi_b200_channel(self._h, _p(a), a.size, _p(out), n_out, _p(seg), 1))
+        return out
 
     # ---- RX ----
     def rx_batch(self, iq, link_off=None, final=True, fetch=True):

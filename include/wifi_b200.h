@@ -143,6 +143,9 @@ int64_t wifi_b200_tx_symbols(wifi_b200_t *h, uint8_t *out, size_t cap);
 
 /* ---- synthetic channel on device buffers ---- */
 int  wifi_b200_channel_dev(wifi_b200_t *h, const float *in_dev, float *out_dev, const wifi_b200_chan_seg *segs, int n_segs);
+/* same with host buffers (in: in_len complex samples, out: out_len, zero where no segment writes) */
+int  wifi_b200_channel(wifi_b200_t *h, const float *in_host, int64_t in_len, float *out_host, int64_t out_len,
+                       const wifi_b200_chan_seg *segs, int n_segs);
 
 /* ---- RX, batch form: n_links independent streams; link l is iq[link_off[l] .. link_off[l+1]) complex
  * samples.  final != 0: the streams end here (flush).  Results stay in the handle until the next rx call. */

@@ -318,3 +318,32 @@ def test_facade_loopback_like_irs_tranceiver(O, W):
     assert all(pdu[0]["dlt"] == 105 and pdu[0]["encoding"] == 3 for pdu in got)
     phy.set_encoding(5)
     assert phy.get_encoding() == 5 and phy.mac_in(m.app_in(b"x" * 100)).size == W.wifi_b200.frame_samples(5, 128)
+
+
+def test_udp_runner_speaks_the_apps_contract(O, W):
+    """upload_image_udp.py datagrams in (=L length + pickle(((y,x,c), 10x10x1 uint8))), decoded patches
+    out on the viewer's port, through mac -> TX -> channel -> RX on the GPU."""
+    import pickle
+    import socket
+    import struct
+    import threading
+    out = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    out.bind(("127.0.0.1", 0))
+    out.settimeout(20)
+    t = W.loopback_runner.IrsTransceiver(in_port=0, out_addr=("127.0.0.1", out.getsockname()[1]), snr=27.0, encoding=3, idle_flush_s=0.05)
+    rng = np.random.default_rng(81)
+    pieces = [((int(rng.integers(0, 30)), int(rng.integers(0, 30)), int(rng.integers(0, 3))), rng.integers(0, 256, (10, 10, 1), dtype=np.uint8)) for _ in range(12)]
+    th = threading.Thread(target=t.serve, kwargs={"max_datagrams": len(pieces)})
+    th.start()
+    s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    for piece in pieces:
+        data = pickle.dumps(piece)
+        s.sendto(struct.pack("=L", len(data)) + data, ("127.0.0.1", t.in_port))      # upload_image_udp.py:29-32
+    got = []
+    for _ in pieces:
+        got.append(pickle.loads(out.recvfrom(2048)[0]))                               # download_image_udp.py:36-44
+    th.join(timeout=30)
+    assert [g[0] for g in got] == [p[0] for p in pieces]
+    assert all(np.array_equal(g[1], p[1]) for g, p in zip(got, pieces))
+    assert t.stats["pdus_out"] == len(pieces)
+    t.close()
