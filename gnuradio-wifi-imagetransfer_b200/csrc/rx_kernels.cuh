@@ -9,6 +9,7 @@
 //   k_pack        R6 unpack bits, deinterleave, depuncture -> 2-bit symbols, 8 trellis steps per word
 //   k_viterbi     R6a-c Viterbi, descramble, CRC-32 -> PSDU bytes
 #pragma once
+#include <cuda_pipeline.h>
 #include "viterbi.cuh"
 
 // ------------------------------------------------------------------ R1 front-end
@@ -37,6 +38,34 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
 // of the stream are zeros, which makes every "index < 0" special case of the oracle an exact
 // no-op (x + 0 == x), so the inner loop is branch free.
 #define DET_ROWS (DET_THREADS + 2)
+struct DetState { float sar, sai, sp; };
+
+// samples [I0, I1) of the chunk; OD / OO / OOD = offsets of the n-16, n-47, n-63 streams in the padded tile
+template <int I0, int I1, int OD, int OO, int OOD>
+__device__ __forceinline__ void det_segment(const cf *base, DetState &st, float thr_f, float thr2, unsigned long long &wbits)
+{
+#pragma unroll 4
+    for (int i = I0; i < I1; ++i) {
+        const cf xn = base[i], xd = base[i + OD], xo = base[i + OO], xod = base[i + OOD];
+        st.sar += xn.re * xd.re + xn.im * xd.im;
+        st.sai += xn.im * xd.re - xn.re * xd.im;
+        const float ar = st.sar, ai = st.sai;
+        st.sar -= xo.re * xod.re + xo.im * xod.im;
+        st.sai -= xo.im * xod.re - xo.re * xod.im;
+        st.sp += xn.re * xn.re + xn.im * xn.im;
+        const float p = st.sp;
+        st.sp -= xod.re * xod.re + xod.im * xod.im;
+        const float m2 = ar * ar + ai * ai;
+        // c = sqrt(m2)/p > thr.  Decide from the squares when the margin (1e-4) dwarfs the rounding of
+        // the exact expression (< 3e-7); evaluate the oracle's expression only inside the margin or when
+        // p is outside the range where the squares are safe.
+        const float t2 = thr2 * (p * p);
+        bool over = m2 > t2;
+        const bool sure = (p > 1e-12f) & (p < 1e12f) & ((m2 > t2 * 1.0001f) | (m2 < t2 * 0.9999f));
+        if (!sure) over = (sqrtf(m2) / p) > thr_f;
+        wbits |= (unsigned long long)over << i;
+    }
+}
 #define DET_IDX(q) ((q) + ((q) >> 6))     // row * 65 + col
 __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
                                                          int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
@@ -51,56 +80,46 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
     const cf *x = iq + L.x_off;
     const int64_t T0 = (tile * DET_THREADS - L.chunk_base) * FE_CHUNK;   // first sample of the tile in the link
     const int64_t lo = -(int64_t)L.hist, hi = L.len;
+    // global -> shared with cp.async (LDGSTS): all 65 copies of a thread are in flight at once,
+    // no register staging; samples outside the stream are zero-filled
+#pragma unroll 5
     for (int q = tid; q < DET_ROWS * FE_CHUNK; q += DET_THREADS) {
         int64_t g = T0 - 2 * FE_CHUNK + q;
-        cf v = {0.f, 0.f};
-        if (g >= lo && g < hi) v = x[g];
-        sx[DET_IDX(q)] = v;
+        cf *dst = &sx[DET_IDX(q)];
+        if (g >= lo && g < hi) __pipeline_memcpy_async(dst, &x[g], sizeof(cf));
+        else *dst = cf{0.f, 0.f};
     }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
     __syncthreads();
     // this thread's chunk is row tid+2 of the padded tile: element c of the chunk (c may be negative,
-    // reaching into the previous rows) sits at base + c + floor(c / 64); with the loops unrolled
-    // every shared-memory address is base + an immediate
+    // reaching into the previous rows) sits at base + c + floor(c / 64).  The walk is cut where one of
+    // the four sample streams (n, n-16, n-47, n-63) crosses a row, so inside a segment every address is
+    // base + i + constant.
     const cf *base = sx + (tid + 2) * (FE_CHUNK + 1);
-#define DET_AT(c) base[(c) + ((c) >> 6)]
-    uint32_t w0 = 0u, w1 = 0u;
+    unsigned long long wbits = 0ull;
     if (T0 + (int64_t)tid * FE_CHUNK < hi) {
-        float sar = 0.f, sai = 0.f, sp = 0.f;
-#pragma unroll
+        DetState st;
+        st.sar = st.sai = st.sp = 0.f;
+#pragma unroll 4
         for (int k = 47; k >= 1; --k) {
-            cf a = DET_AT(-k), d = DET_AT(-k - 16);
-            sar += a.re * d.re + a.im * d.im;
-            sai += a.im * d.re - a.re * d.im;
+            int c = -k, c2 = -k - 16;
+            cf a = base[c + (c >> 6)], d = base[c2 + (c2 >> 6)];
+            st.sar += a.re * d.re + a.im * d.im;
+            st.sai += a.im * d.re - a.re * d.im;
         }
-#pragma unroll
+#pragma unroll 4
         for (int k = 63; k >= 1; --k) {
-            cf a = DET_AT(-k);
-            sp += a.re * a.re + a.im * a.im;
+            cf a = base[-k - 1];
+            st.sp += a.re * a.re + a.im * a.im;
         }
         const float thr2 = thr_f * thr_f;
-#pragma unroll
-        for (int i = 0; i < FE_CHUNK; ++i) {
-            cf xn = DET_AT(i), xd = DET_AT(i - 16), xo = DET_AT(i - 47), xod = DET_AT(i - 63);
-            sar += xn.re * xd.re + xn.im * xd.im;
-            sai += xn.im * xd.re - xn.re * xd.im;
-            const float ar = sar, ai = sai;
-            sar -= xo.re * xod.re + xo.im * xod.im;
-            sai -= xo.im * xod.re - xo.re * xod.im;
-            sp += xn.re * xn.re + xn.im * xn.im;
-            const float p = sp;
-            sp -= xod.re * xod.re + xod.im * xod.im;
-            const float m2 = ar * ar + ai * ai;
-            // c = sqrt(m2)/p > thr.  Decide from the squares when the margin (1e-4) dwarfs the rounding
-            // of the exact expression (< 3e-7); evaluate the oracle's expression only inside the margin
-            // or when p is outside the range where the squares are safe.
-            const float t2 = thr2 * (p * p);
-            bool over = m2 > t2;
-            const bool sure = (p > 1e-12f) && (p < 1e12f) && ((m2 > t2 * 1.0001f) || (m2 < t2 * 0.9999f));
-            if (!sure) over = (sqrtf(m2) / p) > thr_f;
-            if (over) { if (i < 32) w0 |= 1u << (i & 31); else w1 |= 1u << (i & 31); }
-        }
+        det_segment<0, 16, -17, -48, -64>(base, st, thr_f, thr2, wbits);
+        det_segment<16, 47, -16, -48, -64>(base, st, thr_f, thr2, wbits);
+        det_segment<47, 63, -16, -47, -64>(base, st, thr_f, thr2, wbits);
+        det_segment<63, 64, -16, -47, -63>(base, st, thr_f, thr2, wbits);
     }
-#undef DET_AT
+    const uint32_t w0 = (uint32_t)wbits, w1 = (uint32_t)(wbits >> 32);
     const int64_t chunk = tile * DET_THREADS + tid;
     reinterpret_cast<uint2 *>(flags)[chunk] = make_uint2(w0, w1);
     uint32_t any = __ballot_sync(0xffffffffu, (w0 | w1) != 0u);
@@ -231,27 +250,25 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
     const int tid = threadIdx.x;
     const int hist = L.hist;
     int64_t t = F.trigger;
-    if (tid == 0) {
-        // a[t]: the moving_average_cc value sync_short sees on its port 1 at the trigger
-        int64_t i0 = t & ~(int64_t)(FE_CHUNK - 1);
-        float sar = 0.f, sai = 0.f;
-        for (int64_t j = i0 - 47; j < i0; ++j) {
-            if (j < -(int64_t)hist) continue;
-            cf p = fe_prod(x, j, hist);
-            sar += p.re;
-            sai += p.im;
-        }
-        for (int64_t i = i0; i <= t; ++i) {
-            cf pr = fe_prod(x, i, hist);
-            sar += pr.re;
-            sai += pr.im;
-            if (i < t && i - 47 >= -(int64_t)hist) {
-                cf po = fe_prod(x, i - 47, hist);
-                sar -= po.re;
-                sai -= po.im;
+    {
+        // a[t]: the moving_average_cc value sync_short sees on its port 1 at the trigger, recomputed on
+        // the oracle's chunk grid.  The products are formed in parallel, the running sum (whose order
+        // of additions is the contract) by one thread from shared memory.
+        const int64_t i0 = t & ~(int64_t)(FE_CHUNK - 1);
+        const int cnt = (int)(t - i0) + 48;
+        cf *sprod = scorr;   // scratch, reused later
+        for (int q = tid; q < cnt; q += blockDim.x) sprod[q] = fe_prod(x, i0 - 47 + q, hist);
+        __syncthreads();
+        if (tid == 0) {
+            float sar = 0.f, sai = 0.f;
+            for (int q = 0; q < 47; ++q) { sar += sprod[q].re; sai += sprod[q].im; }
+            for (int q = 47; q < cnt; ++q) {
+                sar += sprod[q].re;
+                sai += sprod[q].im;
+                if (q < cnt - 1) { sar -= sprod[q - 47].re; sai -= sprod[q - 47].im; }
             }
+            s_freq = wdm_atan2f(sai, sar) / 16;
         }
-        s_freq = wdm_atan2f(sai, sar) / 16;
     }
     __syncthreads();
     const float freq = s_freq;
@@ -332,7 +349,7 @@ __device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
 }
 
 // phase 0: symbols 0..2 (LTS1, LTS2, SIGNAL) -> EqState ; phase 1: data symbols -> rows
-__global__ void __launch_bounds__(128) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
+__global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
                                                 EqState *states, uint8_t *rows, cf *carrier, DemodParams prm, int phase,
                                                 const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in)
 {
