@@ -164,37 +164,129 @@ __device__ __forceinline__ int64_t next_candidate(const uint32_t *__restrict__ f
     return -1;
 }
 
+// Speculative pass: one warp per 8192-sample segment (= one detect tile) walks the greedy chain inside
+// its segment as if no earlier trigger constrained it.  Chains started at different points merge at
+// their first common trigger, so the sequential pass below only has to re-walk a segment whose first
+// speculative trigger is closer than MIN_GAP to the true trigger before it.
+#define SEG_CHUNKS DET_THREADS          // chunks per segment
+#define SEG_CAP 20                      // >= 8192 / 481 + 1 triggers per segment
+__global__ void __launch_bounds__(128) k_select_spec(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary,
+                                                      const LinkDesc *__restrict__ links, int n_links, int64_t total_segs, int min_plateau,
+                                                      int *__restrict__ spec_trig, int *__restrict__ spec_cnt)
+{
+    int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (seg >= total_segs) return;
+    const int l = find_link(links, n_links, seg * SEG_CHUNKS);
+    const LinkDesc L = links[l];
+    const uint32_t *fw = flags + L.chunk_base * 2;
+    const int64_t n_chunks = (L.len + FE_CHUNK - 1) / FE_CHUNK;
+    const int64_t c0 = seg * SEG_CHUNKS - L.chunk_base;            // first chunk of the segment in the link
+    const int64_t c1 = (c0 + SEG_CHUNKS < n_chunks) ? c0 + SEG_CHUNKS : n_chunks;
+    int64_t pos = c0 * FE_CHUNK;
+    if (pos < L.min_pos) pos = L.min_pos;
+    const int64_t end = (c1 * FE_CHUNK < L.len) ? c1 * FE_CHUNK : L.len;
+    int k = 0;
+    while (pos < end) {
+        int64_t m = next_candidate(fw, summary, L.chunk_base, c1, pos, lane, min_plateau);
+        if (m < 0 || m >= end) break;
+        if (lane == 0 && k < SEG_CAP) spec_trig[seg * SEG_CAP + k] = (int)m;
+        ++k;
+        pos = m + SS_MIN_GAP + 1;
+    }
+    if (lane == 0) spec_cnt[seg] = k < SEG_CAP ? k : SEG_CAP;
+}
+
+// Sequential pass, one warp per link: accepts speculative segments 32 at a time while each first
+// trigger is more than MIN_GAP after the last trigger before it, re-walks the flags otherwise.
+// Then reserves the link's frame and row ranges and writes the frame records.
 __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary, LinkDesc *links,
                                                  int n_links, wifi_b200_frame *frames, int *counters, unsigned long long *row_counter,
-                                                 int64_t max_frames, int min_plateau, int *err, int2 *trig_tmp)
+                                                 int64_t max_frames, int min_plateau, int *err, int *trig_tmp,
+                                                 const int *__restrict__ spec_trig, const int *__restrict__ spec_cnt)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_links) return;
     LinkDesc L = links[warp];
     const uint32_t *fw = flags + L.chunk_base * 2;
     const int64_t n_chunks = (L.len + FE_CHUNK - 1) / FE_CHUNK;
-    int2 *tmp = trig_tmp + L.chunk_base / 4;   // triggers are > 480 samples apart: at most one per 7 chunks
-    int64_t pos = L.min_pos > 0 ? L.min_pos : 0, prev = -1;
+    const int64_t seg0 = L.chunk_base / SEG_CHUNKS;
+    const int64_t n_segs = (n_chunks + SEG_CHUNKS - 1) / SEG_CHUNKS;
+    int *tmp = trig_tmp + L.chunk_base / 4;   // triggers are > 480 samples apart: at most one per 7 chunks
+    int64_t t_prev = (L.min_pos > 0 ? L.min_pos : 0) - SS_MIN_GAP - 1;   // "last trigger" entering the buffer
     int k = 0;
-    for (;;) {
-        int64_t m = next_candidate(fw, summary, L.chunk_base, n_chunks, pos, lane, min_plateau);
-        if (m >= L.len) m = -1;
-        if (prev >= 0) {
-            int64_t endp = (m >= 0) ? m : L.len;
-            int blen = (int)((endp - prev) < SS_MAX_SAMPLES ? (endp - prev) : SS_MAX_SAMPLES);
-            if (lane == 0) tmp[k - 1] = make_int2((int)prev, blen);
+    int64_t s = 0;
+    while (s < n_segs) {
+        // look at up to 32 segments at once
+        int64_t si = s + lane;
+        int cnt = (si < n_segs) ? spec_cnt[seg0 + si] : 0;
+        int first = cnt ? spec_trig[(seg0 + si) * SEG_CAP] : 0;
+        int last = cnt ? spec_trig[(seg0 + si) * SEG_CAP + cnt - 1] : 0;
+        // last trigger before each segment, assuming every earlier segment of the group is accepted
+        int64_t lastv = cnt ? (int64_t)last : -(1ll << 40);
+        int64_t run = lastv;
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t v = __shfl_up_sync(0xffffffffu, run, o);
+            if (lane >= o && v > run) run = v;
         }
-        if (m < 0) break;
-        prev = m;
-        ++k;
-        pos = m + SS_MIN_GAP + 1;
+        int64_t before = __shfl_up_sync(0xffffffffu, run, 1);
+        if (lane == 0 || before < t_prev) before = t_prev;
+        bool okseg = (cnt == 0) || ((int64_t)first > before + SS_MIN_GAP);
+        unsigned bad = __ballot_sync(0xffffffffu, !okseg);
+        int n_ok = bad ? __ffs((int)bad) - 1 : 32;          // segments s .. s+n_ok-1 are accepted as speculated
+        if (s + n_ok > n_segs) n_ok = (int)(n_segs - s);
+        // append their triggers
+        int mine = (lane < n_ok) ? cnt : 0, incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        for (int j = 0; j < mine; ++j) tmp[k + incl - mine + j] = spec_trig[(seg0 + si) * SEG_CAP + j];
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > 0) {
+            int64_t lastrun = __shfl_sync(0xffffffffu, run, n_ok - 1 >= 0 ? n_ok - 1 : 0);
+            if (n_ok > 0 && lastrun > t_prev) t_prev = lastrun;
+        }
+        k += total;
+        s += n_ok;
+        if (bad && s < n_segs) {
+            // segment s starts inside the gap of the previous trigger: walk the true chain through it
+            const int64_t c1 = ((s + 1) * SEG_CHUNKS < n_chunks) ? (s + 1) * SEG_CHUNKS : n_chunks;
+            const int64_t end = (c1 * FE_CHUNK < L.len) ? c1 * FE_CHUNK : L.len;
+            const int scnt = spec_cnt[seg0 + s];
+            int64_t pos = t_prev + SS_MIN_GAP + 1;
+            while (pos < end) {
+                int64_t m = next_candidate(fw, summary, L.chunk_base, c1, pos, lane, min_plateau);
+                if (m < 0 || m >= end) break;
+                // merged with the speculative chain?  then the rest of it is true as well
+                int at = -1;
+                for (int j = 0; j < scnt; ++j)
+                    if (spec_trig[(seg0 + s) * SEG_CAP + j] == (int)m) at = j;
+                if (at >= 0) {
+                    for (int j = at + lane; j < scnt; j += 32) tmp[k + j - at] = spec_trig[(seg0 + s) * SEG_CAP + j];
+                    k += scnt - at;
+                    t_prev = spec_trig[(seg0 + s) * SEG_CAP + scnt - 1];
+                    break;
+                }
+                if (lane == 0) tmp[k] = (int)m;
+                ++k;
+                t_prev = m;
+                pos = m + SS_MIN_GAP + 1;
+            }
+            ++s;
+        }
     }
     __syncwarp();
     // rows reserved per burst: blen/80 + 1 ; exclusive prefix over the link's bursts
+    auto blen_of = [&](int i) -> int {
+        int64_t t = tmp[i];
+        int64_t endp = (i + 1 < k) ? (int64_t)tmp[i + 1] : L.len;
+        return (int)((endp - t) < SS_MAX_SAMPLES ? (endp - t) : SS_MAX_SAMPLES);
+    };
     long long rows = 0;
     for (int b0 = 0; b0 < k; b0 += 32) {
         int i = b0 + lane;
-        if (i < k) rows += tmp[i].y / 80 + 1;
+        if (i < k) rows += blen_of(i) / 80 + 1;
     }
     for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
     int base = 0;
@@ -213,15 +305,15 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
     long long carry = 0;
     for (int b0 = 0; b0 < k; b0 += 32) {
         int i = b0 + lane;
-        int2 tb = i < k ? tmp[i] : make_int2(0, 0);
-        long long mine = i < k ? tb.y / 80 + 1 : 0, incl = mine;
+        int bl = i < k ? blen_of(i) : 0;
+        long long mine = i < k ? bl / 80 + 1 : 0, incl = mine;
         for (int o = 1; o < 32; o <<= 1) {
             long long v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
         if (i < k) {
             wifi_b200_frame f;
-            f.trigger = tb.x; f.link = warp; f.burst_len = tb.y; f.freq_short = 0.f; f.freq_long = 0.f;
+            f.trigger = tmp[i]; f.link = warp; f.burst_len = bl; f.freq_short = 0.f; f.freq_long = 0.f;
             f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
             f.frame_symbols = 0; f.n_rows = 0; f.accepted = 0; f.decoded = 0; f.crc_ok = 0; f.snr = 0.0;
             f.row_off = row_base + carry + incl - mine; f.psdu_off = -1;
@@ -415,7 +507,9 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     // unpack + deinterleave + depuncture), 8 steps per 32-bit word, words_per_sym = N_DBPS/8.
     // BPSK 3/4 (N_DBPS 36) does not fill whole words per symbol and goes through k_pack.
     const int ndbps = c_tab.mcs[enc].n_dbps;
-    const int wps = (phase == 1 && (ndbps & 7) == 0) ? ndbps >> 3 : 0;
+    // (frames decode_mac will refuse -- more than 511 symbols / 1528 bytes -- would not fit the per-frame
+    // word slot and are never decoded from it, so they are not packed)
+    const int wps = (phase == 1 && (ndbps & 7) == 0 && frame_symbols <= WIFI_MAX_SYM && F.length <= WIFI_MAX_PSDU) ? ndbps >> 3 : 0;
     if (wps) {
         for (int i = lane; i < 2 * ndbps; i += 32) s_lut[wib][(i & 15) * 27 + (i >> 4)] = depunct_lut[enc * 432 + i];   // [k][word]: conflict-free reads
         __syncwarp();

@@ -158,7 +158,9 @@ struct wifi_b200 {
     cf *d_iq = nullptr;            // staging for host input (max_samples + history)
     uint32_t *d_flags = nullptr;      // 1 bit per sample: c[n] > threshold
     uint32_t *d_summary = nullptr;    // 1 bit per FE_CHUNK chunk: any flag set
-    int2 *d_trig_tmp = nullptr;       // k_select scratch: (trigger, burst_len) per link
+    int *d_trig_tmp = nullptr;        // k_select scratch: trigger list per link
+    int *d_spec_trig = nullptr;       // speculative triggers per 8192-sample segment
+    int *d_spec_cnt = nullptr;
     int *d_pack_list = nullptr;       // frames whose trellis words k_pack must build
     int64_t tile_cap = 0;
     LinkDesc *d_links = nullptr;
@@ -239,7 +241,7 @@ void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
-                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
+                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_spec_trig, h->d_spec_cnt, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_frames) cudaFreeHost(h->h_frames);
@@ -290,9 +292,12 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
     if (total_tiles > 0)
         k_detect<<<(unsigned)total_tiles, DET_THREADS, DET_SMEM, s>>>(iq, h->d_links, n_links, total_tiles, thr_f, h->d_flags, h->d_summary);
     mark(h, ST_SELECT);
+    if (total_tiles > 0)
+        k_select_spec<<<(unsigned)((total_tiles * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, total_tiles,
+                                                                              h->cfg.min_plateau, h->d_spec_trig, h->d_spec_cnt);
     k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->d_frames, h->d_counters,
                                                         (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
-                                                        h->cfg.min_plateau, h->d_counters + 2, h->d_trig_tmp);
+                                                        h->cfg.min_plateau, h->d_counters + 2, h->d_trig_tmp, h->d_spec_trig, h->d_spec_cnt);
     mark(h, ST_SYNC_LONG);
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -473,7 +478,9 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     h->tile_cap = S / DET_TILE + MAX_LINKS + 1;
     A((void **)&h->d_flags, (size_t)h->tile_cap * DET_THREADS * 8);
     A((void **)&h->d_summary, (size_t)h->tile_cap * (DET_THREADS / 32) * 4 + 256);
-    A((void **)&h->d_trig_tmp, (size_t)h->tile_cap * (DET_THREADS / 4) * sizeof(int2));
+    A((void **)&h->d_trig_tmp, (size_t)h->tile_cap * (DET_THREADS / 4) * sizeof(int));
+    A((void **)&h->d_spec_trig, (size_t)h->tile_cap * SEG_CAP * sizeof(int));
+    A((void **)&h->d_spec_cnt, (size_t)h->tile_cap * sizeof(int));
     A((void **)&h->d_pack_list, (size_t)Fm * sizeof(int));
     A((void **)&h->d_links, (size_t)MAX_LINKS * sizeof(LinkDesc));
     A((void **)&h->d_frames, (size_t)Fm * sizeof(wifi_b200_frame));
