@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--links", type=int, default=64, help="independent links per GPU")
     ap.add_argument("--frames-per-link", type=int, default=512)
     ap.add_argument("--algo", type=int, default=ALGO)
+    ap.add_argument("--soft", action="store_true", help="soft-decision mode (extension, DESIGN.md 9)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=1536, help="frames of the cpu_baseline sample")
@@ -150,7 +151,7 @@ class ClockSampler:
 
 def config_dict(args, n_links, fpl):
     return {"workload": "BASELINE configs[2]: 54 Mb/s 64-QAM 3/4 batched RX, 1528-byte PSDUs (57 symbols, 4961 samples) + 1100-sample gaps, AWGN 30 dB",
-            "equalizer": ["LS", "LMS", "COMB", "STA"][args.algo], "links_per_gpu": n_links, "frames_per_link": fpl,
+            "equalizer": ["LS", "LMS", "COMB", "STA"][args.algo], "decisions": "soft" if getattr(args, "soft", False) else "hard", "links_per_gpu": n_links, "frames_per_link": fpl,
             "samples_per_gpu": int(n_links * (LEAD + fpl * (frame_samples() + GAP))),
             "l2_policy": "input (%.2f GB per GPU) larger than L2, no flush" % (n_links * (LEAD + fpl * (frame_samples() + GAP)) * 8 / 1e9),
             "parallelism": "links sharded across GPUs, no data-path collective"}
@@ -181,7 +182,7 @@ def run_reference(args):
     ok = 0
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        r = O.rx_links(x, off, ln, n_threads=threads, algo=args.algo, want_carrier=False)
+        r = O.rx_links(x, off, ln, n_threads=threads, algo=args.algo, want_carrier=False, soft=args.soft)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -219,7 +220,8 @@ def main():
     n = n_links * fpl
     flen = frame_samples()
     n_samples = n_links * (LEAD + fpl * (flen + GAP))
-    h = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=n_samples + 1024, max_frames=n + n_links + 1024)
+    h = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=n_samples + 1024, max_frames=n + n_links + 1024,
+                 soft_decision=args.soft)
     cap, link_off, psdus = build_capture(h, W, torch, n_links, fpl, seed=1000 + rank)
     torch.cuda.synchronize()
 
@@ -280,7 +282,7 @@ def main():
         bounds = [n_links * i // parts for i in range(parts + 1)]
         part_samples = max(int(link_off[bounds[i + 1]] - link_off[bounds[i]]) for i in range(parts))
         part_frames = (max(bounds[i + 1] - bounds[i] for i in range(parts))) * (fpl + 1) + 1024
-        hs = [W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=part_samples + 1024, max_frames=part_frames) for _ in range(2)]
+        hs = [W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=part_samples + 1024, max_frames=part_frames, soft_decision=args.soft) for _ in range(2)]
         tot = {"frames": 0, "store": 0, "ok": 0}
         lock = threading.Lock()
 
@@ -366,7 +368,8 @@ def main():
         sl = int(link_off[nl])
         xs = cap[:2 * sl].cpu().numpy().view(np.complex64)
         t0 = time.perf_counter()
-        r = O.rx_links(xs, link_off[:nl].astype(np.int64), np.diff(link_off[:nl + 1]).astype(np.int64), n_threads=1, algo=args.algo, want_carrier=False)
+        r = O.rx_links(xs, link_off[:nl].astype(np.int64), np.diff(link_off[:nl + 1]).astype(np.int64), n_threads=1, algo=args.algo, want_carrier=False,
+                       soft=args.soft)
         dt = time.perf_counter() - t0
         # same inputs, same answers: the GPU frame table of these links equals the oracle's
         g = res.frames[np.isin(res.frames["link"], np.arange(nl))]

@@ -430,6 +430,7 @@ struct DemodParams {
     double bw, freq;
     int algo;
     int want_carrier;
+    int soft;          // also emit int8 soft values (soft rows + soft trellis words)
 };
 
 __device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
@@ -443,8 +444,12 @@ __device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
 // phase 0: symbols 0..2 (LTS1, LTS2, SIGNAL) -> EqState ; phase 1: data symbols -> rows
 __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
                                                 EqState *states, uint8_t *rows, cf *carrier, DemodParams prm, int phase,
-                                                const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in)
+                                                const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in,
+                                                int8_t *__restrict__ soft_rows, uint32_t *__restrict__ vit_soft_in)
 {
+    __shared__ int8_t s_soft[4][392];     // soft value of (carrier << 3 | bit); [384] = 0 for erasures
+    __shared__ uint16_t s_slut[4][432];
+    __shared__ float s_h2[4][64];
     __shared__ cf s_hu[4][64];
     __shared__ double s_md[4][64], s_ms[4][64];
     __shared__ uint16_t s_lut[4][432];
@@ -483,6 +488,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     cf HA = {0.f, 0.f}, HB = {0.f, 0.f};
     cf pp[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     double d_er = 0.0, eps0, snr = 0.0;
+    float havg = 1.f;
     int frame_symbols = 0, enc = 0, nb = 1;
     int n_begin, n_end;
     EqState *st = states + f;
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
         HA = st->H[iA]; HB = st->H[iB];
 #pragma unroll
         for (int q = 0; q < 4; ++q) pp[q] = st->prev_pil[q];
-        d_er = st->d_er; eps0 = st->eps0;
+        d_er = st->d_er; eps0 = st->eps0; havg = st->havg;
         n_begin = 3;
         n_end = n_syms < frame_symbols + 3 ? n_syms : frame_symbols + 3;
     }
@@ -515,6 +521,18 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
         __syncwarp();
     }
     uint32_t *vw = vit_in + (int64_t)f * VIT_MAXW;
+    // soft mode: N_DBPS/2 words per symbol (2 steps x 2 int8 each); every MCS fills whole words
+    const bool soft_on = phase == 1 && prm.soft;
+    const int swps = (soft_on && frame_symbols <= WIFI_MAX_SYM && F.length <= WIFI_MAX_PSDU) ? ndbps >> 1 : 0;
+    if (soft_on) {
+        for (int i = lane; i < 2 * ndbps; i += 32) {
+            uint16_t e = depunct_lut[enc * 432 + i];
+            s_slut[wib][i] = (e == 0xffffu) ? 384 : e;
+        }
+        if (lane == 0) s_soft[wib][384] = 0;
+        __syncwarp();
+    }
+    uint32_t *vsw = vit_soft_in ? vit_soft_in + (int64_t)f * SOFT_MAXW : nullptr;
     int n_rows = 0;
     for (int n = n_begin; n < n_end; ++n) {
         // ---- sync_long COPY: fetch the symbol's samples, both derotations ----
@@ -604,24 +622,35 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                 s_md[wib][iB] = (double)md * (double)md; s_ms[wib][iB] = (double)ms * (double)ms;
                 if (usedB) HB = cdiv(s, cf{ltsB * 2.0f, 0.f});
             }
+            s_h2[wib][iA] = HA.re * HA.re + HA.im * HA.im;
+            s_h2[wib][iB] = HB.re * HB.re + HB.im * HB.im;
             __syncwarp();
             if (lane == 0) {
                 double signal = 0, noise = 0;
+                float acc = 0.f;
                 for (int i = 6; i <= 58; ++i) {
                     if (i == 32) continue;
                     noise += s_md[wib][i];
                     signal += s_ms[wib][i];
+                    acc += s_h2[wib][i];
                 }
                 snr = 10 * log10(signal / noise / 2);
+                havg = acc / 52.0f;
             }
             __syncwarp();
         } else {
             cf symA = {0.f, 0.f}, symB = {0.f, 0.f};
             int bitsA = 0, bitsB = 0;
             cf huA = {0.f, 0.f}, huB = {0.f, 0.f};
+            SoftQ sqA, sqB;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) { sqA.q[u][t] = 0; sqB.q[u][t] = 0; }
             if (carA >= 0) {
                 symA = cdiv(a, HA);
                 bitsA = dev_decide(nb, symA);
+                if (soft_on) sqA = dev_soft_demap(nb, symA, (HA.re * HA.re + HA.im * HA.im) / havg);
                 if (prm.algo == WIFI_EQ_LMS) {
                     cf q = cdiv(a, dev_point(nb, bitsA));
                     HA = cadd(cscale(HA, 0.5f), cscale(q, 0.5f));
@@ -631,6 +660,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
             if (carB >= 0) {
                 symB = cdiv(b, HB);
                 bitsB = dev_decide(nb, symB);
+                if (soft_on) sqB = dev_soft_demap(nb, symB, (HB.re * HB.re + HB.im * HB.im) / havg);
                 if (prm.algo == WIFI_EQ_LMS) {
                     cf q = cdiv(b, dev_point(nb, bitsB));
                     HB = cadd(cscale(HB, 0.5f), cscale(q, 0.5f));
@@ -683,6 +713,27 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                     }
                     __syncwarp();
                 }
+                if (soft_on) {
+                    const int hb = nb > 1 ? nb >> 1 : 1;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            if (t < hb && (u == 0 || nb > 1)) {
+                                const int k = u * hb + t;
+                                if (carA >= 0) { s_soft[wib][(carA << 3) | k] = (int8_t)sqA.q[u][t]; soft_rows[row * SOFT_ROW + carA * nb + k] = (int8_t)sqA.q[u][t]; }
+                                if (carB >= 0) { s_soft[wib][(carB << 3) | k] = (int8_t)sqB.q[u][t]; soft_rows[row * SOFT_ROW + carB * nb + k] = (int8_t)sqB.q[u][t]; }
+                            }
+                        }
+                    __syncwarp();
+                    for (int w = lane; w < swps; w += 32) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) word |= (uint32_t)(uint8_t)s_soft[wib][s_slut[wib][4 * w + k]] << (8 * k);
+                        vsw[(n - 3) * swps + w] = word;
+                    }
+                    __syncwarp();
+                }
                 ++n_rows;
             }
         }
@@ -692,7 +743,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) st->prev_pil[q] = pp[q];
-            st->d_er = d_er; st->eps0 = eps0; st->snr = snr;
+            st->d_er = d_er; st->eps0 = eps0; st->snr = snr; st->havg = havg;
         }
     } else if (lane == 0) {
         frames[f].n_rows = n_rows;
@@ -770,7 +821,7 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_signal(wifi_b200_frame *frames, i
 // SIGNAL-less are planned in parallel; any other group falls back to the sequential machine.
 struct PlanState { int cur, copied, need, pending; JobDesc J; bool bad; };
 
-__device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *frames, JobDesc *jobs, int *pack_list, int *n_pack, int *err)
+__device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *frames, JobDesc *jobs, int *pack_list, int *n_pack, int *err, int soft)
 {
     for (int fi = f0; fi < f1; ++fi) {
         wifi_b200_frame F = frames[fi];
@@ -804,7 +855,7 @@ __device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *f
             if (S.bad) { atomicExch(err, WIFI_E_OVERFLOW); continue; }
             for (int s = S.J.n_seg; s < 4; ++s) { S.J.seg_row[s] = 0; S.J.seg_cnt[s] = 0; }
             bool own = (S.J.n_seg == 1 && fi == S.cur);
-            S.J.need_pack = (!own || (c_tab.mcs[S.J.enc].n_dbps & 7) != 0) ? 1 : 0;
+            S.J.need_pack = (!own || (!soft && (c_tab.mcs[S.J.enc].n_dbps & 7) != 0)) ? 1 : 0;
             jobs[S.cur] = S.J;
             if (S.J.need_pack) pack_list[atomicAdd(n_pack, 1)] = S.cur;
             frames[S.cur].decoded = 1;
@@ -814,7 +865,7 @@ __device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *f
 }
 
 __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links, int n_links, wifi_b200_frame *frames, JobDesc *jobs,
-                                               int *pack_list, int *n_pack, int *err)
+                                               int *pack_list, int *n_pack, int *err, int soft)
 {
     int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (l >= n_links) return;
@@ -841,7 +892,7 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
                 J.frame = fi; J.enc = enc; J.len = len; J.n_sym = fsym; J.n_seg = 1;
                 J.seg_row[0] = (int32_t)row_off; J.seg_cnt[0] = fsym;
                 for (int s = 1; s < 4; ++s) { J.seg_row[s] = 0; J.seg_cnt[s] = 0; }
-                J.need_pack = (c_tab.mcs[enc].n_dbps & 7) != 0 ? 1 : 0;
+                J.need_pack = (!soft && (c_tab.mcs[enc].n_dbps & 7) != 0) ? 1 : 0;
                 jobs[fi] = J;
                 if (J.need_pack) pack_list[atomicAdd(n_pack, 1)] = fi;
                 frames[fi].accepted = 1;
@@ -859,7 +910,7 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
             }
         } else {
             __syncwarp();   // the jobs[].n_sym = 0 defaults above must land before the sequential writes
-            if (lane == 0) plan_sequential(S, f0, f0 + 32 < fend ? f0 + 32 : fend, frames, jobs, pack_list, n_pack, err);
+            if (lane == 0) plan_sequential(S, f0, f0 + 32 < fend ? f0 + 32 : fend, frames, jobs, pack_list, n_pack, err, soft);
             S.cur = __shfl_sync(0xffffffffu, S.cur, 0);
             S.copied = __shfl_sync(0xffffffffu, S.copied, 0);
             S.need = __shfl_sync(0xffffffffu, S.need, 0);
@@ -944,7 +995,8 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     for (int k = 0; k < 6; ++k) v.step((prev >> (4 * k)) & 0xfu);
     int slot = 1 % ntb;
     v.end_chunk(ring, slot, ntb, tid);
-    uint32_t state = 0, crc = 0xffffffffu, accw = 0;
+    PsduSink sink;
+    sink.init(out, L, s_crc, s_scr);
     uint32_t next = 1 < nw ? in[1] : 0u;
 #pragma unroll 1
     for (int chunk = 1; chunk <= last_chunk; ++chunk) {
@@ -955,25 +1007,88 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
         for (int k = 0; k < 8; ++k) v.step((bits >> (4 * k)) & 0xfu);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
         uint32_t c = v.end_chunk(ring, slot, ntb, tid, (chunk & 3) == 0);
-        if (chunk >= ntb) {
-            int m = chunk - ntb;   // decoded byte index
-            if (m == 0) {
-                // descramble(): state from the first 7 decoded bits, bit 7 is the first data bit
-                state = c >> 1;
-                uint32_t fb = ((state >> 6) ^ (state >> 3)) & 1u;
-                state = ((state << 1) & 0x7eu) | fb;
-            } else {
-                uint32_t tabv = s_scr[state];
-                uint32_t byte = (__brev(c) >> 24) ^ (tabv & 0xffu);
-                state = tabv >> 8;
-                int pidx = m - 2;
-                if (pidx >= 0) {
-                    crc = s_crc[(crc ^ byte) & 0xffu] ^ (crc >> 8);
-                    accw |= byte << (8 * (pidx & 3));
-                    if ((pidx & 3) == 3 || pidx == L - 1) { out[pidx >> 2] = accw; accw = 0; }
-                }
+        if (chunk >= ntb) sink.push(c, chunk - ntb);
+    }
+    frames[J.frame].crc_ok = sink.crc_ok();
+}
+
+// ------------------------------------------------------------------ soft-decision variants
+// trellis words for gathered jobs in soft mode: word = 2 steps x 2 int8 soft symbols, erasure = 0
+__global__ void __launch_bounds__(256) k_pack_soft(const JobDesc *__restrict__ jobs, const int *__restrict__ pack_list, const int *__restrict__ n_pack,
+                                                    const int8_t *__restrict__ soft_rows, const uint16_t *__restrict__ depunct_lut,
+                                                    uint32_t *__restrict__ vit_soft_in)
+{
+    const int np = *n_pack;
+    for (int e = blockIdx.y; e < np; e += gridDim.y) {
+        const JobDesc J = jobs[pack_list[e]];
+        const McsDesc m = c_tab.mcs[J.enc];
+        const int per = 2 * m.n_dbps;
+        const int n_words = J.n_sym * (m.n_dbps >> 1);
+        const uint16_t *lut = depunct_lut + J.enc * 432;
+        uint32_t *vw = vit_soft_in + (int64_t)J.frame * SOFT_MAXW;
+        for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+            int q = 4 * w;
+            int s = q / per, qi = q - s * per;   // 4 positions never straddle a symbol (per % 4 == 0)
+            int seg = 0, sbase = 0;
+            while (seg < J.n_seg - 1 && s >= sbase + J.seg_cnt[seg]) { sbase += J.seg_cnt[seg]; ++seg; }
+            const int8_t *rp = soft_rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * SOFT_ROW;
+            uint32_t word = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint16_t en = lut[qi + k];
+                uint32_t b = (en == 0xffffu) ? 0u : (uint32_t)(uint8_t)rp[(en >> 3) * m.n_bpsc + (en & 7)];
+                word |= b << (8 * k);
             }
+            vw[w] = word;
         }
     }
-    frames[J.frame].crc_ok = ((crc ^ 0xffffffffu) == 558161692u) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi_soft(const JobDesc *__restrict__ jobs, int n_frames, const uint32_t *__restrict__ vit_soft_in,
+                                                             uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
+{
+    extern __shared__ uint32_t vsm[];
+    uint32_t *ring = vsm;
+    uint32_t *s_crc = vsm + VIT_NTB_MAX * 16 * VIT_BLOCK;
+    uint16_t *s_scr = (uint16_t *)(s_crc + 256);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += VIT_BLOCK) s_crc[i] = c_tab.crc_tab[i];
+    for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
+    __syncthreads();
+    const int job = blockIdx.x * VIT_BLOCK + tid;
+    if (job >= n_frames) return;
+    const JobDesc J = jobs[job];
+    if (J.n_sym == 0) return;
+    const int punct = c_tab.mcs[J.enc].punct;
+    const int ntb = punct == 0 ? 5 : (punct == 1 ? 9 : 10);
+    const int nw = J.n_sym * (c_tab.mcs[J.enc].n_dbps >> 1);     // data words, 2 steps each; later words read 0
+    const uint32_t *in = vit_soft_in + (int64_t)job * SOFT_MAXW;
+    const int L = J.len;
+    const int last_chunk = L + 1 + ntb;
+    VitCoreSoft v;
+    v.init();
+    PsduSink sink;
+    sink.init(psdu + (int64_t)job * (PSDU_STRIDE / 4), L, s_crc, s_scr);
+    int wi = 0;
+    auto two_steps = [&](uint32_t word) {
+        v.step((int)(int8_t)(word & 0xffu), (int)(int8_t)((word >> 8) & 0xffu));
+        v.step((int)(int8_t)((word >> 16) & 0xffu), (int)(int8_t)(word >> 24));
+    };
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k, ++wi) two_steps(wi < nw ? in[wi] : 0u);
+    int slot = 1 % ntb;
+    v.end_chunk(ring, slot, ntb, tid, true);
+#pragma unroll 1
+    for (int chunk = 1; chunk <= last_chunk; ++chunk) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w4[k] = (wi + k < nw) ? in[wi + k] : 0u;
+        wi += 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) two_steps(w4[k]);
+        slot = (slot + 1 == ntb) ? 0 : slot + 1;
+        uint32_t c = v.end_chunk(ring, slot, ntb, tid, (chunk & 1) == 0);
+        if (chunk >= ntb) sink.push(c, chunk - ntb);
+    }
+    frames[J.frame].crc_ok = sink.crc_ok();
 }

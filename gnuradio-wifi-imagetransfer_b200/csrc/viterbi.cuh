@@ -137,3 +137,136 @@ struct VitCore {
         return c;
     }
 };
+
+// descramble + CRC-32 + PSDU word assembly shared by the hard and soft decoders
+// ([UPSTREAM] decode_mac.cc descramble(), boost::crc_32_type).  push() takes the traceback byte c
+// (MSB = earliest bit) of decoded byte index m.
+struct PsduSink {
+    uint32_t state, crc, accw;
+    uint32_t *out;
+    int L;
+    const uint32_t *s_crc;
+    const uint16_t *s_scr;
+    __device__ __forceinline__ void init(uint32_t *o, int len, const uint32_t *crc_tab, const uint16_t *scr_tab)
+    {
+        state = 0; crc = 0xffffffffu; accw = 0; out = o; L = len; s_crc = crc_tab; s_scr = scr_tab;
+    }
+    __device__ __forceinline__ void push(uint32_t c, int m)
+    {
+        if (m == 0) {
+            // state from the first 7 decoded bits, bit 7 is the first descrambled bit (SERVICE)
+            state = c >> 1;
+            uint32_t fb = ((state >> 6) ^ (state >> 3)) & 1u;
+            state = ((state << 1) & 0x7eu) | fb;
+            return;
+        }
+        uint32_t tabv = s_scr[state];
+        uint32_t byte = (__brev(c) >> 24) ^ (tabv & 0xffu);
+        state = tabv >> 8;
+        int pidx = m - 2;
+        if (pidx >= 0) {
+            crc = s_crc[(crc ^ byte) & 0xffu] ^ (crc >> 8);
+            accw |= byte << (8 * (pidx & 3));
+            if ((pidx & 3) == 3 || pidx == L - 1) { out[pidx >> 2] = accw; accw = 0; }
+        }
+    }
+    __device__ __forceinline__ int crc_ok() const { return ((crc ^ 0xffffffffu) == 558161692u) ? 1 : 0; }
+};
+
+// Soft-decision variant (oracle viterbi_soft): 16-bit path metrics, two states per register, branch
+// metric = correlation of the expected output bits with int8 soft inputs, offset +254 per step.
+struct VitCoreSoft {
+    uint32_t M[32], P[32];
+
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { M[i] = 0; P[i] = 0; }
+    }
+    // selector picking halfword (2A+B) of the (Tlo, Thi) pair for butterflies 2j (low lane), 2j+1 (high lane)
+    static __host__ __device__ constexpr uint32_t selx(int j)
+    {
+        uint32_t s = 0;
+        for (int b = 0; b < 2; ++b) {
+            uint32_t k = 2 * j + b;
+            uint32_t idx = 2 * vit_par((2 * k) & 0x6d) + vit_par((2 * k) & 0x4f);
+            s |= ((2 * idx) | ((2 * idx + 1) << 4)) << (8 * b);
+        }
+        return s;
+    }
+    __device__ __forceinline__ void step(int q0, int q1)
+    {
+        const uint32_t t11 = (uint32_t)(q0 + q1 + 254), t00 = 508u - t11;
+        const uint32_t t10 = (uint32_t)(q0 - q1 + 254), t01 = 508u - t10;
+        const uint32_t Tlo = t00 | (t01 << 16), Thi = t10 | (t11 << 16);
+        uint32_t Mn[32], Pn[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t x = prmt(Tlo, Thi, selx(j)), y = 0x01fc01fcu - x;
+            const uint32_t lo = M[j], hi = M[j + 16];
+            const uint32_t m0 = lo + x, m1 = hi + y, m2 = lo + y, m3 = hi + x;
+            const uint32_t k0 = prmt(m0 + 0x7fff7fffu - m1, 0u, 0xbb99u);   // 0xffff where m0 > m1
+            const uint32_t k1 = prmt(m2 + 0x7fff7fffu - m3, 0u, 0xbb99u);
+            const uint32_t v0 = (m0 & k0) | (m1 & ~k0);
+            const uint32_t v1 = (m2 & k1) | (m3 & ~k1);
+            const uint32_t sh0 = P[j] << 1, sh1 = (P[j + 16] << 1) | 0x00010001u;
+            const uint32_t p0 = (sh0 & k0) | (sh1 & ~k0);
+            const uint32_t p1 = (sh0 & k1) | (sh1 & ~k1);
+            Mn[2 * j] = prmt(v0, v1, 0x5410u);
+            Mn[2 * j + 1] = prmt(v0, v1, 0x7632u);
+            Pn[2 * j] = prmt(p0, p1, 0x5410u);
+            Pn[2 * j + 1] = prmt(p0, p1, 0x7632u);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { M[i] = Mn[i]; P[i] = Pn[i]; }
+    }
+    static __device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b)
+    {
+        uint32_t k = prmt((a | 0x80008000u) - b, 0u, 0xbb99u);
+        return (a & k) | (b & ~k);
+    }
+    static __device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b)
+    {
+        uint32_t k = prmt((a | 0x80008000u) - b, 0u, 0xbb99u);
+        return (b & k) | (a & ~k);
+    }
+    __device__ __forceinline__ uint32_t end_chunk(uint32_t *ring, int slot, int ntb, int tid, bool renorm)
+    {
+#pragma unroll
+        for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = prmt(P[2 * w], P[2 * w + 1], 0x6420u);
+        uint32_t mx = M[0];
+#pragma unroll
+        for (int w = 1; w < 32; ++w) mx = vmax2(mx, M[w]);
+        mx = vmax2(mx, mx >> 16);
+        const uint32_t bestw = (mx & 0xffffu) * 0x00010001u;
+        int wsel = 0;
+        uint32_t zsel = 0;
+#pragma unroll
+        for (int w = 31; w >= 0; --w) {
+            uint32_t x = M[w] ^ bestw;
+            uint32_t z = ((x + 0x7fff7fffu) & 0x80008000u) ^ 0x80008000u;   // bit 15 / 31 set where equal
+            if (z) { wsel = w; zsel = z; }
+        }
+        int bs = wsel * 2 + ((__ffs((int)zsel) - 16) >> 4);
+        int sl = slot;
+        for (int i = 0; i < ntb - 1; ++i) {
+            uint32_t w = ring[(sl * 16 + (bs >> 2)) * VIT_BLOCK + tid];
+            bs = (int)((w >> (8 * (bs & 3))) & 0xffu) >> 2;
+            sl = (sl == 0) ? ntb - 1 : sl - 1;
+        }
+        uint32_t w = ring[(sl * 16 + (bs >> 2)) * VIT_BLOCK + tid];
+        uint32_t c = (w >> (8 * (bs & 3))) & 0xffu;
+        if (renorm) {
+            uint32_t mn = M[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) mn = vmin2(mn, M[i]);
+            mn = vmin2(mn, mn >> 16);
+            const uint32_t minw = (mn & 0xffffu) * 0x00010001u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) M[i] -= minw;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) P[i] = 0;
+        return c;
+    }
+};

@@ -170,6 +170,8 @@ struct wifi_b200 {
     cf *d_carrier = nullptr;
     JobDesc *d_jobs = nullptr;
     uint32_t *d_vit_in = nullptr;
+    int8_t *d_soft = nullptr;          // soft mode: int8 per coded bit, SOFT_ROW per row
+    uint32_t *d_vit_soft_in = nullptr; // soft mode trellis words
     uint32_t *d_psdu = nullptr;
     uint16_t *d_depunct = nullptr;
     int *d_counters = nullptr;     // [0] frames [1] pack-list length [2] err ; ints 8..9: row counter (u64)
@@ -241,7 +243,7 @@ void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
-                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_spec_trig, h->d_spec_cnt, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
+                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_frames) cudaFreeHost(h->h_frames);
@@ -249,6 +251,13 @@ void free_all(wifi_b200 *h)
     if (h->h_iq) cudaFreeHost(h->h_iq);
     for (int i = 0; i <= ST_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
+}
+
+int ensure_soft(wifi_b200 *h)
+{
+    if (!h->d_soft) CK(cudaMalloc(&h->d_soft, (size_t)h->row_cap * SOFT_ROW));
+    if (!h->d_vit_soft_in) CK(cudaMalloc(&h->d_vit_soft_in, (size_t)h->cfg.max_frames * SOFT_MAXW * 4));
+    return WIFI_OK;
 }
 
 int ensure_iq_staging(wifi_b200 *h)
@@ -326,24 +335,32 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
     h->n_jobs = nf;       // decode jobs live at the index of their owner frame
     h->n_rows = rows_needed;
     if (nf > 0) {
-        DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier};
+        const int soft = h->cfg.soft_decision ? 1 : 0;
+        if (soft) { int rc_ = ensure_soft(h); if (rc_) return rc_; }
+        DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier, soft};
         k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf);
         mark(h, ST_DEMOD_HEAD);
         k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 0,
-                                                          h->d_depunct, h->d_vit_in);
+                                                          h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_SIGNAL);
         k_signal<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, 0, s>>>(h->d_frames, (int)nf, h->d_states);
         mark(h, ST_DEMOD_DATA);
         k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1,
-                                                          h->d_depunct, h->d_vit_in);
+                                                          h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_PLAN);
         k_plan<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_pack_list, h->d_counters + 1,
-                                                          h->d_counters + 2);
+                                                          h->d_counters + 2, soft);
         mark(h, ST_PACK);
-        k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in);
-        mark(h, ST_VITERBI);
         size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256;
-        k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
+        if (!soft) {
+            k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in);
+            mark(h, ST_VITERBI);
+            k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
+        } else {
+            k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in);
+            mark(h, ST_VITERBI);
+            k_viterbi_soft<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_soft_in, h->d_psdu, h->d_frames);
+        }
     }
     mark(h, ST_D2H);
     if (mirror && h->n_triggers > 0) {
@@ -517,6 +534,7 @@ int wifi_b200_set_param(wifi_b200_t *h, int id, double v)
     case WIFI_P_CHAN_EST: if (v < 0 || v > 3) return WIFI_E_ARG; h->cfg.chan_est = (int)v; break;
     case WIFI_P_ENCODING: if (v < 0 || v > 7) return WIFI_E_ARG; h->cfg.encoding = (int)v; break;
     case WIFI_P_MIN_PLATEAU: if (v < 1 || v > 16) return WIFI_E_ARG; h->cfg.min_plateau = (int)v; break;
+    case WIFI_P_SOFT_DECISION: h->cfg.soft_decision = v != 0; break;
     case WIFI_P_WANT_CARRIER:
         if (v != 0 && !h->d_carrier) {
             cudaSetDevice(h->device);
@@ -541,6 +559,7 @@ double wifi_b200_get_param(wifi_b200_t *h, int id)
     case WIFI_P_ENCODING: return h->cfg.encoding;
     case WIFI_P_MIN_PLATEAU: return h->cfg.min_plateau;
     case WIFI_P_WANT_CARRIER: return h->cfg.want_carrier;
+    case WIFI_P_SOFT_DECISION: return h->cfg.soft_decision;
     default: return NAN;
     }
 }
@@ -795,6 +814,17 @@ int wifi_b200_rx_rows(wifi_b200_t *h, uint8_t *rows, float *carrier, int64_t cap
         if (!h->d_carrier || !h->cfg.want_carrier) { h->err = "carrier output not enabled"; return WIFI_E_ARG; }
         if (h->n_rows) CK(cudaMemcpy(carrier, h->d_carrier, (size_t)h->n_rows * 48 * sizeof(cf), cudaMemcpyDeviceToHost));
     }
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_soft(wifi_b200_t *h, int8_t *soft, int64_t cap_rows)
+{
+    if (!h || !soft) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (!h->cfg.soft_decision || !h->d_soft) { h->err = "soft decisions not enabled"; return WIFI_E_ARG; }
+    if (cap_rows < h->n_rows) return WIFI_E_OVERFLOW;
+    if (h->n_rows) CK(cudaMemcpy(soft, h->d_soft, (size_t)h->n_rows * SOFT_ROW, cudaMemcpyDeviceToHost));
     return WIFI_OK;
 }
 

@@ -19,6 +19,8 @@
 #define DET_TILE (DET_THREADS * FE_CHUNK)   // 8192 samples
 #define PSDU_STRIDE 1536        // bytes reserved per decode job in the psdu store
 #define VIT_MAXW 1560           // 32-bit words (8 trellis steps each) reserved per decode job
+#define SOFT_MAXW 6240          // soft mode: one word = 2 trellis steps x 2 int8 soft symbols
+#define SOFT_ROW 288            // soft values reserved per data symbol (N_CBPS <= 288)
 
 struct cf { float re, im; };
 __device__ __forceinline__ cf cadd(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
@@ -80,6 +82,8 @@ struct EqState {
     double d_er;
     double eps0;
     double snr;
+    float havg;           // mean |H|^2 over the 52 used carriers after the LTS estimate (soft mode weights)
+    float pad0;
     uint8_t sig_bits[48];
 };
 
@@ -158,6 +162,41 @@ __device__ __forceinline__ void warp_fft64(cf &a, cf &b, int lane, const WarpTw 
     cf u = a;
     a = cadd(u, t);
     b = csub(u, t);
+}
+
+// max-log LLR of one axis bit, weighted and quantised exactly as oracle soft_q(): clamp(rint((l*w)*16), +-127)
+__device__ __forceinline__ int dev_soft_q(float l, float w)
+{
+    float v = rintf((l * w) * 16.0f);
+    if (v > 127.f) v = 127.f;
+    if (v < -127.f) v = -127.f;
+    return (int)v;
+}
+// soft values of one carrier (oracle soft_demap).  q[u][t]: axis u (0 = I, 1 = Q), t = 0 sign bit,
+// 1 inner-half bit, 2 ring bit; coded bit k = u * (nb/2) + t.  BPSK: q[0][0] only.
+struct SoftQ { int q[2][3]; };
+__device__ __forceinline__ SoftQ dev_soft_demap(int nb, cf s, float w)
+{
+    SoftQ r;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) r.q[u][t] = 0;
+    if (nb == 1) { r.q[0][0] = dev_soft_q(s.re, w); return r; }
+    const int h = nb >> 1;
+    const float level = (h == 1) ? sqrtf(0.5f) : (h == 2) ? sqrtf(0.1f) : sqrtf(1.0f / 42.0f);
+    const float ax[2] = {s.re / level, s.im / level};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const float a = ax[u], m = fabsf(a);
+        r.q[u][0] = dev_soft_q(a, w);
+        if (h == 2) r.q[u][1] = dev_soft_q(2.0f - m, w);
+        if (h == 3) {
+            r.q[u][1] = dev_soft_q(4.0f - m, w);
+            r.q[u][2] = dev_soft_q(2.0f - fabsf(m - 4.0f), w);
+        }
+    }
+    return r;
 }
 
 // constellation point of a decided index, computed exactly as the table is built

@@ -17,14 +17,14 @@ PSDU_STRIDE = 1536
 
 ENCODINGS = ("BPSK_1_2", "BPSK_3_4", "QPSK_1_2", "QPSK_3_4", "QAM16_1_2", "QAM16_3_4", "QAM64_2_3", "QAM64_3_4")
 EQUALIZERS = ("LS", "LMS", "COMB", "STA")
-P_BANDWIDTH, P_FREQUENCY, P_SENSITIVITY, P_CHAN_EST, P_ENCODING, P_MIN_PLATEAU, P_WANT_CARRIER = range(7)
+P_BANDWIDTH, P_FREQUENCY, P_SENSITIVITY, P_CHAN_EST, P_ENCODING, P_MIN_PLATEAU, P_WANT_CARRIER, P_SOFT_DECISION = range(8)
 E_ARG, E_TOO_LARGE, E_CUDA, E_NOMEM, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4, -5, -6
 
 
 class Cfg(C.Structure):
     _fields_ = [("bandwidth", C.c_double), ("frequency", C.c_double), ("sensitivity", C.c_double),
                 ("chan_est", C.c_int32), ("encoding", C.c_int32), ("min_plateau", C.c_int32), ("device", C.c_int32),
-                ("want_carrier", C.c_int32), ("reserved", C.c_int32), ("max_samples", C.c_int64), ("max_frames", C.c_int64)]
+                ("want_carrier", C.c_int32), ("soft_decision", C.c_int32), ("max_samples", C.c_int64), ("max_frames", C.c_int64)]
 
 
 class ChanSeg(C.Structure):
@@ -57,7 +57,7 @@ EXPORTS = [
     "wifi_b200_get_param", "wifi_b200_last_error", "wifi_b200_strerror", "wifi_b200_stream", "wifi_b200_sync",
     "wifi_b200_mac_frame", "wifi_b200_n_sym", "wifi_b200_frame_samples", "wifi_b200_tx", "wifi_b200_tx_dev",
     "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_counts",
-    "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_flags", "wifi_b200_rx_push",
+    "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
 ]
 
@@ -97,6 +97,7 @@ def lib():
         L.wifi_b200_rx_frames.argtypes = [vp, vp, i64]
         L.wifi_b200_rx_rows.argtypes = [vp, vp, vp, i64]
         L.wifi_b200_rx_psdus.argtypes = [vp, vp, C.c_size_t]
+        L.wifi_b200_rx_soft.argtypes = [vp, vp, i64]
         L.wifi_b200_rx_flags.argtypes = [vp, C.c_int, vp, i64]
         L.wifi_b200_rx_push.argtypes = [vp, vp, C.c_size_t, C.c_int]
         L.wifi_b200_rx_pop.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_int)]
@@ -165,9 +166,9 @@ class RxResult:
 
 class Handle:
     def __init__(self, bandwidth=10e6, frequency=5.89e9, sensitivity=0.56, chan_est=0, encoding=0, min_plateau=2,
-                 device=0, want_carrier=False, max_samples=1 << 22, max_frames=0):
+                 device=0, want_carrier=False, max_samples=1 << 22, max_frames=0, soft_decision=False):
         self._L = lib()
-        cfg = Cfg(bandwidth, frequency, sensitivity, int(chan_est), int(encoding), min_plateau, device, int(want_carrier), 0,
+        cfg = Cfg(bandwidth, frequency, sensitivity, int(chan_est), int(encoding), min_plateau, device, int(want_carrier), int(soft_decision),
                   int(max_samples), int(max_frames))
         h = C.c_void_p()
         rc = self._L.wifi_b200_create(C.byref(cfg), C.byref(h))
@@ -282,6 +283,12 @@ class Handle:
         car = np.zeros((c["n_rows"], 48), np.complex64) if carrier else None
         self._ck(self._L.wifi_b200_rx_rows(self._h, _p(rows), _p(car), c["n_rows"]))
         return (rows, car) if carrier else rows
+
+    def soft_rows(self):
+        c = self.counts()
+        s = np.zeros((c["n_rows"], 288), np.int8)
+        self._ck(self._L.wifi_b200_rx_soft(self._h, _p(s), c["n_rows"]))
+        return s
 
     def flags(self, link, n_samples):
         w = np.zeros((n_samples + 31) // 32, np.uint32)

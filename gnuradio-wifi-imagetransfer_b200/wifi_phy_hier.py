@@ -47,12 +47,12 @@ class mac:
 
 class wifi_phy_hier:
     def __init__(self, bandwidth=10e6, chan_est=LS, encoding=BPSK_1_2, frequency=5.89e9, sensitivity=0.56,
-                 device=0, max_samples=1 << 22, max_frames=0, want_carrier=False):
+                 device=0, max_samples=1 << 22, max_frames=0, want_carrier=False, soft_decision=False):
         self.bandwidth, self.chan_est, self.encoding = float(bandwidth), int(chan_est), int(encoding)
         self.frequency, self.sensitivity = float(frequency), float(sensitivity)
         self._h = _w.Handle(bandwidth=bandwidth, frequency=frequency, sensitivity=sensitivity, chan_est=int(chan_est),
                             encoding=int(encoding), device=device, max_samples=max_samples, max_frames=max_frames,
-                            want_carrier=want_carrier)
+                            want_carrier=want_carrier, soft_decision=soft_decision)
         self._want_carrier = bool(want_carrier)
         self._mac_out_cb, self._carrier_cb = [], []
         self.samp_out = []          # bursts produced by mac_in, in order
@@ -92,6 +92,10 @@ class wifi_phy_hier:
     def set_sensitivity(self, sensitivity):
         self.sensitivity = float(sensitivity)
         self._h.set_param(_w.P_SENSITIVITY, sensitivity)
+
+    def set_soft_decision(self, on):
+        """Extension (no reference counterpart): max-log LLR demapper + soft-decision Viterbi."""
+        self._h.set_param(_w.P_SOFT_DECISION, 1 if on else 0)
 
     @property
     def handle(self):

@@ -52,7 +52,7 @@ enum { WIFI_BPSK_1_2 = 0, WIFI_BPSK_3_4, WIFI_QPSK_1_2, WIFI_QPSK_3_4, WIFI_QAM1
 enum { WIFI_EQ_LS = 0, WIFI_EQ_LMS = 1, WIFI_EQ_COMB = 2, WIFI_EQ_STA = 3 };
 /* ids for wifi_b200_set_param: the hier block's parameters */
 enum { WIFI_P_BANDWIDTH = 0, WIFI_P_FREQUENCY = 1, WIFI_P_SENSITIVITY = 2, WIFI_P_CHAN_EST = 3, WIFI_P_ENCODING = 4,
-       WIFI_P_MIN_PLATEAU = 5, WIFI_P_WANT_CARRIER = 6 };
+       WIFI_P_MIN_PLATEAU = 5, WIFI_P_WANT_CARRIER = 6, WIFI_P_SOFT_DECISION = 7 };
 
 typedef struct wifi_b200_cfg {
     double bandwidth;      /* Hz, hier default 10e6 (wifi_phy_hier.grc:92)                        */
@@ -63,7 +63,7 @@ typedef struct wifi_b200_cfg {
     int32_t min_plateau;   /* 2 (:725)                                                           */
     int32_t device;        /* CUDA device ordinal                                                */
     int32_t want_carrier;  /* keep the equalised constellation points (`carrier` port)            */
-    int32_t reserved;
+    int32_t soft_decision; /* 0: hard decisions as the reference; 1: max-log LLR demapper + soft Viterbi */
     int64_t max_samples;   /* capacity of one rx call, complex samples summed over links          */
     int64_t max_frames;    /* capacity of one rx/tx call, frames (sync_short triggers)            */
 } wifi_b200_cfg;
@@ -155,6 +155,8 @@ int  wifi_b200_rx_counts(wifi_b200_t *h, int64_t *n_frames, int64_t *n_rows, int
 int  wifi_b200_rx_frames(wifi_b200_t *h, wifi_b200_frame *out, int64_t cap);
 int  wifi_b200_rx_rows(wifi_b200_t *h, uint8_t *rows /* n_rows*48 or NULL */, float *carrier /* n_rows*96 or NULL */, int64_t cap_rows);
 int  wifi_b200_rx_psdus(wifi_b200_t *h, uint8_t *store, size_t cap);
+/* soft mode: int8 soft value per coded bit, 288 per row (first N_CBPS used, order carrier*N_BPSC+bit) */
+int  wifi_b200_rx_soft(wifi_b200_t *h, int8_t *soft, int64_t cap_rows);
 /* autocorrelation front-end decisions for one link: bit n of flags = (c[n] > sensitivity) */
 int  wifi_b200_rx_flags(wifi_b200_t *h, int link, uint32_t *flags, int64_t cap_words);
 

@@ -23,7 +23,7 @@ FRAME_DTYPE = np.dtype([
 
 class RxCfg(C.Structure):
     _fields_ = [("threshold", C.c_double), ("min_plateau", C.c_int32), ("algo", C.c_int32), ("freq", C.c_double),
-                ("bw", C.c_double), ("final", C.c_int32), ("want_carrier", C.c_int32)]
+                ("bw", C.c_double), ("final", C.c_int32), ("want_carrier", C.c_int32), ("soft", C.c_int32), ("pad", C.c_int32)]
 
 
 class ChanCfg(C.Structure):
@@ -57,6 +57,7 @@ def lib():
         for f in ("orc_rx_n_frames", "orc_rx_n_rows", "orc_rx_psdu_bytes", "orc_rx_free"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_rx_copy.argtypes = [C.c_void_p] * 5
+        L.orc_rx_copy_soft.argtypes = [C.c_void_p] * 2
     return _LIB
 
 
@@ -154,6 +155,13 @@ def viterbi(depunctured, n_bits, ntraceback):
     return o[:n_bits]
 
 
+def viterbi_soft(depunctured, n_bits, ntraceback):
+    d = np.ascontiguousarray(depunctured, np.int8)
+    o = np.zeros(n_bits + 8, np.uint8)
+    lib().orc_viterbi_soft(_p(d), C.c_int(d.size), C.c_int(n_bits), C.c_int(ntraceback), _p(o))
+    return o[:n_bits]
+
+
 def crc32(data):
     d = np.frombuffer(bytes(data), np.uint8)
     return lib().orc_crc32(_p(d), C.c_int(d.size))
@@ -231,11 +239,11 @@ class RxResult:
         return [self.psdu(i)[:-4] for i in range(len(self.frames)) if self.frames[i]["crc_ok"]]
 
 
-def rx_cfg(threshold=0.56, min_plateau=2, algo=0, freq=5.89e9, bw=10e6, final=True, want_carrier=True):
-    return RxCfg(threshold, min_plateau, algo, freq, bw, int(final), int(want_carrier))
+def rx_cfg(threshold=0.56, min_plateau=2, algo=0, freq=5.89e9, bw=10e6, final=True, want_carrier=True, soft=False):
+    return RxCfg(threshold, min_plateau, algo, freq, bw, int(final), int(want_carrier), int(soft), 0)
 
 
-def _collect(h, want_carrier):
+def _collect(h, want_carrier, soft=False):
     L = lib()
     nf, nr, nb = L.orc_rx_n_frames(h), L.orc_rx_n_rows(h), L.orc_rx_psdu_bytes(h)
     frames = np.zeros(nf, FRAME_DTYPE)
@@ -243,15 +251,20 @@ def _collect(h, want_carrier):
     carrier = np.zeros((nr, 48), np.complex64) if want_carrier else None
     psdu = np.zeros(nb, np.uint8)
     L.orc_rx_copy(h, _p(frames), _p(rows), _p(carrier) if want_carrier else None, _p(psdu))
+    res = RxResult(frames, rows, carrier, psdu)
+    res.soft = None
+    if soft:
+        res.soft = np.zeros((nr, 288), np.int8)
+        L.orc_rx_copy_soft(h, _p(res.soft))
     L.orc_rx_free(h)
-    return RxResult(frames, rows, carrier, psdu)
+    return res
 
 
 def rx(x, link=0, **kw):
     cfg = rx_cfg(**kw)
     a = np.ascontiguousarray(x, np.complex64)
     h = lib().orc_rx(_p(a), C.c_int64(a.size), C.c_int(link), C.byref(cfg))
-    return _collect(C.c_void_p(h), bool(cfg.want_carrier))
+    return _collect(C.c_void_p(h), bool(cfg.want_carrier), bool(cfg.soft))
 
 
 def rx_links(x, offsets, lengths, n_threads=1, **kw):
@@ -260,4 +273,4 @@ def rx_links(x, offsets, lengths, n_threads=1, **kw):
     off = np.ascontiguousarray(offsets, np.int64)
     ln = np.ascontiguousarray(lengths, np.int64)
     h = lib().orc_rx_links(_p(a), _p(off), _p(ln), C.c_int(off.size), C.byref(cfg), C.c_int(n_threads))
-    return _collect(C.c_void_p(h), bool(cfg.want_carrier))
+    return _collect(C.c_void_p(h), bool(cfg.want_carrier), bool(cfg.soft))

@@ -435,6 +435,72 @@ static int viterbi(const uint8_t *sym, int n_avail, int n_bits, int ntb, uint8_t
     }
     return step;
 }
+/* Soft-decision variant (new capability): same trellis, tie rule and chunked traceback
+ * as viterbi(); the branch metric is the correlation of the expected output bits with the soft
+ * inputs q in [-127,127] (0 = erasure / past the end), offset by +254 so metrics never go negative. */
+static int viterbi_soft(const int8_t *sym, int n_avail, int n_bits, int ntb, uint8_t *out_bits)
+{
+    static uint8_t bt0[32], bt1[32];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 32; ++i) {
+            bt0[i] = parity8((2 * i) & 0x6d);
+            bt1[i] = parity8((2 * i) & 0x4f);
+        }
+        init = true;
+    }
+    int32_t M[2][64];
+    uint8_t P[2][64], pp[10][64];
+    std::memset(M, 0, sizeof M);
+    std::memset(P, 0, sizeof P);
+    std::memset(pp, 0, sizeof pp);
+    int store_pos = 0, cur = 0, step = 0, out_count = 0, n_decoded = 0;
+    while (n_decoded < n_bits) {
+        int q0 = (2 * step < n_avail) ? sym[2 * step] : 0;
+        int q1 = (2 * step + 1 < n_avail) ? sym[2 * step + 1] : 0;
+        const int32_t *m = M[cur];
+        const uint8_t *p = P[cur];
+        int32_t *mn = M[cur ^ 1];
+        uint8_t *pn = P[cur ^ 1];
+        for (int k = 0; k < 32; ++k) {
+            int x = (bt0[k] ? q0 : -q0) + (bt1[k] ? q1 : -q1) + 254, y = 508 - x;
+            int32_t m0 = m[k] + x, m1 = m[k + 32] + y, m2 = m[k] + y, m3 = m[k + 32] + x;
+            bool d0 = m0 > m1, d1 = m2 > m3;
+            uint8_t sh0 = (uint8_t)(p[k] << 1), sh1 = (uint8_t)((p[k + 32] << 1) + 1);
+            mn[2 * k] = d0 ? m0 : m1;
+            mn[2 * k + 1] = d1 ? m2 : m3;
+            pn[2 * k] = d0 ? sh0 : sh1;
+            pn[2 * k + 1] = d1 ? sh0 : sh1;
+        }
+        cur ^= 1;
+        ++step;
+        if (step % 8 == 6) {
+            int32_t *mm = M[cur];
+            uint8_t *pc = P[cur];
+            store_pos = (store_pos + 1) % ntb;
+            std::memcpy(pp[store_pos], pc, 64);
+            int best = 0;
+            int32_t bestm = mm[0], minm = mm[0];
+            for (int i = 1; i < 64; ++i) {
+                if (mm[i] > bestm) { bestm = mm[i]; best = i; }
+                if (mm[i] < minm) minm = mm[i];
+            }
+            int pos = store_pos;
+            for (int i = 0; i < ntb - 1; ++i) {
+                best = pp[pos][best] >> 2;
+                pos = (pos - 1 + ntb) % ntb;
+            }
+            uint8_t c = pp[pos][best];
+            for (int i = 0; i < 64; ++i) { pc[i] = 0; mm[i] -= minm; }
+            if (out_count >= ntb) {
+                for (int i = 0; i < 8; ++i) out_bits[(out_count - ntb) * 8 + i] = (c >> (7 - i)) & 1;
+                n_decoded += 8;
+            }
+            ++out_count;
+        }
+    }
+    return step;
+}
 static inline int ntb_of(int enc) { return MCS[enc].punct == 0 ? 5 : (MCS[enc].punct == 1 ? 9 : 10); }
 /* [UP] viterbi_decoder/base.cc depuncture() */
 static int depuncture(const uint8_t *in, int n_in, int enc, uint8_t *out)
@@ -535,13 +601,45 @@ struct Result {
     std::vector<uint8_t> rows;
     std::vector<float> carrier;
     std::vector<uint8_t> psdu;
+    std::vector<int8_t> soft;   /* 288 per row, soft mode only */
 };
+
+/* max-log LLR per coded bit (new capability): per axis a = component / level, bit k=0: a, inner-half bit:
+ * 2-|a| (16-QAM) or 4-|a| (64-QAM), 64-QAM ring bit: 2-||a|-4|; weighted by the carrier's relative channel
+ * power w and quantised to int8: q = clamp(rint((l*w)*16), +-127).  Positive = bit 1 (same sense as decide()). */
+static inline int8_t soft_q(float l, float w)
+{
+    float v = rintf((l * w) * 16.0f);
+    if (v > 127.f) v = 127.f;
+    if (v < -127.f) v = -127.f;
+    return (int8_t)(int)v;
+}
+static inline void soft_demap(int enc, cf s, float w, int8_t *out)
+{
+    int nb = MCS[enc].n_bpsc;
+    if (nb == 1) { out[0] = soft_q(s.re, w); return; }
+    int h = nb / 2;
+    const float level = (h == 1) ? sqrtf(0.5f) : (h == 2) ? sqrtf(0.1f) : sqrtf(1.0f / 42.0f);
+    float ax[2] = {s.re / level, s.im / level};
+    for (int u = 0; u < 2; ++u) {
+        float a = ax[u], m = fabsf(a);
+        out[u * h] = soft_q(a, w);
+        if (h == 2) out[u * h + 1] = soft_q(2.0f - m, w);
+        if (h == 3) {
+            out[u * h + 1] = soft_q(4.0f - m, w);
+            out[u * h + 2] = soft_q(2.0f - fabsf(m - 4.0f), w);
+        }
+    }
+}
 
 /* equalizer::base + ls/lms/comb/sta [UP] lib/equalizer/ *.cc */
 struct Equalizer {
     int algo;
     cf H[64];
     double snr = 0;
+    bool soft = false;
+    float havg = 1.f;      /* mean |H|^2 over the 52 used carriers after the LTS estimate */
+    int8_t softv[288];
     void equalize(cf *in, int n, cf *symbols, uint8_t *bits, int enc)
     {
         const Tables &t = T();
@@ -576,6 +674,12 @@ struct Equalizer {
                 H[i] = cdiv(s, cf{t.lts[i] * 2.0f, 0.f});
             }
             snr = 10 * std::log10(signal / noise / 2);
+            float acc = 0.f;
+            for (int i = 6; i <= 58; ++i) {
+                if (i == 32) continue;
+                acc += H[i].re * H[i].re + H[i].im * H[i].im;
+            }
+            havg = acc / 52.0f;
         } else {
             cf Hu[64];
             float p = t.polarity[(n - 2) % 127];
@@ -588,6 +692,7 @@ struct Equalizer {
                 }
                 symbols[c] = cdiv(in[i], H[i]);
                 bits[c] = (uint8_t)decide(enc, symbols[c]);
+                if (soft) soft_demap(enc, symbols[c], (H[i].re * H[i].re + H[i].im * H[i].im) / havg, &softv[c * MCS[enc].n_bpsc]);
                 if (algo == 1) { /* lms, alpha 0.5 */
                     cf q = cdiv(in[i], T().cons[enc][bits[c]]);
                     H[i] = cadd(cscale(H[i], 0.5f), cscale(q, 0.5f));
@@ -771,7 +876,9 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
         /* frame_equalizer (wifi_phy_hier.grc:550-569) [UP] frame_equalizer_impl.cc general_work */
         Equalizer eq;
         eq.algo = cfg.algo;
+        eq.soft = cfg.soft != 0;
         std::memset(eq.H, 0, sizeof eq.H);
+        std::memset(eq.softv, 0, sizeof eq.softv);
         double total_freq = (double)B.freq - (double)F.freq_long; /* pmt::from_double(d_freq_offset_short - d_freq_offset) */
         double eps0 = total_freq * cfg.bw / (2 * M_PI * cfg.freq);
         double d_er = 0;
@@ -827,6 +934,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
             }
             if (nn > 2) {
                 R.rows.insert(R.rows.end(), bits, bits + 48);
+                if (cfg.soft) R.soft.insert(R.soft.end(), eq.softv, eq.softv + 288);
                 if (cfg.want_carrier)
                     for (int i = 0; i < 48; ++i) { R.carrier.push_back(symbols[i].re); R.carrier.push_back(symbols[i].im); }
                 F.n_rows++;
@@ -873,7 +981,24 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
                         for (int k = 0; k < mc.n_bpsc; ++k) bits[i * mc.n_bpsc + k] = !!(rowp[i / 48][i % 48] & (1 << k));
                     interleave(bits.data(), deint.data(), ns, C.encoding, true);
                     int nav = depuncture(deint.data(), ncb, C.encoding, dep.data());
-                    viterbi(dep.data(), nav, nd, ntb_of(C.encoding), dec.data());
+                    if (!cfg.soft) viterbi(dep.data(), nav, nd, ntb_of(C.encoding), dec.data());
+                    else {
+                        /* same deinterleave / depuncture on the soft values; an erasure is q = 0 */
+                        std::vector<int8_t> sv(ncb), sd(ncb), sdep(2 * nd + 16, 0);
+                        const int *Pm = T().interleave[C.encoding];
+                        for (int i = 0; i < ns; ++i) {
+                            const int8_t *row = &R.soft[(size_t)((rowp[(size_t)i * 1] - R.rows.data()) / 48) * 288];
+                            for (int k = 0; k < mc.n_cbps; ++k) sd[i * mc.n_cbps + Pm[k]] = row[k];
+                        }
+                        int cnt = 0;
+                        for (int q = 0; q < 2 * nd; ++q) {
+                            bool keep = true;
+                            if (mc.punct == 1) keep = (q % 4) != 3;
+                            else if (mc.punct == 2) keep = !((q % 6) == 3 || (q % 6) == 4);
+                            sdep[q] = keep ? sd[cnt++] : 0;
+                        }
+                        viterbi_soft(sdep.data(), 2 * nd, nd, ntb_of(C.encoding), dec.data());
+                    }
                     /* descramble() */
                     std::vector<uint8_t> out(C.length + 3, 0);
                     int state = 0;
@@ -990,6 +1115,7 @@ orc_rx_result *orc_rx_links(const float *x, const int64_t *off, const int64_t *l
         }
         r->r.rows.insert(r->r.rows.end(), p.rows.begin(), p.rows.end());
         r->r.carrier.insert(r->r.carrier.end(), p.carrier.begin(), p.carrier.end());
+        r->r.soft.insert(r->r.soft.end(), p.soft.begin(), p.soft.end());
         r->r.psdu.insert(r->r.psdu.end(), p.psdu.begin(), p.psdu.end());
     }
     return r;
@@ -1004,6 +1130,8 @@ void orc_rx_copy(const orc_rx_result *r, orc_frame *frames, uint8_t *rows, float
     if (carrier) std::memcpy(carrier, r->r.carrier.data(), r->r.carrier.size() * sizeof(float));
     if (psdu) std::memcpy(psdu, r->r.psdu.data(), r->r.psdu.size());
 }
+void orc_rx_copy_soft(const orc_rx_result *r, int8_t *soft) { std::memcpy(soft, r->r.soft.data(), r->r.soft.size()); }
+int orc_viterbi_soft(const int8_t *dep, int n_avail, int n_bits, int ntb, uint8_t *out_bits) { return viterbi_soft(dep, n_avail, n_bits, ntb, out_bits); }
 void orc_rx_free(orc_rx_result *r) { delete r; }
 
 } // extern "C"

@@ -52,6 +52,8 @@ typedef struct orc_rx_cfg {
     double bw;            /* bandwidth, Hz                                      */
     int32_t final;        /* 1: the stream ends with this buffer                */
     int32_t want_carrier; /* keep equalised points                              */
+    int32_t soft;         /* 1: max-log LLR demapper + soft-decision Viterbi (no reference counterpart) */
+    int32_t pad;
 } orc_rx_cfg;
 
 /* ---- tables / small pieces (for known-answer tests) ---- */
@@ -102,6 +104,9 @@ int64_t orc_rx_n_frames(const orc_rx_result *r);
 int64_t orc_rx_n_rows(const orc_rx_result *r);
 int64_t orc_rx_psdu_bytes(const orc_rx_result *r);
 void orc_rx_copy(const orc_rx_result *r, orc_frame *frames, uint8_t *rows, float *carrier, uint8_t *psdu);
+/* soft mode: one int8 per coded bit, 288 per row (first N_CBPS used), bit order c*N_BPSC+k */
+void orc_rx_copy_soft(const orc_rx_result *r, int8_t *soft);
+int  orc_viterbi_soft(const int8_t *depunctured, int n_avail, int n_bits, int ntraceback, uint8_t *out_bits);
 void orc_rx_free(orc_rx_result *r);
 
 #ifdef __cplusplus

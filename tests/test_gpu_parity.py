@@ -347,3 +347,40 @@ def test_udp_runner_speaks_the_apps_contract(O, W):
     assert all(np.array_equal(g[1], p[1]) for g, p in zip(got, pieces))
     assert t.stats["pdus_out"] == len(pieces)
     t.close()
+
+
+@pytest.mark.parametrize("algo", [0, 1, 3])
+def test_soft_decision_mode_matches_oracle(O, W, algo):
+    """Soft-decision extension (max-log LLR demapper + soft Viterbi): no reference
+    counterpart, the oracle defines it.  int8 soft values and everything downstream must be equal."""
+    rng = np.random.default_rng(90 + algo)
+    specs = [(e, int(rng.integers(40, 500))) for e in range(8)] * 2 + [(7, 1528), (1, 919)]
+    taps = ((0, 1.0), (2, 0.35 * np.exp(1j * 0.7)))
+    y, psdus = make_capture(O, rng, specs, snr_db=17, cfo=0.007, taps=taps, seed=algo, gap=700)
+    h = W.Handle(max_samples=1 << 21, max_frames=1024, chan_est=algo, soft_decision=True, want_carrier=True)
+    res = h.rx_batch(y)
+    ref = O.rx(y, algo=algo, soft=True)
+    assert_frames_equal(res, ref)
+    soft = h.soft_rows()
+    for i in range(len(ref.frames)):
+        f, g = ref.frames[i], res.frames[i]
+        ncb = [48, 48, 96, 96, 192, 192, 288, 288][f["encoding"]]
+        a = soft[g["row_off"]:g["row_off"] + g["n_rows"], :ncb]
+        b = ref.soft[f["row_off"]:f["row_off"] + f["n_rows"], :ncb]
+        assert np.array_equal(a, b), ("soft", i)
+    # the soft decoder recovers frames the hard decoder loses at this SNR
+    hard = O.rx(y, algo=algo)
+    assert ref.frames["crc_ok"].sum() > hard.frames["crc_ok"].sum()
+    # switching the parameter at run time gives the hard-decision result again
+    h.set_param(W.wifi_b200.P_SOFT_DECISION, 0)
+    assert_frames_equal(h.rx_batch(y), hard)
+    h.close()
+
+
+def test_soft_decision_truncated_and_gathered(O, W):
+    rng = np.random.default_rng(95)
+    y, _ = make_capture(O, rng, [(3, 120), (5, 300), (6, 500), (1, 60)], snr_db=25, gap=150, seed=5)
+    y = y[:-500]
+    h = W.Handle(max_samples=1 << 19, soft_decision=True, chan_est=1)
+    assert_frames_equal(h.rx_batch(y), O.rx(y, algo=1, soft=True))
+    h.close()

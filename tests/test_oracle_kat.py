@@ -137,3 +137,22 @@ def test_viterbi_clean_and_erasures(O):
     noisy = coded.copy()
     noisy[[50, 170, 290, 431]] ^= 1                 # isolated channel errors are corrected
     assert np.array_equal(O.viterbi(noisy, 400, 5)[:352], bits[:352])
+
+
+def test_soft_viterbi_equals_hard_on_saturated_inputs(O):
+    """With +-q inputs of equal magnitude the correlation metric orders paths exactly like the
+    agreement count, so the soft decoder must reproduce the hard decoder bit for bit."""
+    rng = np.random.default_rng(4)
+    bits = rng.integers(0, 2, 600, dtype=np.uint8)
+    coded = O.conv_encode(bits)
+    noisy = coded.copy()
+    noisy[rng.choice(coded.size, 60, replace=False)] ^= 1
+    hard = O.viterbi(noisy, 600, 5)
+    soft = O.viterbi_soft(np.where(noisy == 1, 64, -64).astype(np.int8), 600, 5)
+    assert np.array_equal(hard[:540], soft[:540])
+    # erasures (q = 0) at the rate-3/4 positions
+    dep = noisy.copy()
+    dep[3::6] = 2
+    dep[4::6] = 2
+    q = np.where(dep == 1, 64, np.where(dep == 0, -64, 0)).astype(np.int8)
+    assert np.array_equal(O.viterbi(dep, 600, 10)[:500], O.viterbi_soft(q, 600, 10)[:500])
