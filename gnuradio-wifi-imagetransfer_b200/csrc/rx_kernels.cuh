@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     cf HA = {0.f, 0.f}, HB = {0.f, 0.f};
     cf pp[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     double d_er = 0.0, eps0, snr = 0.0;
-    float havg = 1.f;
+    float havg = 1.f, w0A = 1.f, w0B = 1.f;
     int frame_symbols = 0, enc = 0, nb = 1;
     int n_begin, n_end;
     EqState *st = states + f;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
         HA = st->H[iA]; HB = st->H[iB];
 #pragma unroll
         for (int q = 0; q < 4; ++q) pp[q] = st->prev_pil[q];
-        d_er = st->d_er; eps0 = st->eps0; havg = st->havg;
+        d_er = st->d_er; eps0 = st->eps0; havg = st->havg; w0A = st->w0[iA]; w0B = st->w0[iB];
         n_begin = 3;
         n_end = n_syms < frame_symbols + 3 ? n_syms : frame_symbols + 3;
     }
@@ -637,6 +637,9 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                 snr = 10 * log10(signal / noise / 2);
                 havg = acc / 52.0f;
             }
+            havg = __shfl_sync(0xffffffffu, havg, 0);
+            w0A = s_h2[wib][iA] / havg;
+            w0B = s_h2[wib][iB] / havg;
             __syncwarp();
         } else {
             cf symA = {0.f, 0.f}, symB = {0.f, 0.f};
@@ -650,7 +653,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
             if (carA >= 0) {
                 symA = cdiv(a, HA);
                 bitsA = dev_decide(nb, symA);
-                if (soft_on) sqA = dev_soft_demap(nb, symA, (HA.re * HA.re + HA.im * HA.im) / havg);
+                if (soft_on) sqA = dev_soft_demap(nb, symA, w0A);
                 if (prm.algo == WIFI_EQ_LMS) {
                     cf q = cdiv(a, dev_point(nb, bitsA));
                     HA = cadd(cscale(HA, 0.5f), cscale(q, 0.5f));
@@ -660,7 +663,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
             if (carB >= 0) {
                 symB = cdiv(b, HB);
                 bitsB = dev_decide(nb, symB);
-                if (soft_on) sqB = dev_soft_demap(nb, symB, (HB.re * HB.re + HB.im * HB.im) / havg);
+                if (soft_on) sqB = dev_soft_demap(nb, symB, w0B);
                 if (prm.algo == WIFI_EQ_LMS) {
                     cf q = cdiv(b, dev_point(nb, bitsB));
                     HB = cadd(cscale(HB, 0.5f), cscale(q, 0.5f));
@@ -740,6 +743,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     }
     if (phase == 0) {
         st->H[iA] = HA; st->H[iB] = HB;
+        st->w0[iA] = w0A; st->w0[iB] = w0B;
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) st->prev_pil[q] = pp[q];

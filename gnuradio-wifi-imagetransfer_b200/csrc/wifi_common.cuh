@@ -82,8 +82,9 @@ struct EqState {
     double d_er;
     double eps0;
     double snr;
-    float havg;           // mean |H|^2 over the 52 used carriers after the LTS estimate (soft mode weights)
+    float havg;           // mean |H|^2 over the 52 used carriers after the LTS estimate
     float pad0;
+    float w0[64];         // soft-bit weight per carrier: |H|^2 / havg frozen at the LTS estimate
     uint8_t sig_bits[48];
 };
 
@@ -164,12 +165,12 @@ __device__ __forceinline__ void warp_fft64(cf &a, cf &b, int lane, const WarpTw 
     b = csub(u, t);
 }
 
-// max-log LLR of one axis bit, weighted and quantised exactly as oracle soft_q(): clamp(rint((l*w)*16), +-127)
+// max-log LLR of one axis bit, weighted and quantised exactly as oracle soft_q(): clamp(rint((l*w)*16), +-32)
 __device__ __forceinline__ int dev_soft_q(float l, float w)
 {
     float v = rintf((l * w) * 16.0f);
-    if (v > 127.f) v = 127.f;
-    if (v < -127.f) v = -127.f;
+    if (v > 32.f) v = 32.f;
+    if (v < -32.f) v = -32.f;
     return (int)v;
 }
 // soft values of one carrier (oracle soft_demap).  q[u][t]: axis u (0 = I, 1 = Q), t = 0 sign bit,

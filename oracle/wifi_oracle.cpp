@@ -606,12 +606,14 @@ struct Result {
 
 /* max-log LLR per coded bit (new capability): per axis a = component / level, bit k=0: a, inner-half bit:
  * 2-|a| (16-QAM) or 4-|a| (64-QAM), 64-QAM ring bit: 2-||a|-4|; weighted by the carrier's relative channel
- * power w and quantised to int8: q = clamp(rint((l*w)*16), +-127).  Positive = bit 1 (same sense as decide()). */
+ * power w (frozen at the LTS estimate: decision-directed equalizers make |H| itself noisy) and quantised:
+ * q = clamp(rint((l*w)*16), +-32) -- a 6-bit soft value; the clamp bounds the damage of a confidently
+ * wrong bit after a decision-directed slip.  Positive = bit 1 (same sense as decide()). */
 static inline int8_t soft_q(float l, float w)
 {
     float v = rintf((l * w) * 16.0f);
-    if (v > 127.f) v = 127.f;
-    if (v < -127.f) v = -127.f;
+    if (v > 32.f) v = 32.f;
+    if (v < -32.f) v = -32.f;
     return (int8_t)(int)v;
 }
 static inline void soft_demap(int enc, cf s, float w, int8_t *out)
@@ -639,6 +641,7 @@ struct Equalizer {
     double snr = 0;
     bool soft = false;
     float havg = 1.f;      /* mean |H|^2 over the 52 used carriers after the LTS estimate */
+    float w0[64];          /* soft-bit weight of each carrier: |H|^2 / havg, frozen at the LTS estimate */
     int8_t softv[288];
     void equalize(cf *in, int n, cf *symbols, uint8_t *bits, int enc)
     {
@@ -680,6 +683,7 @@ struct Equalizer {
                 acc += H[i].re * H[i].re + H[i].im * H[i].im;
             }
             havg = acc / 52.0f;
+            for (int i = 0; i < 64; ++i) w0[i] = (H[i].re * H[i].re + H[i].im * H[i].im) / havg;
         } else {
             cf Hu[64];
             float p = t.polarity[(n - 2) % 127];
@@ -692,7 +696,7 @@ struct Equalizer {
                 }
                 symbols[c] = cdiv(in[i], H[i]);
                 bits[c] = (uint8_t)decide(enc, symbols[c]);
-                if (soft) soft_demap(enc, symbols[c], (H[i].re * H[i].re + H[i].im * H[i].im) / havg, &softv[c * MCS[enc].n_bpsc]);
+                if (soft) soft_demap(enc, symbols[c], w0[i], &softv[c * MCS[enc].n_bpsc]);
                 if (algo == 1) { /* lms, alpha 0.5 */
                     cf q = cdiv(in[i], T().cons[enc][bits[c]]);
                     H[i] = cadd(cscale(H[i], 0.5f), cscale(q, 0.5f));
@@ -879,6 +883,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
         eq.soft = cfg.soft != 0;
         std::memset(eq.H, 0, sizeof eq.H);
         std::memset(eq.softv, 0, sizeof eq.softv);
+        for (int i = 0; i < 64; ++i) eq.w0[i] = 1.f;
         double total_freq = (double)B.freq - (double)F.freq_long; /* pmt::from_double(d_freq_offset_short - d_freq_offset) */
         double eps0 = total_freq * cfg.bw / (2 * M_PI * cfg.freq);
         double d_er = 0;
