@@ -442,14 +442,15 @@ __device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
 }
 
 // phase 0: symbols 0..2 (LTS1, LTS2, SIGNAL) -> EqState ; phase 1: data symbols -> rows
+template <bool SOFT>
 __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
                                                 EqState *states, uint8_t *rows, cf *carrier, DemodParams prm, int phase,
                                                 const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in,
                                                 int8_t *__restrict__ soft_rows, uint32_t *__restrict__ vit_soft_in)
 {
-    __shared__ int8_t s_soft[4][392];     // soft value of (carrier << 3 | bit); [384] = 0 for erasures
-    __shared__ uint16_t s_slut[4][432];
-    __shared__ float s_h2[4][64];
+    __shared__ int8_t s_soft[SOFT ? 4 : 1][SOFT ? 392 : 4];     // soft value of (carrier << 3 | bit); [384] = 0 for erasures
+    __shared__ uint16_t s_slut[SOFT ? 4 : 1][SOFT ? 432 : 2];
+    __shared__ float s_h2[SOFT ? 4 : 1][SOFT ? 64 : 2];
     __shared__ cf s_hu[4][64];
     __shared__ double s_md[4][64], s_ms[4][64];
     __shared__ uint16_t s_lut[4][432];
@@ -505,7 +506,8 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
         HA = st->H[iA]; HB = st->H[iB];
 #pragma unroll
         for (int q = 0; q < 4; ++q) pp[q] = st->prev_pil[q];
-        d_er = st->d_er; eps0 = st->eps0; havg = st->havg; w0A = st->w0[iA]; w0B = st->w0[iB];
+        d_er = st->d_er; eps0 = st->eps0;
+        if (SOFT) { havg = st->havg; w0A = st->w0[iA]; w0B = st->w0[iB]; }
         n_begin = 3;
         n_end = n_syms < frame_symbols + 3 ? n_syms : frame_symbols + 3;
     }
@@ -522,9 +524,9 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     }
     uint32_t *vw = vit_in + (int64_t)f * VIT_MAXW;
     // soft mode: N_DBPS/2 words per symbol (2 steps x 2 int8 each); every MCS fills whole words
-    const bool soft_on = phase == 1 && prm.soft;
+    const bool soft_on = SOFT && phase == 1;
     const int swps = (soft_on && frame_symbols <= WIFI_MAX_SYM && F.length <= WIFI_MAX_PSDU) ? ndbps >> 1 : 0;
-    if (soft_on) {
+    if (SOFT && soft_on) {
         for (int i = lane; i < 2 * ndbps; i += 32) {
             uint16_t e = depunct_lut[enc * 432 + i];
             s_slut[wib][i] = (e == 0xffffu) ? 384 : e;
@@ -622,8 +624,10 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                 s_md[wib][iB] = (double)md * (double)md; s_ms[wib][iB] = (double)ms * (double)ms;
                 if (usedB) HB = cdiv(s, cf{ltsB * 2.0f, 0.f});
             }
-            s_h2[wib][iA] = HA.re * HA.re + HA.im * HA.im;
-            s_h2[wib][iB] = HB.re * HB.re + HB.im * HB.im;
+            if (SOFT) {
+                s_h2[wib][iA] = HA.re * HA.re + HA.im * HA.im;
+                s_h2[wib][iB] = HB.re * HB.re + HB.im * HB.im;
+            }
             __syncwarp();
             if (lane == 0) {
                 double signal = 0, noise = 0;
@@ -632,14 +636,16 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                     if (i == 32) continue;
                     noise += s_md[wib][i];
                     signal += s_ms[wib][i];
-                    acc += s_h2[wib][i];
+                    if (SOFT) acc += s_h2[wib][i];
                 }
                 snr = 10 * log10(signal / noise / 2);
                 havg = acc / 52.0f;
             }
-            havg = __shfl_sync(0xffffffffu, havg, 0);
-            w0A = s_h2[wib][iA] / havg;
-            w0B = s_h2[wib][iB] / havg;
+            if (SOFT) {
+                havg = __shfl_sync(0xffffffffu, havg, 0);
+                w0A = s_h2[wib][iA] / havg;
+                w0B = s_h2[wib][iB] / havg;
+            }
             __syncwarp();
         } else {
             cf symA = {0.f, 0.f}, symB = {0.f, 0.f};
@@ -653,7 +659,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
             if (carA >= 0) {
                 symA = cdiv(a, HA);
                 bitsA = dev_decide(nb, symA);
-                if (soft_on) sqA = dev_soft_demap(nb, symA, w0A);
+                if (SOFT && soft_on) sqA = dev_soft_demap(nb, symA, w0A);
                 if (prm.algo == WIFI_EQ_LMS) {
                     cf q = cdiv(a, dev_point(nb, bitsA));
                     HA = cadd(cscale(HA, 0.5f), cscale(q, 0.5f));
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
             if (carB >= 0) {
                 symB = cdiv(b, HB);
                 bitsB = dev_decide(nb, symB);
-                if (soft_on) sqB = dev_soft_demap(nb, symB, w0B);
+                if (SOFT && soft_on) sqB = dev_soft_demap(nb, symB, w0B);
                 if (prm.algo == WIFI_EQ_LMS) {
                     cf q = cdiv(b, dev_point(nb, bitsB));
                     HB = cadd(cscale(HB, 0.5f), cscale(q, 0.5f));
@@ -716,7 +722,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                     }
                     __syncwarp();
                 }
-                if (soft_on) {
+                if (SOFT && soft_on) {
                     const int hb = nb > 1 ? nb >> 1 : 1;
 #pragma unroll
                     for (int u = 0; u < 2; ++u)
@@ -743,7 +749,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     }
     if (phase == 0) {
         st->H[iA] = HA; st->H[iB] = HB;
-        st->w0[iA] = w0A; st->w0[iB] = w0B;
+        if (SOFT) { st->w0[iA] = w0A; st->w0[iB] = w0B; }
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) st->prev_pil[q] = pp[q];
@@ -1007,8 +1013,8 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
         uint32_t bits = __funnelshift_r(prev, next, 24);
         prev = next;
         next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v.step((bits >> (4 * k)) & 0xfu);
+        v.step4(bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
+        v.step4((bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
         uint32_t c = v.end_chunk(ring, slot, ntb, tid, (chunk & 3) == 0);
         if (chunk >= ntb) sink.push(c, chunk - ntb);

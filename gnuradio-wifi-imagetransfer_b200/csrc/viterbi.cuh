@@ -39,6 +39,18 @@ __host__ __device__ constexpr uint32_t vit_sel(int j)
     return s;
 }
 
+// selector for a packed butterfly whose byte lanes hold butterflies k0..k3
+__host__ __device__ constexpr uint32_t vit_sel4(int k0, int k1, int k2, int k3)
+{
+    const int k[4] = {k0, k1, k2, k3};
+    uint32_t s = 0;
+    for (int b = 0; b < 4; ++b) {
+        uint32_t A = vit_par((2 * k[b]) & 0x6d), B = vit_par((2 * k[b]) & 0x4f);
+        s |= (2 * A + B) << (4 * b);
+    }
+    return s;
+}
+
 struct VitCore {
     uint32_t M[16], P[16];
 
@@ -77,6 +89,78 @@ struct VitCore {
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) { M[i] = Mn[i]; P[i] = Pn[i]; }
+    }
+
+    // per-step branch words: T = disagreements per (A,B) pattern, E = symbols present (not erased)
+    static __device__ __forceinline__ void branch(uint32_t nib, uint32_t &T, uint32_t &E)
+    {
+        const uint32_t s0 = nib & 3u, s1 = (nib >> 2) & 3u;
+        const uint32_t t0 = (s0 == 2u) ? 0u : (s0 ? 0x00000101u : 0x01010000u);
+        const uint32_t t1 = (s1 == 2u) ? 0u : (s1 ? 0x00010001u : 0x01000100u);
+        T = t0 + t1;
+        E = ((s0 != 2u) ? 0x01010101u : 0u) + ((s1 != 2u) ? 0x01010101u : 0u);
+    }
+    // four packed butterflies: lo = old states k_b, hi = old states k_b + 32 (same byte lanes);
+    // v0/q0 = survivors of new states 2k_b, v1/q1 of 2k_b + 1
+    static __device__ __forceinline__ void bfly(uint32_t T, uint32_t E, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t plo, uint32_t phi,
+                                                uint32_t &v0, uint32_t &v1, uint32_t &q0, uint32_t &q1)
+    {
+        const uint32_t svm = prmt(T, 0u, sel), sv = E - svm;
+        const uint32_t m0 = lo + sv, m1 = hi + svm, m2 = lo + svm, m3 = hi + sv;
+        const uint32_t k0 = prmt(m0 + 0x7f7f7f7fu - m1, 0u, 0xba98u);
+        const uint32_t k1 = prmt(m2 + 0x7f7f7f7fu - m3, 0u, 0xba98u);
+        v0 = (m0 & k0) | (m1 & ~k0);
+        v1 = (m2 & k1) | (m3 & ~k1);
+        const uint32_t sh0 = plo << 1, sh1 = (phi << 1) | 0x01010101u;
+        q0 = (sh0 & k0) | (sh1 & ~k0);
+        q1 = (sh0 & k1) | (sh1 & ~k1);
+    }
+    // Four trellis steps with one re-layout instead of four.  A butterfly leaves its survivors split
+    // into "new even states" and "new odd states" words; instead of interleaving them back to natural
+    // order after every step (4 PRMT per word pair), the next steps pair the split words directly --
+    // the state stride inside a word doubles each step: 1 (natural) -> 2 -> 4 -> 8 -> 16 -- and one 4x4
+    // byte transpose per four words (2 PRMT per word) restores natural order after the fourth step.
+    // Chunks are 8 steps, so snapshots and the best-state search always see the natural layout.
+    __device__ __forceinline__ void step4(uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
+    {
+        uint32_t T, E;
+        uint32_t S[16], SP[16], Q[16], QP[16];
+        // A: natural.  pair j: k = 4j + b  ->  S[j] = states 8j + 2b (even), S[8 + j] = 8j + 2b + 1 (odd)
+        branch(n0, T, E);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            bfly(T, E, vit_sel4(4 * j, 4 * j + 1, 4 * j + 2, 4 * j + 3), M[j], M[j + 8], P[j], P[j + 8], S[j], S[8 + j], SP[j], SP[8 + j]);
+        // B: stride 2.  even pair j: k = 8j + 2b, odd pair j: k = 8j + 2b + 1  ->  Q[4j + o] = states 16j + 4b + o
+        branch(n1, T, E);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bfly(T, E, vit_sel4(8 * j, 8 * j + 2, 8 * j + 4, 8 * j + 6), S[j], S[j + 4], SP[j], SP[j + 4], Q[4 * j], Q[4 * j + 1], QP[4 * j], QP[4 * j + 1]);
+            bfly(T, E, vit_sel4(8 * j + 1, 8 * j + 3, 8 * j + 5, 8 * j + 7), S[8 + j], S[12 + j], SP[8 + j], SP[12 + j], Q[4 * j + 2], Q[4 * j + 3],
+                 QP[4 * j + 2], QP[4 * j + 3]);
+        }
+        // C: stride 4.  pair (j, o): k = 16j + 4b + o  ->  S[8j + o'] = states 32j + 8b + o', o' = 2o, 2o + 1
+        branch(n2, T, E);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                bfly(T, E, vit_sel4(16 * j + o, 16 * j + 4 + o, 16 * j + 8 + o, 16 * j + 12 + o), Q[4 * j + o], Q[4 * (j + 2) + o], QP[4 * j + o],
+                     QP[4 * (j + 2) + o], S[8 * j + 2 * o], S[8 * j + 2 * o + 1], SP[8 * j + 2 * o], SP[8 * j + 2 * o + 1]);
+        // D: stride 8.  pair o': k = 8b + o'  ->  Q[o''] = states 16b + o'', o'' = 2o', 2o' + 1
+        branch(n3, T, E);
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+            bfly(T, E, vit_sel4(o, 8 + o, 16 + o, 24 + o), S[o], S[8 + o], SP[o], SP[8 + o], Q[2 * o], Q[2 * o + 1], QP[2 * o], QP[2 * o + 1]);
+        // stride 16 -> natural: natural word w, byte i = Q[4 (w % 4) + i] byte (w / 4)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            uint32_t t0 = prmt(Q[4 * g], Q[4 * g + 1], 0x5140u), t1 = prmt(Q[4 * g], Q[4 * g + 1], 0x7362u);
+            uint32_t t2 = prmt(Q[4 * g + 2], Q[4 * g + 3], 0x5140u), t3 = prmt(Q[4 * g + 2], Q[4 * g + 3], 0x7362u);
+            M[g] = prmt(t0, t2, 0x5410u); M[g + 4] = prmt(t0, t2, 0x7632u); M[g + 8] = prmt(t1, t3, 0x5410u); M[g + 12] = prmt(t1, t3, 0x7632u);
+            t0 = prmt(QP[4 * g], QP[4 * g + 1], 0x5140u); t1 = prmt(QP[4 * g], QP[4 * g + 1], 0x7362u);
+            t2 = prmt(QP[4 * g + 2], QP[4 * g + 3], 0x5140u); t3 = prmt(QP[4 * g + 2], QP[4 * g + 3], 0x7362u);
+            P[g] = prmt(t0, t2, 0x5410u); P[g + 4] = prmt(t0, t2, 0x7632u); P[g + 8] = prmt(t1, t3, 0x5410u); P[g + 12] = prmt(t1, t3, 0x7632u);
+        }
     }
 
     // byte-wise unsigned max / min of packed words (bytes < 0x80)

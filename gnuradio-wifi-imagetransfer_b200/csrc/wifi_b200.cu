@@ -340,13 +340,14 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
         DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier, soft};
         k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf);
         mark(h, ST_DEMOD_HEAD);
-        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 0,
-                                                          h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
+        auto demod = soft ? k_demod<true> : k_demod<false>;
+        demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 0,
+                                                        h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_SIGNAL);
         k_signal<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, 0, s>>>(h->d_frames, (int)nf, h->d_states);
         mark(h, ST_DEMOD_DATA);
-        k_demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1,
-                                                          h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
+        demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1,
+                                                        h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_PLAN);
         k_plan<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_pack_list, h->d_counters + 1,
                                                           h->d_counters + 2, soft);
