@@ -1008,16 +1008,28 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     PsduSink sink;
     sink.init(out, L, s_crc, s_scr);
     uint32_t next = 1 < nw ? in[1] : 0u;
+    // software pipeline: the traceback of chunk j-1 runs interleaved with the trellis steps of chunk j
+    VitCore::Trace tr;
+    tr.bs = 0; tr.sl = slot; tr.left = 0;
+    bool pending = false;
 #pragma unroll 1
     for (int chunk = 1; chunk <= last_chunk; ++chunk) {
         uint32_t bits = __funnelshift_r(prev, next, 24);
         prev = next;
         next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
+        VitCore::trace_hops<3>(tr, ring, ntb, tid);
         v.step4(bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
+        VitCore::trace_hops<3>(tr, ring, ntb, tid);
         v.step4((bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
+        VitCore::trace_hops<3>(tr, ring, ntb, tid);
+        if (pending && chunk - 1 >= ntb) sink.push(VitCore::trace_finish(tr, ring, tid), chunk - 1 - ntb);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
-        uint32_t c = v.end_chunk(ring, slot, ntb, tid, (chunk & 3) == 0);
-        if (chunk >= ntb) sink.push(c, chunk - ntb);
+        tr = v.trace_begin(ring, slot, ntb, tid, (chunk & 3) == 0);
+        pending = true;
+    }
+    if (pending && last_chunk >= ntb) {
+        VitCore::trace_hops<9>(tr, ring, ntb, tid);
+        sink.push(VitCore::trace_finish(tr, ring, tid), last_chunk - ntb);
     }
     frames[J.frame].crc_ok = sink.crc_ok();
 }

@@ -175,6 +175,66 @@ struct VitCore {
         return (b & k) | (a & ~k);
     }
 
+    // The traceback of one chunk is a chain of dependent shared-memory reads.  trace_begin() stores the
+    // snapshot and finds the first best state; trace_hops() advances a few hops (branch-free, so the
+    // scheduler can interleave the chain with the next chunk's add-compare-select work);
+    // trace_finish() reads the output byte.  It must run before the next snapshot is stored (the byte
+    // it reads lives in the slot that snapshot overwrites).
+    struct Trace { int bs, sl, left; };
+    __device__ __forceinline__ Trace trace_begin(uint32_t *ring, int slot, int ntb, int tid, bool renorm)
+    {
+#pragma unroll
+        for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = P[w];
+        uint32_t mx = M[0];
+#pragma unroll
+        for (int w = 1; w < 16; ++w) mx = vmax4(mx, M[w]);
+        mx = vmax4(mx, mx >> 16); mx = vmax4(mx, mx >> 8);
+        const uint32_t bestw = (mx & 0xffu) * 0x01010101u;
+        int wsel = 0;
+        uint32_t zsel = 0;
+#pragma unroll
+        for (int w = 15; w >= 0; --w) {
+            uint32_t x = M[w] ^ bestw;
+            uint32_t z = ((x + 0x7f7f7f7fu) & 0x80808080u) ^ 0x80808080u;
+            if (z) { wsel = w; zsel = z; }
+        }
+        Trace t;
+        t.bs = wsel * 4 + ((__ffs((int)zsel) - 8) >> 3);
+        t.sl = slot;
+        t.left = ntb - 1;
+        if (renorm) {
+            uint32_t mn = M[0];
+#pragma unroll
+            for (int w = 1; w < 16; ++w) mn = vmin4(mn, M[w]);
+            mn = vmin4(mn, mn >> 16); mn = vmin4(mn, mn >> 8);
+            const uint32_t minw = (mn & 0xffu) * 0x01010101u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) M[i] -= minw;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) P[i] = 0;
+        return t;
+    }
+    template <int N>
+    static __device__ __forceinline__ void trace_hops(Trace &t, const uint32_t *ring, int ntb, int tid)
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool go = t.left > 0;
+            uint32_t w = ring[(t.sl * 16 + (t.bs >> 2)) * VIT_BLOCK + tid];
+            int nb = (int)((w >> (8 * (t.bs & 3))) & 0xffu) >> 2;
+            int ns = (t.sl == 0) ? ntb - 1 : t.sl - 1;
+            t.bs = go ? nb : t.bs;
+            t.sl = go ? ns : t.sl;
+            t.left -= go ? 1 : 0;
+        }
+    }
+    static __device__ __forceinline__ uint32_t trace_finish(const Trace &t, const uint32_t *ring, int tid)
+    {
+        uint32_t w = ring[(t.sl * 16 + (t.bs >> 2)) * VIT_BLOCK + tid];
+        return (w >> (8 * (t.bs & 3))) & 0xffu;
+    }
+
     // viterbi_get_output_generic: snapshot the paths into ring slot `slot`, find the first
     // best state, trace back ntb-1 snapshots, return that snapshot's path byte, renormalise
     // the metrics by their minimum and clear the path registers.
