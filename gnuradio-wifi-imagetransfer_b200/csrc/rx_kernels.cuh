@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     __shared__ cf s_hu[4][64];
     __shared__ double s_md[4][64], s_ms[4][64];
     __shared__ uint16_t s_lut[4][432];
-    __shared__ uint8_t s_bits[4][48];
+    __shared__ uint8_t s_bits[4][52];   // 48 decisions + a zero byte that erasure entries of the LUT point at
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * 4 + wib;
     if (f >= n_frames) return;
@@ -518,8 +518,18 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     // (frames decode_mac will refuse -- more than 511 symbols / 1528 bytes -- would not fit the per-frame
     // word slot and are never decoded from it, so they are not packed)
     const int wps = (phase == 1 && (ndbps & 7) == 0 && frame_symbols <= WIFI_MAX_SYM && F.length <= WIFI_MAX_PSDU) ? ndbps >> 3 : 0;
+    // erasure positions are fixed per (MCS, word): they become a constant OR pattern per lane and their
+    // LUT entries point at a zero byte, so the inner loop has no test
+    uint32_t era_word = 0;
     if (wps) {
-        for (int i = lane; i < 2 * ndbps; i += 32) s_lut[wib][(i & 15) * 27 + (i >> 4)] = depunct_lut[enc * 432 + i];   // [k][word]: conflict-free reads
+        for (int i = lane; i < 2 * ndbps; i += 32) {
+            uint16_t e = depunct_lut[enc * 432 + i];
+            s_lut[wib][(i & 15) * 27 + (i >> 4)] = (e == 0xffffu) ? (uint16_t)(48 << 3) : e;   // [k][word]: conflict-free reads
+        }
+        if (lane < wps)
+            for (int k = 0; k < 16; ++k)
+                if (depunct_lut[enc * 432 + 16 * lane + k] == 0xffffu) era_word |= 2u << (2 * k);
+        if (lane == 0) s_bits[wib][48] = 0;
         __syncwarp();
     }
     uint32_t *vw = vit_in + (int64_t)f * VIT_MAXW;
@@ -711,12 +721,11 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                     if (carB >= 0) s_bits[wib][carB] = (uint8_t)bitsB;
                     __syncwarp();
                     if (lane < wps) {
-                        uint32_t word = 0;
+                        uint32_t word = era_word;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
                             uint32_t e = s_lut[wib][k * 27 + lane];
-                            uint32_t sym = (e == 0xffffu) ? 2u : ((s_bits[wib][e >> 3] >> (e & 7)) & 1u);
-                            word |= sym << (2 * k);
+                            word |= ((s_bits[wib][e >> 3] >> (e & 7)) & 1u) << (2 * k);
                         }
                         vw[(n - 3) * wps + lane] = word;
                     }

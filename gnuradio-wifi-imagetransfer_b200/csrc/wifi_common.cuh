@@ -207,13 +207,16 @@ __device__ __forceinline__ cf dev_point(int nb, int v)
     if (nb == 1) return {v ? 1.f : -1.f, 0.f};
     const int h = nb >> 1;
     const float level = (h == 1) ? sqrtf(0.5f) : (h == 2) ? sqrtf(0.1f) : sqrtf(1.0f / 42.0f);
-    int ax[2] = {v & ((1 << h) - 1), v >> h};
+    const int top = (1 << h) - 1;                  // 1, 3, 7: outermost magnitude
     float o[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-        int b0 = ax[u] & 1, b1 = (ax[u] >> 1) & 1, b2 = (ax[u] >> 2) & 1;
-        int mag = (h == 1) ? 1 : (h == 2) ? (b1 ? 1 : 3) : (b1 ? (b2 ? 3 : 1) : (b2 ? 5 : 7));
-        o[u] = (float)(b0 ? mag : -mag) * level;
+        const int ax = u ? (v >> h) : (v & top);
+        // magnitude bits b1 (b2) are a Gray code of the distance from the outermost level
+        const int b1 = (ax >> 1) & 1, b2 = (ax >> 2) & 1;
+        const int g = (h == 3) ? ((b1 << 1) | (b1 ^ b2)) : b1;      // h == 1: b1 = 0
+        const int mag = top - 2 * g;
+        o[u] = (float)((ax & 1) ? mag : -mag) * level;
     }
     return {o[0], o[1]};
 }
