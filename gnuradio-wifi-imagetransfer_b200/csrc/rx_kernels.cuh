@@ -992,9 +992,11 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     uint32_t *ring = vsm;                                   // VIT_NTB_MAX*16*VIT_BLOCK words
     uint32_t *s_crc = vsm + VIT_NTB_MAX * 16 * VIT_BLOCK;   // 256
     uint16_t *s_scr = (uint16_t *)(s_crc + 256);            // 128
+    uint2 *s_bm = (uint2 *)(s_crc + 256 + 64);              // 16 branch-word pairs
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += VIT_BLOCK) s_crc[i] = c_tab.crc_tab[i];
     for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
+    if (tid < 16) { uint32_t T, E; VitCore::branch((uint32_t)tid, T, E); s_bm[tid] = make_uint2(T, E); }
     __syncthreads();
     const int job = blockIdx.x * VIT_BLOCK + tid;
     if (job >= n_frames) return;
@@ -1027,9 +1029,9 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
         prev = next;
         next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
-        v.step4(bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
+        v.step4(s_bm, bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
-        v.step4((bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
+        v.step4(s_bm, (bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
         if (pending && chunk - 1 >= ntb) sink.push(VitCore::trace_finish(tr, ring, tid), chunk - 1 - ntb);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;

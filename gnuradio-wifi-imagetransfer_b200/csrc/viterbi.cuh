@@ -121,17 +121,18 @@ struct VitCore {
     // the state stride inside a word doubles each step: 1 (natural) -> 2 -> 4 -> 8 -> 16 -- and one 4x4
     // byte transpose per four words (2 PRMT per word) restores natural order after the fourth step.
     // Chunks are 8 steps, so snapshots and the best-state search always see the natural layout.
-    __device__ __forceinline__ void step4(uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
+    // bm: 16-entry shared-memory table of branch() results indexed by the 4-bit symbol pair
+    __device__ __forceinline__ void step4(const uint2 *bm, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
     {
         uint32_t T, E;
         uint32_t S[16], SP[16], Q[16], QP[16];
         // A: natural.  pair j: k = 4j + b  ->  S[j] = states 8j + 2b (even), S[8 + j] = 8j + 2b + 1 (odd)
-        branch(n0, T, E);
+        { const uint2 te = bm[n0]; T = te.x; E = te.y; }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             bfly(T, E, vit_sel4(4 * j, 4 * j + 1, 4 * j + 2, 4 * j + 3), M[j], M[j + 8], P[j], P[j + 8], S[j], S[8 + j], SP[j], SP[8 + j]);
         // B: stride 2.  even pair j: k = 8j + 2b, odd pair j: k = 8j + 2b + 1  ->  Q[4j + o] = states 16j + 4b + o
-        branch(n1, T, E);
+        { const uint2 te = bm[n1]; T = te.x; E = te.y; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             bfly(T, E, vit_sel4(8 * j, 8 * j + 2, 8 * j + 4, 8 * j + 6), S[j], S[j + 4], SP[j], SP[j + 4], Q[4 * j], Q[4 * j + 1], QP[4 * j], QP[4 * j + 1]);
@@ -139,7 +140,7 @@ struct VitCore {
                  QP[4 * j + 2], QP[4 * j + 3]);
         }
         // C: stride 4.  pair (j, o): k = 16j + 4b + o  ->  S[8j + o'] = states 32j + 8b + o', o' = 2o, 2o + 1
-        branch(n2, T, E);
+        { const uint2 te = bm[n2]; T = te.x; E = te.y; }
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -147,7 +148,7 @@ struct VitCore {
                 bfly(T, E, vit_sel4(16 * j + o, 16 * j + 4 + o, 16 * j + 8 + o, 16 * j + 12 + o), Q[4 * j + o], Q[4 * (j + 2) + o], QP[4 * j + o],
                      QP[4 * (j + 2) + o], S[8 * j + 2 * o], S[8 * j + 2 * o + 1], SP[8 * j + 2 * o], SP[8 * j + 2 * o + 1]);
         // D: stride 8.  pair o': k = 8b + o'  ->  Q[o''] = states 16b + o'', o'' = 2o', 2o' + 1
-        branch(n3, T, E);
+        { const uint2 te = bm[n3]; T = te.x; E = te.y; }
 #pragma unroll
         for (int o = 0; o < 8; ++o)
             bfly(T, E, vit_sel4(o, 8 + o, 16 + o, 24 + o), S[o], S[8 + o], SP[o], SP[8 + o], Q[2 * o], Q[2 * o + 1], QP[2 * o], QP[2 * o + 1]);
@@ -185,21 +186,34 @@ struct VitCore {
     {
 #pragma unroll
         for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = P[w];
-        uint32_t mx = M[0];
+        // first best state: per byte lane (state mod 4) a tournament over adjacent words that carries the
+        // word index along; the lower word wins ties, so each lane ends with its first maximum.  The four
+        // lane winners are then compared as scalars (larger metric, then smaller state).
+        uint32_t tv[8], ti[8];
 #pragma unroll
-        for (int w = 1; w < 16; ++w) mx = vmax4(mx, M[w]);
-        mx = vmax4(mx, mx >> 16); mx = vmax4(mx, mx >> 8);
-        const uint32_t bestw = (mx & 0xffu) * 0x01010101u;
-        int wsel = 0;
-        uint32_t zsel = 0;
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t a = M[2 * i], b = M[2 * i + 1];
+            const uint32_t k = prmt((a | 0x80808080u) - b, 0u, 0xba98u);          // 0xff where a >= b
+            tv[i] = (a & k) | (b & ~k);
+            ti[i] = ((uint32_t)(2 * i) * 0x01010101u & k) | ((uint32_t)(2 * i + 1) * 0x01010101u & ~k);
+        }
 #pragma unroll
-        for (int w = 15; w >= 0; --w) {
-            uint32_t x = M[w] ^ bestw;
-            uint32_t z = ((x + 0x7f7f7f7fu) & 0x80808080u) ^ 0x80808080u;
-            if (z) { wsel = w; zsel = z; }
+        for (int n = 4; n >= 1; n >>= 1)
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const uint32_t a = tv[2 * i], b = tv[2 * i + 1];
+                const uint32_t k = prmt((a | 0x80808080u) - b, 0u, 0xba98u);
+                tv[i] = (a & k) | (b & ~k);
+                ti[i] = (ti[2 * i] & k) | (ti[2 * i + 1] & ~k);
+            }
+        int bestv = (int)(tv[0] & 0xffu), bests = (int)(ti[0] & 0xffu) * 4;
+#pragma unroll
+        for (int b = 1; b < 4; ++b) {
+            const int vb = (int)((tv[0] >> (8 * b)) & 0xffu), sb = (int)((ti[0] >> (8 * b)) & 0xffu) * 4 + b;
+            if (vb > bestv || (vb == bestv && sb < bests)) { bestv = vb; bests = sb; }
         }
         Trace t;
-        t.bs = wsel * 4 + ((__ffs((int)zsel) - 8) >> 3);
+        t.bs = bests;
         t.sl = slot;
         t.left = ntb - 1;
         if (renorm) {
