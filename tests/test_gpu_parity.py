@@ -384,3 +384,44 @@ def test_soft_decision_truncated_and_gathered(O, W):
     h = W.Handle(max_samples=1 << 19, soft_decision=True, chan_est=1)
     assert_frames_equal(h.rx_batch(y), O.rx(y, algo=1, soft=True))
     h.close()
+
+
+@pytest.mark.parametrize("minp", [1, 3, 5])
+def test_min_plateau_variants(O, W, minp):
+    rng = np.random.default_rng(110 + minp)
+    y, _ = make_capture(O, rng, [(2, 90), (6, 200), (0, 40)], snr_db=9, seed=minp, gap=520)
+    h = W.Handle(max_samples=1 << 18, min_plateau=minp)
+    assert_frames_equal(h.rx_batch(y), O.rx(y, min_plateau=minp))
+    h.close()
+
+
+@pytest.mark.parametrize("scale", [1e-4, 1.0, 3e3])
+def test_amplitude_extremes_and_frame_at_sample_zero(H, O, W, scale):
+    """The front-end decides c > thr from squared quantities with an exact fallback; very small and
+    very large inputs, exact zeros (0/0) and a frame that starts at sample 0 must not change decisions."""
+    rng = np.random.default_rng(120)
+    y, _ = make_capture(O, rng, [(3, 150), (5, 260)], snr_db=22, seed=8, lead=0, gap=600, cfo=0.019)
+    y = (y * np.float32(scale)).astype(np.complex64)
+    y[5000:5400] = 0                       # dead air: 0/0 in the correlation ratio
+    H.set_param(W.wifi_b200.P_CHAN_EST, 0)
+    assert_frames_equal(H.rx_batch(y), O.rx(y, algo=0))
+    _, _, c = O.frontend(y)
+    assert np.array_equal(H.flags(0, y.size), c.astype(np.float64) > 0.56)
+
+
+def test_streaming_small_pushes_and_soft(O, W):
+    rng = np.random.default_rng(130)
+    y, _ = make_capture(O, rng, [(int(rng.integers(0, 8)), int(rng.integers(40, 300))) for _ in range(8)], snr_db=16, cfo=-0.004, seed=9)
+    ref = O.rx(y, algo=0, soft=True)
+    want = [(int(f["trigger"]), ref.psdu(i)[:-4]) for i, f in enumerate(ref.frames) if f["crc_ok"]]
+    h = W.Handle(max_samples=1 << 18, soft_decision=True)
+    got, pos = [], 0
+    while pos < y.size:
+        n = int(rng.integers(1, 700))
+        h.rx_push(y[pos:pos + n], flush=(pos + n >= y.size))
+        got += h.rx_pop()
+        pos += n
+    assert [(int(f["trigger"]), d) for f, d in got] == want and len(want) >= 5
+    st = h.stats()
+    assert st["crc_ok"] == len(want) and st["pdu_bytes"] == sum(len(d) for _, d in want)
+    h.close()
