@@ -34,6 +34,19 @@ ALGO = 1          # LMS
 LEAD = 128
 
 
+def set_workload(name):
+    global ENC, PSDU_LEN, GAP, SNR_DB, N_DBPS, TAPS, WORKLOAD_DESC
+    if name == "c2":
+        ENC, PSDU_LEN, GAP, SNR_DB, N_DBPS = 4, 1500, 1100, 25.0, 96
+        TAPS = True
+        WORKLOAD_DESC = "BASELINE configs[1]: one 20 Msps stream, 16-QAM 1/2, 1500-byte PSDUs (126 symbols, 10481 samples) + 1100-sample gaps, per-frame CFO, 3-tap multipath, 25 dB"
+
+
+N_DBPS = 216
+TAPS = False
+WORKLOAD_DESC = "BASELINE configs[2]: 54 Mb/s 64-QAM 3/4 batched RX, 1528-byte PSDUs (57 symbols, 4961 samples) + 1100-sample gaps, AWGN 30 dB"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -43,6 +56,7 @@ def parse():
     ap.add_argument("--links", type=int, default=64, help="independent links per GPU")
     ap.add_argument("--frames-per-link", type=int, default=512)
     ap.add_argument("--algo", type=int, default=ALGO)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2"], help="c3 = BASELINE configs[2] (metric workload); c2 = configs[1]: one 10 s 20 Msps stream, 16-QAM 1/2, CFO + 3-tap multipath")
     ap.add_argument("--soft", action="store_true", help="soft-decision mode (extension, DESIGN.md 9)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -51,7 +65,7 @@ def parse():
 
 
 def frame_samples():
-    n_sym = -(-(16 + 8 * PSDU_LEN + 6) // 216)
+    n_sym = -(-(16 + 8 * PSDU_LEN + 6) // N_DBPS)
     return 80 * (5 + n_sym) + 1
 
 
@@ -96,6 +110,14 @@ def build_capture(h, W, torch, n_links, fpl, seed):
     seg["phase0"][:n] = rng.uniform(-np.pi, np.pi, n)
     seg["n_taps"] = 1
     seg["tap_re"][:, 0] = 1.0
+    if TAPS:   # h = [1, 0.4 e^{j phi1}, 0, 0.2 e^{j phi2}] / |h| per frame
+        p1, p2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+        nrm = 1.0 / np.sqrt(1 + 0.16 + 0.04)
+        seg["n_taps"][:n] = 3
+        seg["delay"][:n, 1], seg["delay"][:n, 2] = 1, 3
+        seg["tap_re"][:n, 0] = nrm
+        seg["tap_re"][:n, 1], seg["tap_im"][:n, 1] = 0.4 * nrm * np.cos(p1), 0.4 * nrm * np.sin(p1)
+        seg["tap_re"][:n, 2], seg["tap_im"][:n, 2] = 0.2 * nrm * np.cos(p2), 0.2 * nrm * np.sin(p2)
     seg["seed"] = seed
     seg["stream"] = 0
     h.channel_dev(tx.data_ptr(), cap.data_ptr(), seg)
@@ -150,7 +172,7 @@ class ClockSampler:
 
 
 def config_dict(args, n_links, fpl):
-    return {"workload": "BASELINE configs[2]: 54 Mb/s 64-QAM 3/4 batched RX, 1528-byte PSDUs (57 symbols, 4961 samples) + 1100-sample gaps, AWGN 30 dB",
+    return {"workload": WORKLOAD_DESC,
             "equalizer": ["LS", "LMS", "COMB", "STA"][args.algo], "decisions": "soft" if getattr(args, "soft", False) else "hard", "links_per_gpu": n_links, "frames_per_link": fpl,
             "samples_per_gpu": int(n_links * (LEAD + fpl * (frame_samples() + GAP))),
             "l2_policy": "input (%.2f GB per GPU) larger than L2, no flush" % (n_links * (LEAD + fpl * (frame_samples() + GAP)) * 8 / 1e9),
@@ -203,6 +225,9 @@ def run_reference(args):
 
 def main():
     args = parse()
+    set_workload(args.workload)
+    if args.workload == "c2" and args.links == 64 and args.frames_per_link == 512:
+        args.links, args.frames_per_link = 1, 17270          # 10 s at 20 Msps
     if args.impl == "reference":
         run_reference(args)
         return
@@ -345,7 +370,8 @@ def main():
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
     n_jobs = st_ok if st_ok else n
     # algorithmic bytes per launch of the dominant kernel (Viterbi): N_CBPS coded bits in + PSDU bytes out per frame
-    vit_alg = n * (57 * 288 / 8 + PSDU_LEN)
+    n_sym_w = -(-(16 + 8 * PSDU_LEN + 6) // N_DBPS)
+    vit_alg = n * (n_sym_w * {216: 288, 96: 192}[N_DBPS] / 8 + PSDU_LEN)
     vit_ms = stage_ms.get("viterbi", 0.0)
     achieved = vit_alg / (vit_ms * 1e-3) / 1e9 if vit_ms > 0 else 0.0
     # integer work of the kernel: 64 ACS x 4 int-ops per decoded bit
@@ -367,7 +393,7 @@ def main():
     line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "decoded_mbps": mbps, "frames_per_step": tot_frames, "crc_ok_per_step": tot_ok,
-            "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 10 * args.steps,   # detect, select_spec, select, sync_long, demod x2, signal, plan, pack, viterbi
+            "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 12 * args.steps,   # detect, select_spec, select, frames_init, plan_fast, sync_long, demod x2, signal, plan, pack, viterbi
             "roofline": roof, "stage_ms": stage_ms,
             "path_hbm": {"algorithmic_GBps": path_alg / (step_ms * 1e-3) / 1e9, "frac_of_peak": path_alg / (step_ms * 1e-3) / 1e9 / hbm_peak}}
     if not args.no_cpu and world == 1:

@@ -172,7 +172,7 @@ __device__ __forceinline__ int64_t next_candidate(const uint32_t *__restrict__ f
 #define SEG_CAP 20                      // >= 8192 / 481 + 1 triggers per segment
 __global__ void __launch_bounds__(128) k_select_spec(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary,
                                                       const LinkDesc *__restrict__ links, int n_links, int64_t total_segs, int min_plateau,
-                                                      int *__restrict__ spec_trig, int *__restrict__ spec_cnt)
+                                                      int *__restrict__ spec_trig, int4 *__restrict__ spec_meta)
 {
     int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -186,15 +186,18 @@ __global__ void __launch_bounds__(128) k_select_spec(const uint32_t *__restrict_
     int64_t pos = c0 * FE_CHUNK;
     if (pos < L.min_pos) pos = L.min_pos;
     const int64_t end = (c1 * FE_CHUNK < L.len) ? c1 * FE_CHUNK : L.len;
-    int k = 0;
+    int k = 0, first = 0, last = 0;
     while (pos < end) {
         int64_t m = next_candidate(fw, summary, L.chunk_base, c1, pos, lane, min_plateau);
         if (m < 0 || m >= end) break;
         if (lane == 0 && k < SEG_CAP) spec_trig[seg * SEG_CAP + k] = (int)m;
+        if (k == 0) first = (int)m;
+        last = (int)m;
         ++k;
         pos = m + SS_MIN_GAP + 1;
     }
-    if (lane == 0) spec_cnt[seg] = k < SEG_CAP ? k : SEG_CAP;
+    // (count, first, last) in one 16-byte record: all the sequential pass needs for a regular segment
+    if (lane == 0) spec_meta[seg] = make_int4(k < SEG_CAP ? k : SEG_CAP, first, last, 0);
 }
 
 // Sequential pass, one warp per link: accepts speculative segments 32 at a time while each first
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(128) k_select_spec(const uint32_t *__restrict_
 __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary, LinkDesc *links,
                                                  int n_links, wifi_b200_frame *frames, int *counters, unsigned long long *row_counter,
                                                  int64_t max_frames, int min_plateau, int *err, int *trig_tmp,
-                                                 const int *__restrict__ spec_trig, const int *__restrict__ spec_cnt)
+                                                 const int *__restrict__ spec_trig, const int4 *__restrict__ spec_meta)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_links) return;
@@ -216,36 +219,92 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
     int64_t t_prev = (L.min_pos > 0 ? L.min_pos : 0) - SS_MIN_GAP - 1;   // "last trigger" entering the buffer
     int k = 0;
     int64_t s = 0;
+    // prefetch of the next group's records (the common case advances by exactly 128 segments)
+    int4 nxt[4];
+    int64_t nxt_s = -1;
+    auto load_group = [&](int64_t s0, int4 *m) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int64_t si = s0 + lane * 4 + q;
+            m[q] = (si < n_segs) ? spec_meta[seg0 + si] : make_int4(0, 0, 0, 0);
+        }
+    };
     while (s < n_segs) {
-        // look at up to 32 segments at once
-        int64_t si = s + lane;
-        int cnt = (si < n_segs) ? spec_cnt[seg0 + si] : 0;
-        int first = cnt ? spec_trig[(seg0 + si) * SEG_CAP] : 0;
-        int last = cnt ? spec_trig[(seg0 + si) * SEG_CAP + cnt - 1] : 0;
+        // look at up to 128 segments at once, four consecutive ones per lane
+        int4 meta[4];
+        if (nxt_s == s) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) meta[q] = nxt[q];
+        } else {
+            load_group(s, meta);
+        }
+        nxt_s = s + 128;
+        load_group(nxt_s, nxt);
+        int cnt[4], first[4], last[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { cnt[q] = meta[q].x; first[q] = meta[q].y; last[q] = meta[q].z; }
         // last trigger before each segment, assuming every earlier segment of the group is accepted
-        int64_t lastv = cnt ? (int64_t)last : -(1ll << 40);
-        int64_t run = lastv;
+        const int64_t NONE = -(1ll << 40);
+        int64_t lane_last = NONE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (cnt[q]) lane_last = last[q];      // triggers ascend with the segment index
+        int64_t run = lane_last;
         for (int o = 1; o < 32; o <<= 1) {
             int64_t v = __shfl_up_sync(0xffffffffu, run, o);
             if (lane >= o && v > run) run = v;
         }
         int64_t before = __shfl_up_sync(0xffffffffu, run, 1);
         if (lane == 0 || before < t_prev) before = t_prev;
-        bool okseg = (cnt == 0) || ((int64_t)first > before + SS_MIN_GAP);
-        unsigned bad = __ballot_sync(0xffffffffu, !okseg);
-        int n_ok = bad ? __ffs((int)bad) - 1 : 32;          // segments s .. s+n_ok-1 are accepted as speculated
+        int my_bad = 4;                                                  // first segment of this lane that is not acceptable
+        int64_t b4 = before;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (cnt[q]) {
+                if (my_bad == 4 && !((int64_t)first[q] > b4 + SS_MIN_GAP)) my_bad = q;
+                b4 = last[q];
+            }
+        }
+        unsigned badm = __ballot_sync(0xffffffffu, my_bad < 4);
+        int n_ok;                                                        // segments s .. s+n_ok-1 are accepted as speculated
+        if (badm) {
+            int bl = __ffs((int)badm) - 1;
+            n_ok = bl * 4 + __shfl_sync(0xffffffffu, my_bad, bl);
+        } else {
+            n_ok = 128;
+        }
         if (s + n_ok > n_segs) n_ok = (int)(n_segs - s);
+        const bool bad = badm != 0u;
         // append their triggers
-        int mine = (lane < n_ok) ? cnt : 0, incl = mine;
+        int mine = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (lane * 4 + q < n_ok) mine += cnt[q];
+        int incl = mine;
         for (int o = 1; o < 32; o <<= 1) {
             int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        for (int j = 0; j < mine; ++j) tmp[k + incl - mine + j] = spec_trig[(seg0 + si) * SEG_CAP + j];
+        int wpos = k + incl - mine;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (lane * 4 + q < n_ok) {
+                int64_t si = s + lane * 4 + q;
+                if (cnt[q] > 0) tmp[wpos] = first[q];
+                if (cnt[q] > 1) tmp[wpos + cnt[q] - 1] = last[q];
+                for (int j = 1; j < cnt[q] - 1; ++j) tmp[wpos + j] = spec_trig[(seg0 + si) * SEG_CAP + j];
+                wpos += cnt[q];
+            }
+        }
         int total = __shfl_sync(0xffffffffu, incl, 31);
         if (total > 0) {
-            int64_t lastrun = __shfl_sync(0xffffffffu, run, n_ok - 1 >= 0 ? n_ok - 1 : 0);
-            if (n_ok > 0 && lastrun > t_prev) t_prev = lastrun;
+            // last accepted trigger: the largest `last` among accepted segments
+            int64_t acc_last = NONE;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (lane * 4 + q < n_ok && cnt[q]) acc_last = last[q];
+            for (int o = 16; o > 0; o >>= 1) {
+                int64_t v = __shfl_xor_sync(0xffffffffu, acc_last, o);
+                if (v > acc_last) acc_last = v;
+            }
+            if (acc_last > t_prev) t_prev = acc_last;
         }
         k += total;
         s += n_ok;
@@ -253,7 +312,7 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
             // segment s starts inside the gap of the previous trigger: walk the true chain through it
             const int64_t c1 = ((s + 1) * SEG_CHUNKS < n_chunks) ? (s + 1) * SEG_CHUNKS : n_chunks;
             const int64_t end = (c1 * FE_CHUNK < L.len) ? c1 * FE_CHUNK : L.len;
-            const int scnt = spec_cnt[seg0 + s];
+            const int scnt = spec_meta[seg0 + s].x;
             int64_t pos = t_prev + SS_MIN_GAP + 1;
             while (pos < end) {
                 int64_t m = next_candidate(fw, summary, L.chunk_base, c1, pos, lane, min_plateau);
@@ -277,49 +336,38 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
         }
     }
     __syncwarp();
-    // rows reserved per burst: blen/80 + 1 ; exclusive prefix over the link's bursts
-    auto blen_of = [&](int i) -> int {
-        int64_t t = tmp[i];
-        int64_t endp = (i + 1 < k) ? (int64_t)tmp[i + 1] : L.len;
-        return (int)((endp - t) < SS_MAX_SAMPLES ? (endp - t) : SS_MAX_SAMPLES);
-    };
-    long long rows = 0;
-    for (int b0 = 0; b0 < k; b0 += 32) {
-        int i = b0 + lane;
-        if (i < k) rows += blen_of(i) / 80 + 1;
-    }
-    for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
-    int base = 0;
-    long long row_base = 0;
+    // Reserve the link's frame records and equalizer rows.  Row offsets need no scan: bursts do not
+    // overlap, so frame i may start at row floor(t_i / 80) + i of the link's range (its burst_len/80 + 1
+    // rows end before the next frame's first row); the range is floor(len / 80) + k + 1 rows.
     if (lane == 0) {
-        base = atomicAdd(&counters[0], k);
-        row_base = (long long)atomicAdd(row_counter, (unsigned long long)rows);
+        int base = atomicAdd(&counters[0], k);
+        long long row_base = (long long)atomicAdd(row_counter, (unsigned long long)(L.len / 80 + k + 1));
         bool ovf = (int64_t)base + k > max_frames;
         if (ovf) atomicExch(err, WIFI_E_OVERFLOW);
         links[warp].frame_first = base;
         links[warp].frame_count = ovf ? 0 : k;
+        links[warp].row_base = row_base;
     }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    row_base = __shfl_sync(0xffffffffu, row_base, 0);
-    if ((int64_t)base + k > max_frames) return;
-    long long carry = 0;
-    for (int b0 = 0; b0 < k; b0 += 32) {
-        int i = b0 + lane;
-        int bl = i < k ? blen_of(i) : 0;
-        long long mine = i < k ? bl / 80 + 1 : 0, incl = mine;
-        for (int o = 1; o < 32; o <<= 1) {
-            long long v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (i < k) {
-            wifi_b200_frame f;
-            f.trigger = tmp[i]; f.link = warp; f.burst_len = bl; f.freq_short = 0.f; f.freq_long = 0.f;
-            f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
-            f.frame_symbols = 0; f.n_rows = 0; f.accepted = 0; f.decoded = 0; f.crc_ok = 0; f.snr = 0.0;
-            f.row_off = row_base + carry + incl - mine; f.psdu_off = -1;
-            frames[base + i] = f;
-        }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// frame records of all links, one thread per frame (grid.y = link)
+__global__ void __launch_bounds__(128) k_frames_init(const LinkDesc *__restrict__ links, const int *__restrict__ trig_tmp, wifi_b200_frame *frames)
+{
+    const int l = blockIdx.y;
+    const LinkDesc L = links[l];
+    const int *tmp = trig_tmp + L.chunk_base / 4;
+    const int k = L.frame_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        const int64_t t = tmp[i];
+        const int64_t endp = (i + 1 < k) ? (int64_t)tmp[i + 1] : L.len;
+        wifi_b200_frame f;
+        f.trigger = t; f.link = l;
+        f.burst_len = (int)((endp - t) < SS_MAX_SAMPLES ? (endp - t) : SS_MAX_SAMPLES);
+        f.freq_short = 0.f; f.freq_long = 0.f;
+        f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
+        f.frame_symbols = 0; f.n_rows = 0; f.accepted = 0; f.decoded = 0; f.crc_ok = 0; f.snr = 0.0;
+        f.row_off = L.row_base + t / 80 + i; f.psdu_off = -1;
+        frames[L.frame_first + i] = f;
     }
 }
 
@@ -883,11 +931,39 @@ __device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *f
     }
 }
 
+// Fast path: one thread per frame.  A "regular" frame forms its own job and a SIGNAL-less frame forms
+// none, whatever surrounds them -- unless some frame of the link is irregular (SIGNAL ok but no rows,
+// too few rows, or an oversize tag), in which case the link is flagged and k_plan replays the exact
+// sequential state machine over it.
+__global__ void __launch_bounds__(128) k_plan_fast(wifi_b200_frame *frames, int n_frames, JobDesc *jobs, int *pack_list, int *n_pack,
+                                                    int *link_dirty, int soft)
+{
+    int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fi >= n_frames) return;
+    const wifi_b200_frame *F = frames + fi;
+    const int sig = F->sig_ok, nrows = F->n_rows, fsym = F->frame_symbols, len = F->length, enc = F->encoding;
+    jobs[fi].n_sym = 0;
+    if (!sig) return;
+    const bool regular = nrows > 0 && fsym <= WIFI_MAX_SYM && len <= WIFI_MAX_PSDU && nrows >= fsym;
+    if (!regular) { link_dirty[F->link] = 1; return; }
+    JobDesc J;
+    J.frame = fi; J.enc = enc; J.len = len; J.n_sym = fsym; J.n_seg = 1;
+    J.seg_row[0] = (int32_t)F->row_off; J.seg_cnt[0] = fsym;
+    for (int s = 1; s < 4; ++s) { J.seg_row[s] = 0; J.seg_cnt[s] = 0; }
+    J.need_pack = (!soft && (c_tab.mcs[enc].n_dbps & 7) != 0) ? 1 : 0;
+    jobs[fi] = J;
+    if (J.need_pack) pack_list[atomicAdd(n_pack, 1)] = fi;
+    frames[fi].accepted = 1;
+    frames[fi].decoded = 1;
+    frames[fi].psdu_off = (int64_t)fi * PSDU_STRIDE;
+}
+
 __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links, int n_links, wifi_b200_frame *frames, JobDesc *jobs,
-                                               int *pack_list, int *n_pack, int *err, int soft)
+                                               int *pack_list, int *n_pack, int *err, int soft, const int *__restrict__ link_dirty)
 {
     int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (l >= n_links) return;
+    if (!link_dirty[l]) return;          // every frame of the link was regular or SIGNAL-less: k_plan_fast is exact
     const LinkDesc L = links[l];
     PlanState S;
     S.cur = -1; S.copied = 0; S.need = 0; S.pending = -1; S.bad = false; S.J.n_seg = 0;
@@ -900,7 +976,8 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
         if (valid) {
             const wifi_b200_frame *F = frames + fi;
             sig = F->sig_ok; nrows = F->n_rows; fsym = F->frame_symbols; len = F->length; enc = F->encoding; row_off = F->row_off;
-            jobs[fi].n_sym = 0;
+            jobs[fi].n_sym = 0;          // undo what the fast path wrote for this frame
+            frames[fi].accepted = 0; frames[fi].decoded = 0; frames[fi].psdu_off = -1;
         }
         bool regular = valid && sig && nrows > 0 && fsym <= WIFI_MAX_SYM && len <= WIFI_MAX_PSDU && nrows >= fsym;
         bool quiet = !valid || !sig;
@@ -948,6 +1025,7 @@ __global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, 
     const int np = *n_pack;
     for (int e = blockIdx.y; e < np; e += gridDim.y) {
         const JobDesc J = jobs[pack_list[e]];
+        if (J.n_sym == 0 || !J.need_pack) continue;     // stale entry of a link that was re-planned
         const int ndbps = c_tab.mcs[J.enc].n_dbps;
         const int per = 2 * ndbps;
         const int n_data = J.n_sym * ndbps;
@@ -1054,6 +1132,7 @@ __global__ void __launch_bounds__(256) k_pack_soft(const JobDesc *__restrict__ j
     const int np = *n_pack;
     for (int e = blockIdx.y; e < np; e += gridDim.y) {
         const JobDesc J = jobs[pack_list[e]];
+        if (J.n_sym == 0 || !J.need_pack) continue;
         const McsDesc m = c_tab.mcs[J.enc];
         const int per = 2 * m.n_dbps;
         const int n_words = J.n_sym * (m.n_dbps >> 1);

@@ -160,8 +160,9 @@ struct wifi_b200 {
     uint32_t *d_summary = nullptr;    // 1 bit per FE_CHUNK chunk: any flag set
     int *d_trig_tmp = nullptr;        // k_select scratch: trigger list per link
     int *d_spec_trig = nullptr;       // speculative triggers per 8192-sample segment
-    int *d_spec_cnt = nullptr;
+    int4 *d_spec_cnt = nullptr;       // per segment (count, first, last, -)
     int *d_pack_list = nullptr;       // frames whose trellis words k_pack must build
+    int *d_link_dirty = nullptr;      // links that need the sequential decode_mac replay
     int64_t tile_cap = 0;
     LinkDesc *d_links = nullptr;
     wifi_b200_frame *d_frames = nullptr;
@@ -243,7 +244,7 @@ void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
-                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
+                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_frames) cudaFreeHost(h->h_frames);
@@ -307,6 +308,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
     k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->d_frames, h->d_counters,
                                                         (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
                                                         h->cfg.min_plateau, h->d_counters + 2, h->d_trig_tmp, h->d_spec_trig, h->d_spec_cnt);
+    k_frames_init<<<dim3(8, n_links), 128, 0, s>>>(h->d_links, h->d_trig_tmp, h->d_frames);
     mark(h, ST_SYNC_LONG);
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -349,8 +351,10 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
         demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1,
                                                         h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_PLAN);
+        CK(cudaMemsetAsync(h->d_link_dirty, 0, (size_t)n_links * sizeof(int), s));
+        k_plan_fast<<<(unsigned)((nf + 127) / 128), 128, 0, s>>>(h->d_frames, (int)nf, h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_link_dirty, soft);
         k_plan<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_pack_list, h->d_counters + 1,
-                                                          h->d_counters + 2, soft);
+                                                          h->d_counters + 2, soft, h->d_link_dirty);
         mark(h, ST_PACK);
         size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256 + 128;   // ring, CRC table, descrambler table, branch words
         if (!soft) {
@@ -490,7 +494,7 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     if (upload_tables(h) != WIFI_OK) return fail(WIFI_E_CUDA);
     if (cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM) != cudaSuccess) return fail(WIFI_E_CUDA);
     const int64_t S = cfg.max_samples, Fm = cfg.max_frames;
-    h->row_cap = S / 80 + Fm + 64;
+    h->row_cap = S / 80 + Fm + MAX_LINKS + 64;
     bool ok = true;
     auto A = [&](void **p, size_t bytes) { if (ok && cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) ok = false; };
     h->tile_cap = S / DET_TILE + MAX_LINKS + 1;
@@ -498,8 +502,9 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     A((void **)&h->d_summary, (size_t)h->tile_cap * (DET_THREADS / 32) * 4 + 256);
     A((void **)&h->d_trig_tmp, (size_t)h->tile_cap * (DET_THREADS / 4) * sizeof(int));
     A((void **)&h->d_spec_trig, (size_t)h->tile_cap * SEG_CAP * sizeof(int));
-    A((void **)&h->d_spec_cnt, (size_t)h->tile_cap * sizeof(int));
-    A((void **)&h->d_pack_list, (size_t)Fm * sizeof(int));
+    A((void **)&h->d_spec_cnt, (size_t)h->tile_cap * sizeof(int4));
+    A((void **)&h->d_pack_list, (size_t)2 * Fm * sizeof(int));
+    A((void **)&h->d_link_dirty, (size_t)MAX_LINKS * sizeof(int));
     A((void **)&h->d_links, (size_t)MAX_LINKS * sizeof(LinkDesc));
     A((void **)&h->d_frames, (size_t)Fm * sizeof(wifi_b200_frame));
     A((void **)&h->d_states, (size_t)Fm * sizeof(EqState));

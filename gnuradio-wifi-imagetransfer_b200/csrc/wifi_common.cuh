@@ -73,6 +73,7 @@ struct LinkDesc {
     int32_t hist;         // valid samples stored before x_off (streaming history); older samples read as 0
     int32_t pad0;
     int64_t min_pos;      // first sample index sync_short may trigger on (previous trigger + MIN_GAP + 1)
+    int64_t row_base;     // first equalizer row reserved for the link
 };
 
 // per-frame equalizer state handed from the SIGNAL phase to the data phase
