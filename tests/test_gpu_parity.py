@@ -425,3 +425,27 @@ def test_streaming_small_pushes_and_soft(O, W):
     st = h.stats()
     assert st["crc_ok"] == len(want) and st["pdu_bytes"] == sum(len(d) for _, d in want)
     h.close()
+
+
+def test_overlapping_segment_shards_dedup_to_whole_stream(O, W):
+    """one capture cut into overlapping segments (as ranks would take them), each
+    decoded on its own, frames owned by the segment whose core region holds the trigger.  The union
+    equals the single-pass result (here both segments run on the same GPU, one after the other)."""
+    S = W.sharding
+    rng = np.random.default_rng(140)
+    y, _ = make_capture(O, rng, [(int(rng.integers(0, 8)), int(rng.integers(100, 700))) for _ in range(40)], snr_db=24, seed=14, gap=900,
+                        cfo=0.003)
+    h = W.Handle(max_samples=1 << 21, max_frames=512, chan_est=0)
+    whole = h.rx_batch(y)
+    got = []
+    for seg in S.shard_stream(y.size, 3):
+        r = h.rx_batch(y[seg["start"]:seg["end"]], final=(seg["end"] == y.size))
+        keep = S.owned(r.frames, seg)
+        for i in np.nonzero(keep)[0]:
+            f = r.frames[i]
+            got.append((int(f["trigger"]) + seg["start"], int(f["crc_ok"]), int(f["encoding"]), int(f["length"]), r.psdu(i) if f["decoded"] else None))
+    want = [(int(f["trigger"]), int(f["crc_ok"]), int(f["encoding"]), int(f["length"]), whole.psdu(i) if f["decoded"] else None)
+            for i, f in enumerate(whole.frames)]
+    assert sorted(got, key=lambda t: t[0]) == want
+    assert sum(w[1] for w in want) >= 36
+    h.close()
