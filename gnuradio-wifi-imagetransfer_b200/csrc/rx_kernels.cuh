@@ -1190,17 +1190,28 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi_soft(const JobDesc *__res
     for (int k = 0; k < 3; ++k, ++wi) two_steps(wi < nw ? in[wi] : 0u);
     int slot = 1 % ntb;
     v.end_chunk(ring, slot, ntb, tid, true);
+    VitCore::Trace tr;
+    tr.bs = 0; tr.sl = slot; tr.left = 0;
+    bool pending = false;
 #pragma unroll 1
     for (int chunk = 1; chunk <= last_chunk; ++chunk) {
         uint32_t w4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) w4[k] = (wi + k < nw) ? in[wi + k] : 0u;
         wi += 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) two_steps(w4[k]);
+        VitCore::trace_hops<3>(tr, ring, ntb, tid);
+        v.step4(w4[0], w4[1]);
+        VitCore::trace_hops<3>(tr, ring, ntb, tid);
+        v.step4(w4[2], w4[3]);
+        VitCore::trace_hops<3>(tr, ring, ntb, tid);
+        if (pending && chunk - 1 >= ntb) sink.push(VitCore::trace_finish(tr, ring, tid), chunk - 1 - ntb);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
-        uint32_t c = v.end_chunk(ring, slot, ntb, tid, (chunk & 1) == 0);
-        if (chunk >= ntb) sink.push(c, chunk - ntb);
+        tr = v.trace_begin(ring, slot, ntb, tid, (chunk & 1) == 0);
+        pending = true;
+    }
+    if (pending && last_chunk >= ntb) {
+        VitCore::trace_hops<9>(tr, ring, ntb, tid);
+        sink.push(VitCore::trace_finish(tr, ring, tid), last_chunk - ntb);
     }
     frames[J.frame].crc_ok = sink.crc_ok();
 }

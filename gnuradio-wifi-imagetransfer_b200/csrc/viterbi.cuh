@@ -378,6 +378,123 @@ struct VitCoreSoft {
 #pragma unroll
         for (int i = 0; i < 32; ++i) { M[i] = Mn[i]; P[i] = Pn[i]; }
     }
+    // selector picking, for two butterflies k0 (low lane) and k1 (high lane), halfword (2A+B) of (Tlo, Thi)
+    static __host__ __device__ constexpr uint32_t sel2(int k0, int k1)
+    {
+        const int k[2] = {k0, k1};
+        uint32_t s = 0;
+        for (int b = 0; b < 2; ++b) {
+            uint32_t idx = 2 * vit_par((2 * k[b]) & 0x6d) + vit_par((2 * k[b]) & 0x4f);
+            s |= ((2 * idx) | ((2 * idx + 1) << 4)) << (8 * b);
+        }
+        return s;
+    }
+    static __device__ __forceinline__ void bfly(uint32_t Tlo, uint32_t Thi, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t plo, uint32_t phi,
+                                                uint32_t &v0, uint32_t &v1, uint32_t &p0, uint32_t &p1)
+    {
+        const uint32_t x = prmt(Tlo, Thi, sel), y = 0x01fc01fcu - x;
+        const uint32_t m0 = lo + x, m1 = hi + y, m2 = lo + y, m3 = hi + x;
+        const uint32_t k0 = prmt(m0 + 0x7fff7fffu - m1, 0u, 0xbb99u);
+        const uint32_t k1 = prmt(m2 + 0x7fff7fffu - m3, 0u, 0xbb99u);
+        v0 = (m0 & k0) | (m1 & ~k0);
+        v1 = (m2 & k1) | (m3 & ~k1);
+        const uint32_t sh0 = plo << 1, sh1 = (phi << 1) | 0x00010001u;
+        p0 = (sh0 & k0) | (sh1 & ~k0);
+        p1 = (sh0 & k1) | (sh1 & ~k1);
+    }
+    static __device__ __forceinline__ void branch(int q0, int q1, uint32_t &Tlo, uint32_t &Thi)
+    {
+        const uint32_t t11 = (uint32_t)(q0 + q1 + 254), t00 = 508u - t11;
+        const uint32_t t10 = (uint32_t)(q0 - q1 + 254), t01 = 508u - t10;
+        Tlo = t00 | (t01 << 16);
+        Thi = t10 | (t11 << 16);
+    }
+    // Four steps with one re-layout (see VitCore::step4): with two states per word the stride inside a
+    // word goes 1 -> 2 -> 4 -> 8 -> 16 and one halfword transpose per word pair restores natural order.
+    // w0 / w1: the two input words (2 steps x 2 int8 each).
+    __device__ __forceinline__ void step4(uint32_t w0, uint32_t w1)
+    {
+        uint32_t Tlo, Thi;
+        uint32_t S[32], SP[32], Q[32], QP[32];
+        // A: natural, pair j: k = 2j + b -> S[j] = {4j, 4j+2}, S[16+j] = {4j+1, 4j+3}
+        branch((int)(int8_t)(w0 & 0xffu), (int)(int8_t)((w0 >> 8) & 0xffu), Tlo, Thi);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bfly(Tlo, Thi, sel2(2 * j, 2 * j + 1), M[j], M[j + 16], P[j], P[j + 16], S[j], S[16 + j], SP[j], SP[16 + j]);
+        // B: stride 2.  even pair j: k = 4j + 2b ; odd pair j: k = 4j + 2b + 1 -> Q[4j + o] = {8j + o, 8j + 4 + o}
+        branch((int)(int8_t)((w0 >> 16) & 0xffu), (int)(int8_t)(w0 >> 24), Tlo, Thi);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            bfly(Tlo, Thi, sel2(4 * j, 4 * j + 2), S[j], S[j + 8], SP[j], SP[j + 8], Q[4 * j], Q[4 * j + 1], QP[4 * j], QP[4 * j + 1]);
+            bfly(Tlo, Thi, sel2(4 * j + 1, 4 * j + 3), S[16 + j], S[24 + j], SP[16 + j], SP[24 + j], Q[4 * j + 2], Q[4 * j + 3], QP[4 * j + 2], QP[4 * j + 3]);
+        }
+        // C: stride 4.  pair (j, o): k = 8j + 4b + o -> S[8j + o'] = {16j + o', 16j + 8 + o'}, o' = 2o, 2o+1
+        branch((int)(int8_t)(w1 & 0xffu), (int)(int8_t)((w1 >> 8) & 0xffu), Tlo, Thi);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                bfly(Tlo, Thi, sel2(8 * j + o, 8 * j + 4 + o), Q[4 * j + o], Q[4 * (j + 4) + o], QP[4 * j + o], QP[4 * (j + 4) + o],
+                     S[8 * j + 2 * o], S[8 * j + 2 * o + 1], SP[8 * j + 2 * o], SP[8 * j + 2 * o + 1]);
+        // D: stride 8.  pair (j, o'): k = 16j + 8b + o' -> Q[16j + o''] = {32j + o'', 32j + 16 + o''}, o'' = 2o', 2o'+1
+        branch((int)(int8_t)((w1 >> 16) & 0xffu), (int)(int8_t)(w1 >> 24), Tlo, Thi);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                bfly(Tlo, Thi, sel2(16 * j + o, 16 * j + 8 + o), S[8 * j + o], S[8 * (j + 2) + o], SP[8 * j + o], SP[8 * (j + 2) + o],
+                     Q[16 * j + 2 * o], Q[16 * j + 2 * o + 1], QP[16 * j + 2 * o], QP[16 * j + 2 * o + 1]);
+        // stride 16 -> natural: natural word w = {2w, 2w+1}; Q[16j + e], Q[16j + e + 1] (e even) hold them in the same lane
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+                M[(32 * j + e) >> 1] = prmt(Q[16 * j + e], Q[16 * j + e + 1], 0x5410u);
+                M[(32 * j + 16 + e) >> 1] = prmt(Q[16 * j + e], Q[16 * j + e + 1], 0x7632u);
+                P[(32 * j + e) >> 1] = prmt(QP[16 * j + e], QP[16 * j + e + 1], 0x5410u);
+                P[(32 * j + 16 + e) >> 1] = prmt(QP[16 * j + e], QP[16 * j + e + 1], 0x7632u);
+            }
+    }
+    // snapshot + first best state (index-carrying tournament over adjacent words) + optional renormalisation
+    __device__ __forceinline__ VitCore::Trace trace_begin(uint32_t *ring, int slot, int ntb, int tid, bool renorm)
+    {
+#pragma unroll
+        for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = prmt(P[2 * w], P[2 * w + 1], 0x6420u);
+        uint32_t tv[16], ti[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t a = M[2 * i], b = M[2 * i + 1];
+            const uint32_t k = prmt((a | 0x80008000u) - b, 0u, 0xbb99u);          // 0xffff where a >= b
+            tv[i] = (a & k) | (b & ~k);
+            ti[i] = ((uint32_t)(2 * i) * 0x00010001u & k) | ((uint32_t)(2 * i + 1) * 0x00010001u & ~k);
+        }
+#pragma unroll
+        for (int n = 8; n >= 1; n >>= 1)
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const uint32_t a = tv[2 * i], b = tv[2 * i + 1];
+                const uint32_t k = prmt((a | 0x80008000u) - b, 0u, 0xbb99u);
+                tv[i] = (a & k) | (b & ~k);
+                ti[i] = (ti[2 * i] & k) | (ti[2 * i + 1] & ~k);
+            }
+        const int v0 = (int)(tv[0] & 0xffffu), s0 = (int)(ti[0] & 0xffffu) * 2;
+        const int v1 = (int)(tv[0] >> 16), s1 = (int)(ti[0] >> 16) * 2 + 1;
+        VitCore::Trace t;
+        t.bs = (v1 > v0 || (v1 == v0 && s1 < s0)) ? s1 : s0;
+        t.sl = slot;
+        t.left = ntb - 1;
+        if (renorm) {
+            uint32_t mn = M[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) mn = vmin2(mn, M[i]);
+            mn = vmin2(mn, mn >> 16);
+            const uint32_t minw = (mn & 0xffffu) * 0x00010001u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) M[i] -= minw;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) P[i] = 0;
+        return t;
+    }
     static __device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b)
     {
         uint32_t k = prmt((a | 0x80008000u) - b, 0u, 0xbb99u);
