@@ -12,13 +12,28 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false", "-lin
               "-shared", "-Xcompiler", "-fPIC"]
 
 
+HASH = SO + ".srchash"
+
+
+def _src_hash():
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in DEPS:
+        h.update(open(d, "rb").read())
+    return h.hexdigest()
+
+
 def stale():
+    """Stale = the sources' content differs from what the binary was built from (mtimes are not
+    trusted: the tree is copied to the GPU box)."""
     if not os.path.exists(SO):
         return True
     if not all(os.path.exists(d) for d in DEPS):
         return False  # sources stripped: use the shipped binary
-    t = os.path.getmtime(SO)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    try:
+        return open(HASH).read().strip() != _src_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
@@ -27,6 +42,8 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
     subprocess.check_call(cmd, cwd=HERE)
+    with open(HASH, "w") as f:
+        f.write(_src_hash())
     return SO
 
 

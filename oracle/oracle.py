@@ -37,9 +37,23 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "wifi_oracle.cpp"), os.path.join(_HERE, "wifi_oracle.h"),
             os.path.join(_HERE, "..", "include", "wifi_detmath.h")]
     have_src = all(os.path.exists(s) for s in srcs)
-    stale = have_src and os.path.exists(so) and any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    hfile = so + ".srchash"
+    digest = None
+    if have_src:
+        import hashlib
+        hh = hashlib.sha256()
+        for s in srcs + [os.path.join(_HERE, "Makefile")]:
+            hh.update(open(s, "rb").read())
+        digest = hh.hexdigest()
+    try:
+        stale = have_src and open(hfile).read().strip() != digest   # content, not mtimes: the tree is copied to the GPU box
+    except OSError:
+        stale = have_src
     if force or not os.path.exists(so) or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"])
+        if digest:
+            with open(hfile, "w") as f:
+                f.write(digest)
     return so
 
 
