@@ -4,6 +4,7 @@
 
 Workload (BASELINE.json configs[2], SURVEY.md 8d "C3"): synthetic 20 MHz baseband, 64-QAM 3/4,
 1528-byte PSDUs (57 OFDM symbols, 4961 samples) back to back with 1100-sample idle gaps,
+74 links x 512 frames per GPU (37888 frames = 148 SMs x 4 blocks x 64: whole waves of the Viterbi kernel),
 AWGN at 30 dB, LMS equalizer, hard-decision Viterbi.  The capture is generated on the GPU by
 the library's own TX chain and Philox channel and is far larger than L2 (no flush needed).
 
@@ -53,7 +54,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--links", type=int, default=64, help="independent links per GPU")
+    ap.add_argument("--links", type=int, default=74, help="independent links per GPU (74 x 512 frames = 148 SMs x 4 blocks x 64 trellises: whole waves of k_viterbi)")
     ap.add_argument("--frames-per-link", type=int, default=512)
     ap.add_argument("--algo", type=int, default=ALGO)
     ap.add_argument("--workload", default="c3", choices=["c3", "c2"], help="c3 = BASELINE configs[2] (metric workload); c2 = configs[1]: one 10 s 20 Msps stream, 16-QAM 1/2, CFO + 3-tap multipath")
@@ -226,7 +227,7 @@ def run_reference(args):
 def main():
     args = parse()
     set_workload(args.workload)
-    if args.workload == "c2" and args.links == 64 and args.frames_per_link == 512:
+    if args.workload == "c2" and args.links == 74 and args.frames_per_link == 512:
         args.links, args.frames_per_link = 1, 17270          # 10 s at 20 Msps
     if args.impl == "reference":
         run_reference(args)
