@@ -388,7 +388,7 @@ def main():
         pass
     roof = {"kernel": "k_viterbi", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": vit_alg, "ms_per_launch": vit_ms,
-            "note": "integer-ALU-bound kernel (ncu: sm__inst_executed_pipe_alu 72%% of peak, DRAM 0.6%%): %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % (dec_bits * 256 / (vit_ms * 1e-3) / 1e12 if vit_ms else 0.0)}
+            "note": "integer-ALU-bound kernel (ncu, profiles/r01_ncu_full_top_kernels.json: sm__inst_executed_pipe_alu 85%% of peak, DRAM < 1%%): %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % (dec_bits * 256 / (vit_ms * 1e-3) / 1e12 if vit_ms else 0.0)}
     path_alg = n_samples * 8 + n * PSDU_LEN
     step_ms = 1e3 * elapsed_max / args.steps
     line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
