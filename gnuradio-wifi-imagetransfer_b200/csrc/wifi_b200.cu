@@ -429,6 +429,7 @@ int set_links(wifi_b200 *h, const uint64_t *link_off, int n_links, int final)
         if (link_off[l + 1] < link_off[l]) { h->err = "link offsets not ascending"; return WIFI_E_ARG; }
         L.x_off = (int64_t)link_off[l];
         L.len = (int64_t)(link_off[l + 1] - link_off[l]);
+        if (L.len >= (1ll << 31)) { h->err = "a link is limited to 2^31-1 samples (trigger positions are 32-bit inside the library)"; return WIFI_E_TOO_LARGE; }
         L.is_final = final ? 1 : 0;
     }
     return WIFI_OK;

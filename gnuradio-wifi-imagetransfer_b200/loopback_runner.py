@@ -11,7 +11,7 @@ It stands where the `IRS_tranceiver` loopback flowgraph stands (gnu_radio/IRS_tr
 so the reference's sender and viewer scripts run unchanged against it.  All PHY work happens in
 libwifi_b200.so on the GPU (TX, Philox channel, RX); this file only moves datagrams.
 
-    python -m loopback_runner --encoding 3 --snr 22          (from the package directory)
+    python -c "import wifi_b200; wifi_b200.loopback_runner.main()" --encoding 3 --snr 27
 """
 import argparse
 import math
