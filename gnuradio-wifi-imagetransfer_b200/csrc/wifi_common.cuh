@@ -172,6 +172,7 @@ __device__ __forceinline__ int dev_soft_q(float l, float w)
     float v = rintf((l * w) * 16.0f);
     if (v > 32.f) v = 32.f;
     if (v < -32.f) v = -32.f;
+    if (!(v == v)) v = 0.f;   /* NaN input: no information (float -> int of NaN is not portable) */
     return (int)v;
 }
 // soft values of one carrier (oracle soft_demap).  q[u][t]: axis u (0 = I, 1 = Q), t = 0 sign bit,

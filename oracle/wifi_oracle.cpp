@@ -614,6 +614,7 @@ static inline int8_t soft_q(float l, float w)
     float v = rintf((l * w) * 16.0f);
     if (v > 32.f) v = 32.f;
     if (v < -32.f) v = -32.f;
+    if (!(v == v)) v = 0.f;   /* NaN input: no information (float -> int of NaN is not portable) */
     return (int8_t)(int)v;
 }
 static inline void soft_demap(int enc, cf s, float w, int8_t *out)

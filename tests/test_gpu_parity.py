@@ -449,3 +449,19 @@ def test_overlapping_segment_shards_dedup_to_whole_stream(O, W):
     assert sorted(got, key=lambda t: t[0]) == want
     assert sum(w[1] for w in want) >= 36
     h.close()
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_non_finite_samples_do_not_break_parity(O, W, soft):
+    """NaN / Inf samples (a saturated or corrupted capture) poison the frames they touch in the same
+    way on both sides; the other frames decode."""
+    rng = np.random.default_rng(150)
+    y, psdus = make_capture(O, rng, [(2, 200), (5, 300), (7, 400), (0, 80)], snr_db=28, seed=15, gap=800)
+    y = y.copy()
+    y[1500:1503] = np.nan              # inside frame 0's data
+    y[6000] = np.inf + 0j               # inside frame 1
+    h = W.Handle(max_samples=1 << 18, soft_decision=soft, chan_est=1)
+    res, ref = h.rx_batch(y), O.rx(y, algo=1, soft=soft)
+    assert_frames_equal(res, ref)
+    assert ref.frames["crc_ok"].sum() >= 2
+    h.close()

@@ -32,9 +32,9 @@ def assert_frames_equal(gpu, ref, float_exact=True):
         assert np.array_equal(gpu.frames[k], ref.frames[k]), (k, gpu.frames[k], ref.frames[k])
     if float_exact:
         for k in ("freq_short", "freq_long"):
-            assert np.array_equal(gpu.frames[k], ref.frames[k]), (k, gpu.frames[k], ref.frames[k])
+            assert np.array_equal(gpu.frames[k], ref.frames[k], equal_nan=True), (k, gpu.frames[k], ref.frames[k])
     ok = ref.frames["sig_ok"] == 1
-    assert np.allclose(gpu.frames["snr"][ok], ref.frames["snr"][ok], rtol=1e-9, atol=1e-9)   # double log10: libm vs device
+    assert np.allclose(gpu.frames["snr"][ok], ref.frames["snr"][ok], rtol=1e-9, atol=1e-9, equal_nan=True)   # double log10: libm vs device
     for i in range(len(ref.frames)):
         if ref.frames[i]["decoded"]:
             assert gpu.psdu(i) == ref.psdu(i), ("psdu", i)
