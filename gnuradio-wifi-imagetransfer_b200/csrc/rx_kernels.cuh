@@ -473,6 +473,9 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
     }
 }
 
+#ifndef DEMOD_MINB
+#define DEMOD_MINB 5
+#endif
 // ------------------------------------------------------------------ R3 COPY + R4 + R5
 struct DemodParams {
     double bw, freq;
@@ -490,9 +493,11 @@ __device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
 }
 
 // phase 0: symbols 0..2 (LTS1, LTS2, SIGNAL) -> EqState ; phase 1: data symbols -> rows
-template <bool SOFT>
-__global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
-                                                EqState *states, uint8_t *rows, cf *carrier, DemodParams prm, int phase,
+// ALGO: the equalizer (WIFI_EQ_*) as a template parameter: the symbol loop carries only its own update rule
+// PHASE: 0 = LTS1, LTS2, SIGNAL -> EqState ; 1 = data symbols -> rows (and trellis words)
+template <bool SOFT, int ALGO, int PHASE>
+__global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
+                                                EqState *states, uint8_t *rows, cf *carrier, DemodParams prm,
                                                 const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in,
                                                 int8_t *__restrict__ soft_rows, uint32_t *__restrict__ vit_soft_in)
 {
@@ -503,6 +508,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     __shared__ double s_md[4][64], s_ms[4][64];
     __shared__ uint16_t s_lut[4][432];
     __shared__ uint8_t s_bits[4][52];   // 48 decisions + a zero byte that erasure entries of the LUT point at
+    constexpr int phase = PHASE;
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * 4 + wib;
     if (f >= n_frames) return;
@@ -594,19 +600,34 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
     }
     uint32_t *vsw = vit_soft_in ? vit_soft_in + (int64_t)f * SOFT_MAXW : nullptr;
     int n_rows = 0;
+    // raw samples of symbol n for this lane (burst positions j0, j0 + 1); the loads of symbol n + 1 are
+    // issued before symbol n is processed so that their latency hides behind a whole symbol of arithmetic
+    auto sym_j0 = [&](int n) { return fs + ((n < 2) ? 64 * n + q0 : 128 + 80 * (n - 2) + 16 + q0); };
+    auto fetch_raw = [&](int n, cf (&raw)[2]) {
+        const int j0 = sym_j0(n);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = j0 + u;
+            const int64_t src = t + j - 16;
+            raw[u] = (j < avail && src >= -(int64_t)hist) ? x[src] : cf{0.f, 0.f};
+        }
+    };
+    cf raw[2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (n_begin < n_end) fetch_raw(n_begin, raw);
     for (int n = n_begin; n < n_end; ++n) {
-        // ---- sync_long COPY: fetch the symbol's samples, both derotations ----
+        if (PHASE == 1) __builtin_assume(n >= 3);
+        // ---- sync_long COPY: the symbol's samples, both derotations ----
         cf a, b;
         {
-            int rel0 = (n < 2) ? 64 * n + q0 : 128 + 80 * (n - 2) + 16 + q0;
+            const int j0 = sym_j0(n);
+            const cf s0 = raw[0], s1 = raw[1];
+            if (n + 1 < n_end) fetch_raw(n + 1, raw);
             cf v[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                int j = fs + rel0 + u;
+                const int j = j0 + u;
                 if (j < avail) {
-                    int64_t src = t + j - 16;
-                    cf s = src >= -(int64_t)hist ? x[src] : cf{0.f, 0.f};
-                    cf bj = cmul(s, crot(-fshort * (float)j));
+                    cf bj = cmul(u ? s1 : s0, crot(-fshort * (float)j));
                     v[u] = cmul(bj, crot((float)j * fo));
                 } else {
                     v[u] = {0.f, 0.f};
@@ -626,21 +647,27 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
         const float p = (n >= 2) ? c_tab.polarity[(n - 2) % 127] : 1.f;
         cf pil[4];
         double beta;
+        cf sbeta;
         if (n < 2) {
-            cf s = cadd(cadd(csub(c11, c25), c39), c53);
-            beta = (double)wdm_atan2f(s.im, s.re);
+            sbeta = cadd(cadd(csub(c11, c25), c39), c53);
             pil[0] = c11; pil[1] = cf{-c25.re, -c25.im}; pil[2] = c39; pil[3] = c53;
         } else {
             pil[0] = cscale(c11, p); pil[1] = cscale(c25, p); pil[2] = cscale(c39, p); pil[3] = cscale(c53, -p);
-            cf s = cadd(cadd(cadd(pil[0], pil[2]), pil[1]), pil[3]);
-            beta = (double)wdm_atan2f(s.im, s.re);
+            sbeta = cadd(cadd(cadd(pil[0], pil[2]), pil[1]), pil[3]);
         }
+        // the pilot phase (beta) and the pilot-to-pilot rotation (er) are both one atan2 of a warp-uniform
+        // argument: lanes 0-15 evaluate the first, lanes 16-31 the second, one shuffle each hands them out
+        cf ser = {0.f, 0.f};
+        if (n >= 2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ser = cadd(ser, cmul(cf{pp[q].re, -pp[q].im}, pil[q]));
+        }
+        const bool up = lane >= 16;
+        const float at = wdm_atan2f(up ? ser.im : sbeta.im, up ? ser.re : sbeta.re);
+        beta = (double)__shfl_sync(0xffffffffu, at, 0);
         double er = 0.0;
         if (n >= 2) {
-            cf s = {0.f, 0.f};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s = cadd(s, cmul(cf{pp[q].re, -pp[q].im}, pil[q]));
-            er = (double)wdm_atan2f(s.im, s.re);
+            er = (double)__shfl_sync(0xffffffffu, at, 16);
             er *= prm.bw / (2 * M_PI * prm.freq * 80);
         }
 #pragma unroll
@@ -651,7 +678,7 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
         if (n >= 2) d_er = (1 - 0.1) * d_er + 0.1 * er;
 
         // ---- equalizer::equalize ----
-        if (prm.algo == WIFI_EQ_COMB) {
+        if (ALGO == WIFI_EQ_COMB) {
             cf r11 = cmul(c11, wb), r25 = cmul(c25, wb), r39 = cmul(c39, wb), r53 = cmul(c53, wb);
             cf cp[4];
             if (n < 2) { cp[0] = r11; cp[1] = cf{-r25.re, -r25.im}; cp[2] = r39; cp[3] = r53; }
@@ -718,22 +745,22 @@ __global__ void __launch_bounds__(128, 5) k_demod(const cf *__restrict__ iq, con
                 symA = cdiv(a, HA);
                 bitsA = dev_decide(nb, symA);
                 if (SOFT && soft_on) sqA = dev_soft_demap(nb, symA, w0A);
-                if (prm.algo == WIFI_EQ_LMS) {
+                if (ALGO == WIFI_EQ_LMS) {
                     cf q = cdiv(a, dev_point(nb, bitsA));
                     HA = cadd(cscale(HA, 0.5f), cscale(q, 0.5f));
-                } else if (prm.algo == WIFI_EQ_STA) huA = cdiv(a, dev_point(nb, bitsA));
+                } else if (ALGO == WIFI_EQ_STA) huA = cdiv(a, dev_point(nb, bitsA));
             } else if (iA == 39) huA = cscale(a, p);
             else if (iA == 53) huA = cscale(a, -p);
             if (carB >= 0) {
                 symB = cdiv(b, HB);
                 bitsB = dev_decide(nb, symB);
                 if (SOFT && soft_on) sqB = dev_soft_demap(nb, symB, w0B);
-                if (prm.algo == WIFI_EQ_LMS) {
+                if (ALGO == WIFI_EQ_LMS) {
                     cf q = cdiv(b, dev_point(nb, bitsB));
                     HB = cadd(cscale(HB, 0.5f), cscale(q, 0.5f));
-                } else if (prm.algo == WIFI_EQ_STA) huB = cdiv(b, dev_point(nb, bitsB));
+                } else if (ALGO == WIFI_EQ_STA) huB = cdiv(b, dev_point(nb, bitsB));
             } else if (iB == 11 || iB == 25) huB = cscale(b, p);
-            if (prm.algo == WIFI_EQ_STA) {
+            if (ALGO == WIFI_EQ_STA) {
                 s_hu[wib][iA] = huA; s_hu[wib][iB] = huB;
                 __syncwarp();
 #pragma unroll
@@ -1107,9 +1134,9 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
         prev = next;
         next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
-        v.step4(s_bm, bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
+        v.step4<0>(s_bm, bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
-        v.step4(s_bm, (bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
+        v.step4<4>(s_bm, (bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
         if (pending && chunk - 1 >= ntb) sink.push(VitCore::trace_finish(tr, ring, tid), chunk - 1 - ntb);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
@@ -1200,9 +1227,9 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi_soft(const JobDesc *__res
         for (int k = 0; k < 4; ++k) w4[k] = (wi + k < nw) ? in[wi + k] : 0u;
         wi += 4;
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
-        v.step4(w4[0], w4[1]);
+        v.step4<0>(w4[0], w4[1]);
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
-        v.step4(w4[2], w4[3]);
+        v.step4<4>(w4[2], w4[3]);
         VitCore::trace_hops<3>(tr, ring, ntb, tid);
         if (pending && chunk - 1 >= ntb) sink.push(VitCore::trace_finish(tr, ring, tid), chunk - 1 - ntb);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;

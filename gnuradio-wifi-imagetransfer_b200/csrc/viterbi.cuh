@@ -102,6 +102,9 @@ struct VitCore {
     }
     // four packed butterflies: lo = old states k_b, hi = old states k_b + 32 (same byte lanes);
     // v0/q0 = survivors of new states 2k_b, v1/q1 of 2k_b + 1
+    // BIT: the decision bit of this step inside the path byte.  The bytes are never shifted: step s of a
+    // chunk ORs its decision in at bit 7 - s (earliest decision = MSB, as upstream's shift register leaves it).
+    template <uint32_t BIT>
     static __device__ __forceinline__ void bfly(uint32_t T, uint32_t E, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t plo, uint32_t phi,
                                                 uint32_t &v0, uint32_t &v1, uint32_t &q0, uint32_t &q1)
     {
@@ -111,9 +114,9 @@ struct VitCore {
         const uint32_t k1 = prmt(m2 + 0x7f7f7f7fu - m3, 0u, 0xba98u);
         v0 = (m0 & k0) | (m1 & ~k0);
         v1 = (m2 & k1) | (m3 & ~k1);
-        const uint32_t sh0 = plo << 1, sh1 = (phi << 1) | 0x01010101u;
-        q0 = (sh0 & k0) | (sh1 & ~k0);
-        q1 = (sh0 & k1) | (sh1 & ~k1);
+        const uint32_t pb = phi + BIT;
+        q0 = (plo & k0) | (pb & ~k0);
+        q1 = (plo & k1) | (pb & ~k1);
     }
     // Four trellis steps with one re-layout instead of four.  A butterfly leaves its survivors split
     // into "new even states" and "new odd states" words; instead of interleaving them back to natural
@@ -122,21 +125,24 @@ struct VitCore {
     // byte transpose per four words (2 PRMT per word) restores natural order after the fourth step.
     // Chunks are 8 steps, so snapshots and the best-state search always see the natural layout.
     // bm: 16-entry shared-memory table of branch() results indexed by the 4-bit symbol pair
+    // S0: index of the first of the four steps inside its 8-step chunk (0 or 4)
+    template <int S0>
     __device__ __forceinline__ void step4(const uint2 *bm, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
     {
+        constexpr uint32_t B0 = 0x01010101u << (7 - S0), B1 = B0 >> 1, B2 = B0 >> 2, B3 = B0 >> 3;
         uint32_t T, E;
         uint32_t S[16], SP[16], Q[16], QP[16];
         // A: natural.  pair j: k = 4j + b  ->  S[j] = states 8j + 2b (even), S[8 + j] = 8j + 2b + 1 (odd)
         { const uint2 te = bm[n0]; T = te.x; E = te.y; }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            bfly(T, E, vit_sel4(4 * j, 4 * j + 1, 4 * j + 2, 4 * j + 3), M[j], M[j + 8], P[j], P[j + 8], S[j], S[8 + j], SP[j], SP[8 + j]);
+            bfly<B0>(T, E, vit_sel4(4 * j, 4 * j + 1, 4 * j + 2, 4 * j + 3), M[j], M[j + 8], P[j], P[j + 8], S[j], S[8 + j], SP[j], SP[8 + j]);
         // B: stride 2.  even pair j: k = 8j + 2b, odd pair j: k = 8j + 2b + 1  ->  Q[4j + o] = states 16j + 4b + o
         { const uint2 te = bm[n1]; T = te.x; E = te.y; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            bfly(T, E, vit_sel4(8 * j, 8 * j + 2, 8 * j + 4, 8 * j + 6), S[j], S[j + 4], SP[j], SP[j + 4], Q[4 * j], Q[4 * j + 1], QP[4 * j], QP[4 * j + 1]);
-            bfly(T, E, vit_sel4(8 * j + 1, 8 * j + 3, 8 * j + 5, 8 * j + 7), S[8 + j], S[12 + j], SP[8 + j], SP[12 + j], Q[4 * j + 2], Q[4 * j + 3],
+            bfly<B1>(T, E, vit_sel4(8 * j, 8 * j + 2, 8 * j + 4, 8 * j + 6), S[j], S[j + 4], SP[j], SP[j + 4], Q[4 * j], Q[4 * j + 1], QP[4 * j], QP[4 * j + 1]);
+            bfly<B1>(T, E, vit_sel4(8 * j + 1, 8 * j + 3, 8 * j + 5, 8 * j + 7), S[8 + j], S[12 + j], SP[8 + j], SP[12 + j], Q[4 * j + 2], Q[4 * j + 3],
                  QP[4 * j + 2], QP[4 * j + 3]);
         }
         // C: stride 4.  pair (j, o): k = 16j + 4b + o  ->  S[8j + o'] = states 32j + 8b + o', o' = 2o, 2o + 1
@@ -145,13 +151,13 @@ struct VitCore {
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int o = 0; o < 4; ++o)
-                bfly(T, E, vit_sel4(16 * j + o, 16 * j + 4 + o, 16 * j + 8 + o, 16 * j + 12 + o), Q[4 * j + o], Q[4 * (j + 2) + o], QP[4 * j + o],
+                bfly<B2>(T, E, vit_sel4(16 * j + o, 16 * j + 4 + o, 16 * j + 8 + o, 16 * j + 12 + o), Q[4 * j + o], Q[4 * (j + 2) + o], QP[4 * j + o],
                      QP[4 * (j + 2) + o], S[8 * j + 2 * o], S[8 * j + 2 * o + 1], SP[8 * j + 2 * o], SP[8 * j + 2 * o + 1]);
         // D: stride 8.  pair o': k = 8b + o'  ->  Q[o''] = states 16b + o'', o'' = 2o', 2o' + 1
         { const uint2 te = bm[n3]; T = te.x; E = te.y; }
 #pragma unroll
         for (int o = 0; o < 8; ++o)
-            bfly(T, E, vit_sel4(o, 8 + o, 16 + o, 24 + o), S[o], S[8 + o], SP[o], SP[8 + o], Q[2 * o], Q[2 * o + 1], QP[2 * o], QP[2 * o + 1]);
+            bfly<B3>(T, E, vit_sel4(o, 8 + o, 16 + o, 24 + o), S[o], S[8 + o], SP[o], SP[8 + o], Q[2 * o], Q[2 * o + 1], QP[2 * o], QP[2 * o + 1]);
         // stride 16 -> natural: natural word w, byte i = Q[4 (w % 4) + i] byte (w / 4)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -389,6 +395,8 @@ struct VitCoreSoft {
         }
         return s;
     }
+    // BIT: position of this step's decision in the path halfword (never shifted, see VitCore::bfly)
+    template <uint32_t BIT>
     static __device__ __forceinline__ void bfly(uint32_t Tlo, uint32_t Thi, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t plo, uint32_t phi,
                                                 uint32_t &v0, uint32_t &v1, uint32_t &p0, uint32_t &p1)
     {
@@ -398,9 +406,9 @@ struct VitCoreSoft {
         const uint32_t k1 = prmt(m2 + 0x7fff7fffu - m3, 0u, 0xbb99u);
         v0 = (m0 & k0) | (m1 & ~k0);
         v1 = (m2 & k1) | (m3 & ~k1);
-        const uint32_t sh0 = plo << 1, sh1 = (phi << 1) | 0x00010001u;
-        p0 = (sh0 & k0) | (sh1 & ~k0);
-        p1 = (sh0 & k1) | (sh1 & ~k1);
+        const uint32_t pb = phi + BIT;
+        p0 = (plo & k0) | (pb & ~k0);
+        p1 = (plo & k1) | (pb & ~k1);
     }
     static __device__ __forceinline__ void branch(int q0, int q1, uint32_t &Tlo, uint32_t &Thi)
     {
@@ -412,20 +420,22 @@ struct VitCoreSoft {
     // Four steps with one re-layout (see VitCore::step4): with two states per word the stride inside a
     // word goes 1 -> 2 -> 4 -> 8 -> 16 and one halfword transpose per word pair restores natural order.
     // w0 / w1: the two input words (2 steps x 2 int8 each).
+    template <int S0>
     __device__ __forceinline__ void step4(uint32_t w0, uint32_t w1)
     {
+        constexpr uint32_t B0 = 0x00010001u << (7 - S0), B1 = B0 >> 1, B2 = B0 >> 2, B3 = B0 >> 3;
         uint32_t Tlo, Thi;
         uint32_t S[32], SP[32], Q[32], QP[32];
         // A: natural, pair j: k = 2j + b -> S[j] = {4j, 4j+2}, S[16+j] = {4j+1, 4j+3}
         branch((int)(int8_t)(w0 & 0xffu), (int)(int8_t)((w0 >> 8) & 0xffu), Tlo, Thi);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bfly(Tlo, Thi, sel2(2 * j, 2 * j + 1), M[j], M[j + 16], P[j], P[j + 16], S[j], S[16 + j], SP[j], SP[16 + j]);
+        for (int j = 0; j < 16; ++j) bfly<B0>(Tlo, Thi, sel2(2 * j, 2 * j + 1), M[j], M[j + 16], P[j], P[j + 16], S[j], S[16 + j], SP[j], SP[16 + j]);
         // B: stride 2.  even pair j: k = 4j + 2b ; odd pair j: k = 4j + 2b + 1 -> Q[4j + o] = {8j + o, 8j + 4 + o}
         branch((int)(int8_t)((w0 >> 16) & 0xffu), (int)(int8_t)(w0 >> 24), Tlo, Thi);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            bfly(Tlo, Thi, sel2(4 * j, 4 * j + 2), S[j], S[j + 8], SP[j], SP[j + 8], Q[4 * j], Q[4 * j + 1], QP[4 * j], QP[4 * j + 1]);
-            bfly(Tlo, Thi, sel2(4 * j + 1, 4 * j + 3), S[16 + j], S[24 + j], SP[16 + j], SP[24 + j], Q[4 * j + 2], Q[4 * j + 3], QP[4 * j + 2], QP[4 * j + 3]);
+            bfly<B1>(Tlo, Thi, sel2(4 * j, 4 * j + 2), S[j], S[j + 8], SP[j], SP[j + 8], Q[4 * j], Q[4 * j + 1], QP[4 * j], QP[4 * j + 1]);
+            bfly<B1>(Tlo, Thi, sel2(4 * j + 1, 4 * j + 3), S[16 + j], S[24 + j], SP[16 + j], SP[24 + j], Q[4 * j + 2], Q[4 * j + 3], QP[4 * j + 2], QP[4 * j + 3]);
         }
         // C: stride 4.  pair (j, o): k = 8j + 4b + o -> S[8j + o'] = {16j + o', 16j + 8 + o'}, o' = 2o, 2o+1
         branch((int)(int8_t)(w1 & 0xffu), (int)(int8_t)((w1 >> 8) & 0xffu), Tlo, Thi);
@@ -433,7 +443,7 @@ struct VitCoreSoft {
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int o = 0; o < 4; ++o)
-                bfly(Tlo, Thi, sel2(8 * j + o, 8 * j + 4 + o), Q[4 * j + o], Q[4 * (j + 4) + o], QP[4 * j + o], QP[4 * (j + 4) + o],
+                bfly<B2>(Tlo, Thi, sel2(8 * j + o, 8 * j + 4 + o), Q[4 * j + o], Q[4 * (j + 4) + o], QP[4 * j + o], QP[4 * (j + 4) + o],
                      S[8 * j + 2 * o], S[8 * j + 2 * o + 1], SP[8 * j + 2 * o], SP[8 * j + 2 * o + 1]);
         // D: stride 8.  pair (j, o'): k = 16j + 8b + o' -> Q[16j + o''] = {32j + o'', 32j + 16 + o''}, o'' = 2o', 2o'+1
         branch((int)(int8_t)((w1 >> 16) & 0xffu), (int)(int8_t)(w1 >> 24), Tlo, Thi);
@@ -441,7 +451,7 @@ struct VitCoreSoft {
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int o = 0; o < 8; ++o)
-                bfly(Tlo, Thi, sel2(16 * j + o, 16 * j + 8 + o), S[8 * j + o], S[8 * (j + 2) + o], SP[8 * j + o], SP[8 * (j + 2) + o],
+                bfly<B3>(Tlo, Thi, sel2(16 * j + o, 16 * j + 8 + o), S[8 * j + o], S[8 * (j + 2) + o], SP[8 * j + o], SP[8 * (j + 2) + o],
                      Q[16 * j + 2 * o], Q[16 * j + 2 * o + 1], QP[16 * j + 2 * o], QP[16 * j + 2 * o + 1]);
         // stride 16 -> natural: natural word w = {2w, 2w+1}; Q[16j + e], Q[16j + e + 1] (e even) hold them in the same lane
 #pragma unroll

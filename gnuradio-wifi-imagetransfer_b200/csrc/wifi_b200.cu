@@ -342,13 +342,18 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
         DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier, soft};
         k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf);
         mark(h, ST_DEMOD_HEAD);
-        auto demod = soft ? k_demod<true> : k_demod<false>;
-        demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 0,
+        typedef void (*demod_fn)(const cf *, const LinkDesc *, wifi_b200_frame *, int, EqState *, uint8_t *, cf *, DemodParams,
+                                 const uint16_t *, uint32_t *, int8_t *, uint32_t *);
+#define DEMOD_ROW(S, P) {k_demod<S, WIFI_EQ_LS, P>, k_demod<S, WIFI_EQ_LMS, P>, k_demod<S, WIFI_EQ_COMB, P>, k_demod<S, WIFI_EQ_STA, P>}
+        static const demod_fn demod_tab[2][2][4] = {{DEMOD_ROW(false, 0), DEMOD_ROW(false, 1)}, {DEMOD_ROW(true, 0), DEMOD_ROW(true, 1)}};
+#undef DEMOD_ROW
+        const demod_fn demod_head = demod_tab[soft ? 1 : 0][0][prm.algo & 3], demod_data = demod_tab[soft ? 1 : 0][1][prm.algo & 3];
+        demod_head<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm,
                                                         h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_SIGNAL);
         k_signal<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, 0, s>>>(h->d_frames, (int)nf, h->d_states);
         mark(h, ST_DEMOD_DATA);
-        demod<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm, 1,
+        demod_data<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm,
                                                         h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_PLAN);
         CK(cudaMemsetAsync(h->d_link_dirty, 0, (size_t)n_links * sizeof(int), s));
