@@ -108,7 +108,11 @@ struct VitCore {
     static __device__ __forceinline__ void bfly(uint32_t T, uint32_t E, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t plo, uint32_t phi,
                                                 uint32_t &v0, uint32_t &v1, uint32_t &q0, uint32_t &q1)
     {
-        const uint32_t svm = prmt(T, 0u, sel), sv = E - svm;
+        // the selectors of a step come in complementary pairs (pattern p <-> 3 - p, i.e. sel ^ 0x3333), and
+        // T[3 - p] = E - T[p]: one permute serves both, with the two branch words swapped
+        const uint32_t selc = sel < (sel ^ 0x3333u) ? sel : (sel ^ 0x3333u);
+        const uint32_t ta = prmt(T, 0u, selc), tb = E - ta;
+        const uint32_t svm = (sel == selc) ? ta : tb, sv = (sel == selc) ? tb : ta;
         const uint32_t m0 = lo + sv, m1 = hi + svm, m2 = lo + svm, m3 = hi + sv;
         const uint32_t k0 = prmt(m0 + 0x7f7f7f7fu - m1, 0u, 0xba98u);
         const uint32_t k1 = prmt(m2 + 0x7f7f7f7fu - m3, 0u, 0xba98u);
@@ -192,42 +196,31 @@ struct VitCore {
     {
 #pragma unroll
         for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = P[w];
-        // first best state: per byte lane (state mod 4) a tournament over adjacent words that carries the
-        // word index along; the lower word wins ties, so each lane ends with its first maximum.  The four
-        // lane winners are then compared as scalars (larger metric, then smaller state).
-        uint32_t tv[8], ti[8];
+        // first best state from 16-bit keys (metric << 8) | (63 - state): the largest key is the largest
+        // metric at the smallest state; two keys per word, reduced with the packed-halfword maximum
+        // (VIMNMX.U16x2 / VIMNMX3 on sm_100a)
+        uint32_t key[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t a = M[2 * i], b = M[2 * i + 1];
-            const uint32_t k = prmt((a | 0x80808080u) - b, 0u, 0xba98u);          // 0xff where a >= b
-            tv[i] = (a & k) | (b & ~k);
-            ti[i] = ((uint32_t)(2 * i) * 0x01010101u & k) | ((uint32_t)(2 * i + 1) * 0x01010101u & ~k);
+        for (int w = 0; w < 16; ++w) {
+            const uint32_t c = (uint32_t)(63 - 4 * w) | ((uint32_t)(62 - 4 * w) << 8) | ((uint32_t)(61 - 4 * w) << 16) | ((uint32_t)(60 - 4 * w) << 24);
+            key[2 * w] = prmt(M[w], c, 0x1504u);
+            key[2 * w + 1] = prmt(M[w], c, 0x3726u);
         }
 #pragma unroll
-        for (int n = 4; n >= 1; n >>= 1)
+        for (int n = 16; n >= 1; n >>= 1)
 #pragma unroll
-            for (int i = 0; i < n; ++i) {
-                const uint32_t a = tv[2 * i], b = tv[2 * i + 1];
-                const uint32_t k = prmt((a | 0x80808080u) - b, 0u, 0xba98u);
-                tv[i] = (a & k) | (b & ~k);
-                ti[i] = (ti[2 * i] & k) | (ti[2 * i + 1] & ~k);
-            }
-        int bestv = (int)(tv[0] & 0xffu), bests = (int)(ti[0] & 0xffu) * 4;
-#pragma unroll
-        for (int b = 1; b < 4; ++b) {
-            const int vb = (int)((tv[0] >> (8 * b)) & 0xffu), sb = (int)((ti[0] >> (8 * b)) & 0xffu) * 4 + b;
-            if (vb > bestv || (vb == bestv && sb < bests)) { bestv = vb; bests = sb; }
-        }
+            for (int i = 0; i < n; ++i) key[i] = __vmaxu2(key[i], key[i + n]);
+        const uint32_t kbest = max(key[0] & 0xffffu, key[0] >> 16);
         Trace t;
-        t.bs = bests;
+        t.bs = 63 - (int)(kbest & 0xffu);
         t.sl = slot;
         t.left = ntb - 1;
         if (renorm) {
-            uint32_t mn = M[0];
-#pragma unroll
-            for (int w = 1; w < 16; ++w) mn = vmin4(mn, M[w]);
-            mn = vmin4(mn, mn >> 16); mn = vmin4(mn, mn >> 8);
-            const uint32_t minw = (mn & 0xffu) * 0x01010101u;
+            // Only metric differences matter (upstream subtracts the minimum after every chunk).  Any state
+            // is reached from any other in K - 1 = 6 steps of at most 2 agreements each, so min >= max - 12:
+            // subtracting max - 12 keeps every byte non-negative without a search for the minimum.
+            const uint32_t mx = kbest >> 8;
+            const uint32_t minw = (mx > 12u ? mx - 12u : 0u) * 0x01010101u;
 #pragma unroll
             for (int i = 0; i < 16; ++i) M[i] -= minw;
         }
@@ -235,15 +228,24 @@ struct VitCore {
         for (int i = 0; i < 16; ++i) P[i] = 0;
         return t;
     }
+    // byte (slot, state) of this thread's ring: the ring is word-interleaved across the block's threads,
+    // word (slot * 16 + state / 4) * VIT_BLOCK + tid, so the path byte is a single byte load
+    static __device__ __forceinline__ uint32_t ring_byte(const uint32_t *ring, int sl, int bs, int tid)
+    {
+        const uint8_t *rb = reinterpret_cast<const uint8_t *>(ring) + tid * 4;
+        return rb[sl * (16 * VIT_BLOCK * 4) + (bs >> 2) * (VIT_BLOCK * 4) + (bs & 3)];
+    }
     template <int N>
     static __device__ __forceinline__ void trace_hops(Trace &t, const uint32_t *ring, int ntb, int tid)
     {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
+            // Branch-free on purpose: the chain of dependent loads interleaves with the add-compare-select
+            // work.  (Measured: a variant without the three selects, for warps whose frames all trace back
+            // nine snapshots, is slower -- the kernel is bound by its schedule, not by these few ops.)
             const bool go = t.left > 0;
-            uint32_t w = ring[(t.sl * 16 + (t.bs >> 2)) * VIT_BLOCK + tid];
-            int nb = (int)((w >> (8 * (t.bs & 3))) & 0xffu) >> 2;
-            int ns = (t.sl == 0) ? ntb - 1 : t.sl - 1;
+            const int nb = (int)(ring_byte(ring, t.sl, t.bs, tid) >> 2);
+            const int ns = (t.sl == 0) ? ntb - 1 : t.sl - 1;
             t.bs = go ? nb : t.bs;
             t.sl = go ? ns : t.sl;
             t.left -= go ? 1 : 0;
@@ -251,8 +253,7 @@ struct VitCore {
     }
     static __device__ __forceinline__ uint32_t trace_finish(const Trace &t, const uint32_t *ring, int tid)
     {
-        uint32_t w = ring[(t.sl * 16 + (t.bs >> 2)) * VIT_BLOCK + tid];
-        return (w >> (8 * (t.bs & 3))) & 0xffu;
+        return ring_byte(ring, t.sl, t.bs, tid);
     }
 
     // viterbi_get_output_generic: snapshot the paths into ring slot `slot`, find the first
