@@ -130,12 +130,23 @@ class wifi_phy_hier:
         """Feed a chunk of the continuous stream; returns the PDUs decode_mac publishes."""
         self._h.rx_push(samples, flush=flush)
         out = []
+        car = None
         while True:
             got = self._h.rx_pop()
             if not got:
                 break
             for f, data in got:
                 out.append((self._meta(f), data))
+                if self._want_carrier and self._carrier_cb:
+                    # frame_equalizer's 'symbols' PDUs (48 equalised points per data symbol) of the frames this
+                    # push completed; the rows belong to the batch the push just ran
+                    if car is None:
+                        car = self._h.rows(carrier=True)[1]
+                    r0, r1 = int(f["row_off"]), int(f["row_off"]) + int(f["n_rows"])
+                    if 0 <= r0 and r1 <= len(car):
+                        for r in range(r0, r1):
+                            for cb in self._carrier_cb:
+                                cb(({}, car[r]))
         for pdu in out:
             for cb in self._mac_out_cb:
                 cb(pdu)

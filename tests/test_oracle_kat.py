@@ -156,3 +156,31 @@ def test_soft_viterbi_equals_hard_on_saturated_inputs(O):
     dep[4::6] = 2
     q = np.where(dep == 1, 64, np.where(dep == 0, -64, 0)).astype(np.int8)
     assert np.array_equal(O.viterbi(dep, 600, 10)[:500], O.viterbi_soft(q, 600, 10)[:500])
+
+
+# IEEE 802.11-2012 Annex L (802.11a-1999 Annex G), Table L-1: the 100-octet example PSDU -- MAC header,
+# "Joy, bright spark of divinity,\nDaughter of Elysium,\nFire-insired we trea" and its FCS 67 33 21 b6
+ANNEX_G_HDR = bytes.fromhex("0402002e006008cd37a60020d6013cf1006008ad3baf0000")
+ANNEX_G_TEXT = b"Joy, bright spark of divinity,\nDaughter of Elysium,\nFire-insired we trea"
+ANNEX_G_FCS = bytes.fromhex("673321b6")
+
+
+def test_annex_g_message_fcs_geometry_and_loopback(O):
+    body = ANNEX_G_HDR + ANNEX_G_TEXT
+    assert len(body) == 96
+    # the standard's FCS is what the oracle's CRC (mac.cc / decode_mac.cc: boost::crc_32_type) produces, LSB first
+    assert O.crc32(body).to_bytes(4, "little") == ANNEX_G_FCS
+    psdu = body + ANNEX_G_FCS
+    assert O.crc32(psdu) == 558161692
+    # 36 Mb/s: N_DBPS 144, 16 + 800 + 6 = 822 bits -> 6 symbols (42 pad bits), SIGNAL = the Annex G.4 vector
+    assert O.n_sym(5, 100) == 6
+    assert "".join(map(str, O.signal_field(5, 100))) == "100101001101000000010100100000110010010010010100"
+    iq = O.tx_frame(psdu, 5, seed=0b1011101)               # the example's scrambler state
+    assert iq.size == 80 * (5 + 6) + 1
+    # the example frame decodes back to the example PSDU through the oracle's receiver
+    x = np.concatenate([np.zeros(200, np.complex64), iq, np.zeros(600, np.complex64)]).astype(np.complex64)
+    y = O.channel(x, gain=1.0, noise_sigma=0.01, seed=7)
+    r = O.rx(y, algo=0)
+    assert r.pdus() == [psdu[:-4]]
+    f = r.frames[np.nonzero(r.frames["crc_ok"])[0][0]]
+    assert (int(f["encoding"]), int(f["length"]), int(f["frame_symbols"])) == (5, 100, 6)
