@@ -156,6 +156,7 @@ struct wifi_b200 {
     std::string err;
     // device workspace
     cf *d_iq = nullptr;            // staging for host input (max_samples + history)
+    int16_t *d_sc16 = nullptr;     // staging for wire-format (int16 I/Q) host input
     uint32_t *d_flags = nullptr;      // 1 bit per sample: c[n] > threshold
     uint32_t *d_summary = nullptr;    // 1 bit per FE_CHUNK chunk: any flag set
     int *d_trig_tmp = nullptr;        // k_select scratch: trigger list per link
@@ -243,7 +244,7 @@ int upload_tables(wifi_b200 *h)
 void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
+    void *ptrs[] = {h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
                     h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -265,6 +266,35 @@ int ensure_iq_staging(wifi_b200 *h)
 {
     if (!h->d_iq) CK(cudaMalloc(&h->d_iq, (size_t)(h->cfg.max_samples + 512) * sizeof(cf)));
     return WIFI_OK;
+}
+
+int ensure_sc16_staging(wifi_b200 *h)
+{
+    if (!h->d_sc16) CK(cudaMalloc(&h->d_sc16, (size_t)(h->cfg.max_samples + 512) * 2 * sizeof(int16_t)));
+    return WIFI_OK;
+}
+
+// wire-format ingest: 4 complex samples per thread (16 B in, 32 B out), x = (float)i16 * scale
+__global__ void __launch_bounds__(256) k_sc16_to_fc32(const int16_t *__restrict__ in, cf *__restrict__ out, int64_t n, float scale)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n && (((uintptr_t)(in + 2 * i)) & 15) == 0 && (((uintptr_t)(out + i)) & 15) == 0) {
+            const int4 v = *reinterpret_cast<const int4 *>(in + 2 * i);
+            const int w[4] = {v.x, v.y, v.z, v.w};
+            float4 o[2];
+            float *of = reinterpret_cast<float *>(o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                of[2 * k] = (float)(int16_t)(w[k] & 0xffff) * scale;
+                of[2 * k + 1] = (float)(int16_t)(w[k] >> 16) * scale;
+            }
+            reinterpret_cast<float4 *>(out + i)[0] = o[0];
+            reinterpret_cast<float4 *>(out + i)[1] = o[1];
+        } else {
+            for (int64_t j = i; j < n && j < i + 4; ++j) out[j] = cf{(float)in[2 * j] * scale, (float)in[2 * j + 1] * scale};
+        }
+    }
 }
 
 void mark(wifi_b200 *h, int i)
@@ -780,6 +810,38 @@ int wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *lin
         std::lock_guard<std::mutex> lk(g_h2d_mu[h->device & 63]);
         CK(cudaMemcpyAsync(h->d_iq, iq_host + 2 * base, (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+    }
+    rc = run_rx(h, h->d_iq, true, false);
+    if (rc) return rc;
+    update_stats(h);
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_batch_sc16(wifi_b200_t *h, const int16_t *iq_host, float scale, const uint64_t *link_off, int n_links, int final)
+{
+    if (!h || !iq_host) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    int rc = set_links(h, link_off, n_links, final);
+    if (rc) return rc;
+    rc = ensure_iq_staging(h);
+    if (rc) return rc;
+    rc = ensure_sc16_staging(h);
+    if (rc) return rc;
+    uint64_t base = link_off[0];
+    int64_t total = (int64_t)(link_off[n_links] - base);
+    for (auto &L : h->h_links) L.x_off -= (int64_t)base;
+    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
+    mark(h, ST_H2D);
+    {
+        std::lock_guard<std::mutex> lk(g_h2d_mu[h->device & 63]);     // one capture copy at a time per GPU (see rx_batch)
+        CK(cudaMemcpyAsync(h->d_sc16, iq_host + 2 * base, (size_t)total * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (total > 0) {
+        int64_t blocks = (total / 4 + 255) / 256 + 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        k_sc16_to_fc32<<<(unsigned)blocks, 256, 0, h->stream>>>(h->d_sc16, h->d_iq, total, scale);
     }
     rc = run_rx(h, h->d_iq, true, false);
     if (rc) return rc;

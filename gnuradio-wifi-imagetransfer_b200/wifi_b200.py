@@ -56,7 +56,7 @@ EXPORTS = [
     "wifi_b200_abi_version", "wifi_b200_device_count", "wifi_b200_create", "wifi_b200_destroy", "wifi_b200_set_param",
     "wifi_b200_get_param", "wifi_b200_last_error", "wifi_b200_strerror", "wifi_b200_stream", "wifi_b200_sync",
     "wifi_b200_mac_frame", "wifi_b200_n_sym", "wifi_b200_frame_samples", "wifi_b200_tx", "wifi_b200_tx_dev",
-    "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_counts",
+    "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
 ]
@@ -93,6 +93,7 @@ def lib():
         L.wifi_b200_channel.argtypes = [vp, vp, i64, vp, i64, vp, C.c_int]
         for f in ("wifi_b200_rx_batch", "wifi_b200_rx_batch_dev"):
             getattr(L, f).argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.wifi_b200_rx_batch_sc16.argtypes = [vp, vp, C.c_float, vp, C.c_int, C.c_int]
         L.wifi_b200_rx_counts.argtypes = [vp, vp, vp, vp, vp]
         L.wifi_b200_rx_frames.argtypes = [vp, vp, i64]
         L.wifi_b200_rx_rows.argtypes = [vp, vp, vp, i64]
@@ -255,6 +256,13 @@ class Handle:
         a = np.ascontiguousarray(iq, np.complex64)
         lo = np.array([0, a.size], np.uint64) if link_off is None else np.ascontiguousarray(link_off, np.uint64)
         self._ck(self._L.wifi_b200_rx_batch(self._h, _p(a), _p(lo), lo.size - 1, int(final)))
+        return self.results() if fetch else None
+
+    def rx_batch_sc16(self, iq16, scale, link_off=None, final=True, fetch=True):
+        """Wire-format capture: interleaved int16 I/Q (2 values per sample); x = float32(i16) * float32(scale) on the GPU."""
+        a = np.ascontiguousarray(iq16, np.int16).reshape(-1)
+        lo = np.array([0, a.size // 2], np.uint64) if link_off is None else np.ascontiguousarray(link_off, np.uint64)
+        self._ck(self._L.wifi_b200_rx_batch_sc16(self._h, _p(a), C.c_float(scale), _p(lo), lo.size - 1, int(final)))
         return self.results() if fetch else None
 
     def rx_batch_dev(self, iq_ptr, link_off, final=True, fetch=False):

@@ -151,6 +151,11 @@ int  wifi_b200_channel(wifi_b200_t *h, const float *in_host, int64_t in_len, flo
  * samples.  final != 0: the streams end here (flush).  Results stay in the handle until the next rx call. */
 int  wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int final);
 int  wifi_b200_rx_batch_dev(wifi_b200_t *h, const float *iq_dev, const uint64_t *link_off, int n_links, int final);
+/* Same from the radio's wire format: interleaved int16 I/Q (what uhd.usrp_source / the HackRF deliver before
+ * the host driver converts to fc32; gnu_radio/IRS_AP.py:163-177 asks UHD for cpu_format "fc32").  The GPU forms
+ * x = (float)i16 * scale, one rounding per component -- exactly UHD's sc16 -> fc32 host converter -- so the
+ * result equals wifi_b200_rx_batch on the host-converted samples while the capture crosses PCIe at 4 B/sample. */
+int  wifi_b200_rx_batch_sc16(wifi_b200_t *h, const int16_t *iq_host, float scale, const uint64_t *link_off, int n_links, int final);
 int  wifi_b200_rx_counts(wifi_b200_t *h, int64_t *n_frames, int64_t *n_rows, int64_t *n_pdus, int64_t *psdu_store_bytes);
 int  wifi_b200_rx_frames(wifi_b200_t *h, wifi_b200_frame *out, int64_t cap);
 int  wifi_b200_rx_rows(wifi_b200_t *h, uint8_t *rows /* n_rows*48 or NULL */, float *carrier /* n_rows*96 or NULL */, int64_t cap_rows);

@@ -465,3 +465,33 @@ def test_non_finite_samples_do_not_break_parity(O, W, soft):
     assert_frames_equal(res, ref)
     assert ref.frames["crc_ok"].sum() >= 2
     h.close()
+
+
+@pytest.mark.gpu
+def test_sc16_wire_format_ingest_equals_host_conversion(H, O, W):
+    """int16 I/Q converted on the GPU (x = float32(i16) * scale, UHD's sc16 -> fc32 rule) decodes exactly like the
+    same samples converted on the host and pushed through the fc32 entry point."""
+    H.set_param(W.wifi_b200.P_CHAN_EST, 0)
+    rng = np.random.default_rng(21)
+    parts = [np.zeros(411, np.complex64)]
+    psdus = []
+    for i, enc in enumerate((7, 4, 0, 5, 2)):
+        p = O.mac_frame(rng.integers(0, 256, 150 + 90 * i, dtype=np.uint8).tobytes(), seq=i)
+        psdus.append(p)
+        parts += [O.tx_frame(p, enc, seed=i + 1), np.zeros(900 + 37 * i, np.complex64)]
+    x = np.concatenate(parts).astype(np.complex64)
+    y = O.channel(x, gain=0.5, cfo=0.002, noise_sigma=0.5 * 10 ** (-30 / 20), seed=4)
+    scale = np.float32(1.0 / 8192.0)                                    # ~13-bit ADC headroom
+    i16 = np.clip(np.rint(np.stack([y.real, y.imag], axis=1) / scale), -32768, 32767).astype(np.int16)
+    host = (i16.astype(np.float32) * scale).reshape(-1).view(np.complex64)
+    # two links so that the odd link offset exercises the unaligned tail of the converter
+    cut = 3001
+    off = np.array([0, cut, host.size], np.uint64)
+    a = H.rx_batch(host, off)
+    b = H.rx_batch_sc16(i16, float(scale), off)
+    ref = O.rx_links(host, [0, cut], [cut, host.size - cut], algo=0)
+    for k in ("trigger", "link", "burst_len", "frame_start", "sig_ok", "encoding", "length", "n_rows", "decoded", "crc_ok"):
+        assert np.array_equal(a.frames[k], b.frames[k]) and np.array_equal(b.frames[k], ref.frames[k]), k
+    assert np.array_equal(a.frames["freq_short"], b.frames["freq_short"]) and np.array_equal(a.frames["snr"], b.frames["snr"])
+    assert a.pdus() == b.pdus() == ref.pdus()
+    assert len(b.pdus()) >= 3
