@@ -181,7 +181,7 @@ def config_dict(args, n_links, fpl):
             "parallelism": "links sharded across GPUs, no data-path collective"}
 
 
-def run_reference(args):
+def run_reference(args, out_fd):
     """CPU arm: the oracle (port of the reference algorithm) on all host threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -222,16 +222,31 @@ def run_reference(args):
             "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     line["decoded_mbps"] = ok * (PSDU_LEN - 4) * 8 / (t / len(times)) / 1e6
-    print(json.dumps(line))
+    _emit(out_fd, line)
+
+
+def _claim_stdout():
+    """Libraries write banners to file descriptor 1 (NCCL prints its version there); the contract is ONE
+    JSON line on stdout.  Everything else goes to stderr, the line goes to the saved descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_fd, line):
+    sys.stdout.flush()
+    os.write(real_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
     args = parse()
+    out_fd = _claim_stdout()
     set_workload(args.workload)
     if args.workload == "c2" and args.links == 74 and args.frames_per_link == 512:
         args.links, args.frames_per_link = 1, 17270          # 10 s at 20 Msps
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, out_fd)
         return
     import torch
     import torch.distributed as dist
@@ -448,7 +463,7 @@ def main():
         line["cpu_baseline"] = {"value": sl / dt / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
                                 "sample": "first %d links (%d frames, %d samples) of the same capture, oracle single thread, %.1f s" % (nl, nl * fpl, sl, dt),
                                 "matches_gpu_frame_table": bool(same)}
-    print(json.dumps(line))
+    _emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
 

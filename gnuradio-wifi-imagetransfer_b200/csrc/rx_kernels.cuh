@@ -507,7 +507,9 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
     __shared__ cf s_hu[4][64];
     __shared__ double s_md[4][64], s_ms[4][64];
     __shared__ uint16_t s_lut[4][432];
-    __shared__ uint8_t s_bits[4][52];   // 48 decisions + a zero byte that erasure entries of the LUT point at
+    // decisions as bit planes: byte (carrier << 3 | bit) = that coded bit (0 / 1), so a LUT entry is the byte
+    // offset itself; carrier 48 is a zero slot that the erasure entries point at
+    __shared__ __align__(8) uint8_t s_bits[4][49 * 8];
     constexpr int phase = PHASE;
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * 4 + wib;
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
         if (lane < wps)
             for (int k = 0; k < 16; ++k)
                 if (depunct_lut[enc * 432 + 16 * lane + k] == 0xffffu) era_word |= 2u << (2 * k);
-        if (lane == 0) s_bits[wib][48] = 0;
+        if (lane == 0) *reinterpret_cast<uint2 *>(&s_bits[wib][48 * 8]) = make_uint2(0u, 0u);
         __syncwarp();
     }
     uint32_t *vw = vit_in + (int64_t)f * VIT_MAXW;
@@ -742,23 +744,25 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
 #pragma unroll
                 for (int t = 0; t < 3; ++t) { sqA.q[u][t] = 0; sqB.q[u][t] = 0; }
             if (carA >= 0) {
+                cf ptA;
                 symA = cdiv(a, HA);
-                bitsA = dev_decide(nb, symA);
+                dev_decide_point(nb, symA, bitsA, ptA);
                 if (SOFT && soft_on) sqA = dev_soft_demap(nb, symA, w0A);
                 if (ALGO == WIFI_EQ_LMS) {
-                    cf q = cdiv(a, dev_point(nb, bitsA));
+                    cf q = cdiv(a, ptA);
                     HA = cadd(cscale(HA, 0.5f), cscale(q, 0.5f));
-                } else if (ALGO == WIFI_EQ_STA) huA = cdiv(a, dev_point(nb, bitsA));
+                } else if (ALGO == WIFI_EQ_STA) huA = cdiv(a, ptA);
             } else if (iA == 39) huA = cscale(a, p);
             else if (iA == 53) huA = cscale(a, -p);
             if (carB >= 0) {
+                cf ptB;
                 symB = cdiv(b, HB);
-                bitsB = dev_decide(nb, symB);
+                dev_decide_point(nb, symB, bitsB, ptB);
                 if (SOFT && soft_on) sqB = dev_soft_demap(nb, symB, w0B);
                 if (ALGO == WIFI_EQ_LMS) {
-                    cf q = cdiv(b, dev_point(nb, bitsB));
+                    cf q = cdiv(b, ptB);
                     HB = cadd(cscale(HB, 0.5f), cscale(q, 0.5f));
-                } else if (ALGO == WIFI_EQ_STA) huB = cdiv(b, dev_point(nb, bitsB));
+                } else if (ALGO == WIFI_EQ_STA) huB = cdiv(b, ptB);
             } else if (iB == 11 || iB == 25) huB = cscale(b, p);
             if (ALGO == WIFI_EQ_STA) {
                 s_hu[wib][iA] = huA; s_hu[wib][iB] = huB;
@@ -792,15 +796,20 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
                     if (carB >= 0) carrier[row * 48 + carB] = symB;
                 }
                 if (wps) {
-                    if (carA >= 0) s_bits[wib][carA] = (uint8_t)bitsA;
-                    if (carB >= 0) s_bits[wib][carB] = (uint8_t)bitsB;
+                    // spread the six decision bits over six bytes: (x & 15) * (1 + 2^7 + 2^14 + 2^21) puts bit j at bit 8 j
+                    if (carA >= 0)
+                        *reinterpret_cast<uint2 *>(&s_bits[wib][carA * 8]) =
+                            make_uint2((((uint32_t)bitsA & 15u) * 0x00204081u) & 0x01010101u, (((uint32_t)bitsA >> 4) * 0x81u) & 0x0101u);
+                    if (carB >= 0)
+                        *reinterpret_cast<uint2 *>(&s_bits[wib][carB * 8]) =
+                            make_uint2((((uint32_t)bitsB & 15u) * 0x00204081u) & 0x01010101u, (((uint32_t)bitsB >> 4) * 0x81u) & 0x0101u);
                     __syncwarp();
                     if (lane < wps) {
                         uint32_t word = era_word;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
-                            uint32_t e = s_lut[wib][k * 27 + lane];
-                            word |= ((s_bits[wib][e >> 3] >> (e & 7)) & 1u) << (2 * k);
+                            const uint32_t e = s_lut[wib][k * 27 + lane];
+                            word += (uint32_t)s_bits[wib][e] << (2 * k);          // disjoint bit positions: + is |
                         }
                         vw[(n - 3) * wps + lane] = word;
                     }

@@ -122,6 +122,52 @@ __device__ __forceinline__ int dev_decide(int nb, cf s)
     return r;
 }
 
+// One axis of a decision and of the decided constellation point.  The comparisons are dev_decide()'s, the
+// point is the table value (float)(+-magnitude) * level picked by selects instead of rebuilt from the bits.
+template <int H>   // bits per axis: 1, 2, 3
+__device__ __forceinline__ void dev_axis(float v, int &bits, float &pt)
+{
+    const int sgn = v > 0;
+    if (H == 1) {
+        const float level = sqrtf(0.5f);
+        bits = sgn;
+        pt = sgn ? level : -level;                 // (float)(+-1) * level
+    } else if (H == 2) {
+        const float level = sqrtf(0.1f);
+        const int inner = fabsf(v) < (2 * level);
+        bits = sgn | (inner << 1);
+        const float m = inner ? 1.0f * level : 3.0f * level;
+        pt = sgn ? m : -m;
+    } else {
+        const float level = sqrtf(1.0f / 42.0f);
+        const float ar = fabsf(v);
+        const int b1 = ar < (4 * level);
+        const int b2 = (ar < (6 * level)) && (ar > (2 * level));
+        bits = sgn | (b1 << 1) | (b2 << 2);
+        // Gray: (b1, b2) = 00 -> 7, 01 -> 5, 11 -> 3, 10 -> 1
+        const float m = b1 ? (b2 ? 3.0f * level : 1.0f * level) : (b2 ? 5.0f * level : 7.0f * level);
+        pt = sgn ? m : -m;
+    }
+}
+// decision + decided point of one carrier, dispatched on the (warp-uniform) modulation
+__device__ __forceinline__ void dev_decide_point(int nb, cf s, int &bits, cf &pt)
+{
+    int bi, bq;
+    if (nb == 6) {
+        dev_axis<3>(s.re, bi, pt.re); dev_axis<3>(s.im, bq, pt.im);
+        bits = bi | (bq << 3);
+    } else if (nb == 4) {
+        dev_axis<2>(s.re, bi, pt.re); dev_axis<2>(s.im, bq, pt.im);
+        bits = bi | (bq << 2);
+    } else if (nb == 2) {
+        dev_axis<1>(s.re, bi, pt.re); dev_axis<1>(s.im, bq, pt.im);
+        bits = bi | (bq << 1);
+    } else {
+        bits = s.re > 0;
+        pt = cf{bits ? 1.f : -1.f, 0.f};
+    }
+}
+
 __device__ __forceinline__ int dev_bitrev5(int v) { return (int)(__brev((unsigned)v) >> 27); }
 
 // Per-lane twiddles of the warp FFT, fetched once per kernel (the table index depends on the
