@@ -40,10 +40,17 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
 #define DET_ROWS (DET_THREADS + 2)
 struct DetState { float sar, sai, sp; };
 
+// the oracle's expression c = |a| / p > thr; out of line: it runs for a handful of samples per tile and its
+// square root / division slow paths would otherwise be replicated in every unrolled copy of the walk
+__device__ __noinline__ bool det_exact(float m2, float p, float thr_f) { return (sqrtf(m2) / p) > thr_f; }
+
 // samples [I0, I1) of the chunk; OD / OO / OOD = offsets of the n-16, n-47, n-63 streams in the padded tile
+// A segment lies inside one 32-bit half of the chunk's flag word; `w` is that half, a running one-hot mask marks the bit.
 template <int I0, int I1, int OD, int OO, int OOD>
-__device__ __forceinline__ void det_segment(const cf *base, DetState &st, float thr_f, float thr2, unsigned long long &wbits)
+__device__ __forceinline__ void det_segment(const cf *base, DetState &st, float thr_f, float thr2, uint32_t &w)
 {
+    static_assert((I0 >> 5) == ((I1 - 1) >> 5), "segment straddles the two flag words");
+    uint32_t bit = 1u << (I0 & 31);
 #pragma unroll 4
     for (int i = I0; i < I1; ++i) {
         const cf xn = base[i], xd = base[i + OD], xo = base[i + OO], xod = base[i + OOD];
@@ -62,8 +69,9 @@ __device__ __forceinline__ void det_segment(const cf *base, DetState &st, float 
         const float t2 = thr2 * (p * p);
         bool over = m2 > t2;
         const bool sure = (p > 1e-12f) & (p < 1e12f) & ((m2 > t2 * 1.0001f) | (m2 < t2 * 0.9999f));
-        if (!sure) over = (sqrtf(m2) / p) > thr_f;
-        wbits |= (unsigned long long)over << i;
+        if (!sure) over = det_exact(m2, p, thr_f);
+        if (over) w |= bit;
+        bit += bit;
     }
 }
 #define DET_IDX(q) ((q) + ((q) >> 6))     // row * 65 + col
@@ -97,14 +105,14 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
     // the four sample streams (n, n-16, n-47, n-63) crosses a row, so inside a segment every address is
     // base + i + constant.
     const cf *base = sx + (tid + 2) * (FE_CHUNK + 1);
-    unsigned long long wbits = 0ull;
+    uint32_t w0 = 0u, w1 = 0u;
     if (T0 + (int64_t)tid * FE_CHUNK < hi) {
         DetState st;
         st.sar = st.sai = st.sp = 0.f;
+        // the 47 (63) samples before the chunk live in the previous padded row: element -k sits at base - k - 1
 #pragma unroll 4
         for (int k = 47; k >= 1; --k) {
-            int c = -k, c2 = -k - 16;
-            cf a = base[c + (c >> 6)], d = base[c2 + (c2 >> 6)];
+            const cf a = base[-k - 1], d = base[-k - 17];
             st.sar += a.re * d.re + a.im * d.im;
             st.sai += a.im * d.re - a.re * d.im;
         }
@@ -114,12 +122,12 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
             st.sp += a.re * a.re + a.im * a.im;
         }
         const float thr2 = thr_f * thr_f;
-        det_segment<0, 16, -17, -48, -64>(base, st, thr_f, thr2, wbits);
-        det_segment<16, 47, -16, -48, -64>(base, st, thr_f, thr2, wbits);
-        det_segment<47, 63, -16, -47, -64>(base, st, thr_f, thr2, wbits);
-        det_segment<63, 64, -16, -47, -63>(base, st, thr_f, thr2, wbits);
+        det_segment<0, 16, -17, -48, -64>(base, st, thr_f, thr2, w0);
+        det_segment<16, 32, -16, -48, -64>(base, st, thr_f, thr2, w0);
+        det_segment<32, 47, -16, -48, -64>(base, st, thr_f, thr2, w1);
+        det_segment<47, 63, -16, -47, -64>(base, st, thr_f, thr2, w1);
+        det_segment<63, 64, -16, -47, -63>(base, st, thr_f, thr2, w1);
     }
-    const uint32_t w0 = (uint32_t)wbits, w1 = (uint32_t)(wbits >> 32);
     const int64_t chunk = tile * DET_THREADS + tid;
     reinterpret_cast<uint2 *>(flags)[chunk] = make_uint2(w0, w1);
     uint32_t any = __ballot_sync(0xffffffffu, (w0 | w1) != 0u);
