@@ -426,18 +426,19 @@ def main():
     achieved = vit_alg / (vit_ms * 1e-3) / 1e9 if vit_ms > 0 else 0.0
     # integer work of the kernel: 64 ACS x 4 int-ops per decoded bit
     dec_bits = n * (PSDU_LEN + 2) * 8
-    traffic = None
+    traffic, alu_pct = None, None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of k_viterbi from the committed ncu --set full capture (same workload)
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_top_kernels.json")))
         for kk in prof["kernels"]:
             if kk["kernel"] == "k_viterbi":
                 u = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
                 traffic = sum(float(kk[m]["value"]) * u[kk[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                alu_pct = float(kk["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]["value"])
     except Exception:
         pass
     roof = {"kernel": "k_viterbi", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": vit_alg, "ms_per_launch": vit_ms,
-            "note": "integer-ALU-bound kernel (ncu, profiles/r01_ncu_full_top_kernels.json: sm__inst_executed_pipe_alu 85%% of peak, DRAM < 1%%): %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % (dec_bits * 256 / (vit_ms * 1e-3) / 1e12 if vit_ms else 0.0)}
+            "note": "integer-ALU-bound kernel (ncu, profiles/r01_ncu_full_top_kernels.json: sm__inst_executed_pipe_alu %s%% of peak, DRAM about 1%%): %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % ("%.0f" % alu_pct if alu_pct is not None else "?", dec_bits * 256 / (vit_ms * 1e-3) / 1e12 if vit_ms else 0.0)}
     path_alg = n_samples * 8 + n * PSDU_LEN
     step_ms = 1e3 * elapsed_max / args.steps
     line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
