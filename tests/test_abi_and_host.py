@@ -94,3 +94,22 @@ def test_sources_do_not_name_banned_memcpy_batch_calls():
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                     assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_pcap_tap_and_parse_mac(W, tmp_path):
+    """wireshark_connector / parse_mac stand-ins (reference taps, IRS_tranceiver.grc:446-495,1022-1038)."""
+    import struct
+    m = W.mac()
+    pdus = [({"dlt": 105}, m.app_in(bytes([i]) * (10 + i))[1][:-4]) for i in range(3)]      # mac_out carries no FCS
+    path = str(tmp_path / "wifi.pcap")
+    with W.pcap.PcapWriter(path) as w:
+        for i, p in enumerate(pdus):
+            w.write(p, ts=1000.5 + i)
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<IHH", raw, 0) == (0xA1B2C3D4, 2, 4) and struct.unpack_from("<I", raw, 20)[0] == 105
+    lt, recs = W.pcap.read_pcap(path)
+    assert lt == 105 and [r[1] for r in recs] == [p[1] for p in pdus] and abs(recs[1][0] - 1001.5) < 1e-6
+    h = W.pcap.parse_mac(pdus[2][1])
+    assert h["frame_control"] == 0x0008 and h["type"] == 2 and h["subtype"] == 0 and h["seq_nr"] == 2 and h["frag_nr"] == 0
+    assert h["addr1"] == "42:42:42:42:42:42" and h["addr2"] == "23:23:23:23:23:23" and h["addr3"] == "ff:ff:ff:ff:ff:ff"
+    assert h["payload_len"] == 12 and W.pcap.parse_mac(b"short") is None
