@@ -210,10 +210,9 @@ __global__ void __launch_bounds__(128) k_select_spec(const uint32_t *__restrict_
 
 // Sequential pass, one warp per link: accepts speculative segments 32 at a time while each first
 // trigger is more than MIN_GAP after the last trigger before it, re-walks the flags otherwise.
-// Then reserves the link's frame and row ranges and writes the frame records.
+// Leaves the triggers in trig_tmp and their count in links[].frame_count.
 __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary, LinkDesc *links,
-                                                 int n_links, wifi_b200_frame *frames, int *counters, unsigned long long *row_counter,
-                                                 int64_t max_frames, int min_plateau, int *err, int *trig_tmp,
+                                                 int n_links, int min_plateau, int *trig_tmp,
                                                  const int *__restrict__ spec_trig, const int4 *__restrict__ spec_meta)
 {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -344,17 +343,50 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
         }
     }
     __syncwarp();
-    // Reserve the link's frame records and equalizer rows.  Row offsets need no scan: bursts do not
-    // overlap, so frame i may start at row floor(t_i / 80) + i of the link's range (its burst_len/80 + 1
-    // rows end before the next frame's first row); the range is floor(len / 80) + k + 1 rows.
-    if (lane == 0) {
-        int base = atomicAdd(&counters[0], k);
-        long long row_base = (long long)atomicAdd(row_counter, (unsigned long long)(L.len / 80 + k + 1));
-        bool ovf = (int64_t)base + k > max_frames;
+    if (lane == 0) links[warp].frame_count = k;     // k_reserve turns the counts into ranges
+}
+
+// Frame-record and equalizer-row ranges of all links: an exclusive prefix sum over the links in link order, so
+// the frame table is ordered by (link, trigger) on every run.  Row offsets inside a link need no scan: bursts
+// do not overlap, so frame i may start at row floor(t_i / 80) + i of the link's range (its burst_len/80 + 1
+// rows end before the next frame's first row); the range is floor(len / 80) + k + 1 rows.
+__global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, int *counters, unsigned long long *row_counter,
+                                                   int64_t max_frames, int *err)
+{
+    __shared__ long long s_f[1024], s_r[1024];
+    const int tid = threadIdx.x;
+    const int per = (n_links + 1023) / 1024;
+    const int l0 = tid * per < n_links ? tid * per : n_links, l1 = l0 + per < n_links ? l0 + per : n_links;
+    long long f = 0, r = 0;
+    for (int l = l0; l < l1; ++l) {
+        f += links[l].frame_count;
+        r += links[l].len / 80 + links[l].frame_count + 1;
+    }
+    s_f[tid] = f;
+    s_r[tid] = r;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long af = tid >= o ? s_f[tid - o] : 0, ar = tid >= o ? s_r[tid - o] : 0;
+        __syncthreads();
+        s_f[tid] += af;
+        s_r[tid] += ar;
+        __syncthreads();
+    }
+    long long bf = s_f[tid] - f, br = s_r[tid] - r;
+    const long long total_f = s_f[1023];
+    const bool ovf = total_f > max_frames;
+    for (int l = l0; l < l1; ++l) {
+        const int k = links[l].frame_count;
+        links[l].frame_first = (int)bf;
+        links[l].row_base = br;
+        if (ovf) links[l].frame_count = 0;
+        bf += k;
+        br += links[l].len / 80 + k + 1;
+    }
+    if (tid == 0) {
+        counters[0] = total_f > 0x7fffffffll ? 0x7fffffff : (int)total_f;
+        *row_counter = (unsigned long long)s_r[1023];
         if (ovf) atomicExch(err, WIFI_E_OVERFLOW);
-        links[warp].frame_first = base;
-        links[warp].frame_count = ovf ? 0 : k;
-        links[warp].row_base = row_base;
     }
 }
 

@@ -335,9 +335,10 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
     if (total_tiles > 0)
         k_select_spec<<<(unsigned)((total_tiles * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, total_tiles,
                                                                               h->cfg.min_plateau, h->d_spec_trig, h->d_spec_cnt);
-    k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->d_frames, h->d_counters,
-                                                        (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
-                                                        h->cfg.min_plateau, h->d_counters + 2, h->d_trig_tmp, h->d_spec_trig, h->d_spec_cnt);
+    k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->cfg.min_plateau, h->d_trig_tmp,
+                                                        h->d_spec_trig, h->d_spec_cnt);
+    k_reserve<<<1, 1024, 0, s>>>(h->d_links, n_links, h->d_counters, (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
+                                 h->d_counters + 2);
     k_frames_init<<<dim3(8, n_links), 128, 0, s>>>(h->d_links, h->d_trig_tmp, h->d_frames);
     mark(h, ST_SYNC_LONG);
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));

@@ -495,3 +495,44 @@ def test_sc16_wire_format_ingest_equals_host_conversion(H, O, W):
     assert np.array_equal(a.frames["freq_short"], b.frames["freq_short"]) and np.array_equal(a.frames["snr"], b.frames["snr"])
     assert a.pdus() == b.pdus() == ref.pdus()
     assert len(b.pdus()) >= 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_fuzz_random_captures(O, W, seed):
+    """Random frame mixes (all MCS, lengths 1..1528, tight and wide gaps, 4-34 dB, CFO, 3-tap multipath, every
+    equalizer, hard and soft decisions, several links): frame table, rows, equalised points and PSDUs equal the
+    oracle's -- including the frames that fail."""
+    rng = np.random.default_rng(9000 + seed)
+    algo = int(rng.integers(0, 4))
+    soft = bool(seed & 1)
+    n_links = int(rng.integers(1, 4))
+    links, offs = [], [0]
+    for l in range(n_links):
+        parts = [np.zeros(int(rng.integers(0, 400)), np.complex64)]
+        for i in range(int(rng.integers(3, 9))):
+            enc = int(rng.integers(0, 8))
+            ln = int(rng.choice([int(rng.integers(1, 60)), int(rng.integers(60, 600)), int(rng.integers(600, 1529))], p=[0.2, 0.6, 0.2]))
+            if enc < 2 and ln > 400:
+                ln = int(rng.integers(1, 400))          # keep the BPSK frames (and the oracle's run time) short
+            parts.append(O.tx_frame(make_psdu(O, rng, ln, seq=i), enc, seed=int(rng.integers(1, 128))))
+            parts.append(np.zeros(int(rng.choice([int(rng.integers(0, 60)), int(rng.integers(300, 1500))], p=[0.25, 0.75])), np.complex64))
+        x = np.concatenate(parts).astype(np.complex64)
+        taps = ((0, 1.0),) if rng.random() < 0.5 else ((0, 1.0), (1, 0.4 * np.exp(1j * rng.uniform(0, 6.28))), (3, 0.2 * np.exp(1j * rng.uniform(0, 6.28))))
+        snr = float(rng.uniform(4, 34))
+        links.append(O.channel(x, gain=0.6, cfo=float(rng.uniform(-0.02, 0.02)), noise_sigma=0.6 * 10 ** (-snr / 20), taps=taps, seed=100 * seed + l))
+        offs.append(offs[-1] + links[-1].size)
+    y = np.concatenate(links)
+    h = W.Handle(max_samples=y.size + 1024, max_frames=256, want_carrier=True, chan_est=algo, soft_decision=soft)
+    try:
+        res = h.rx_batch(y, np.array(offs, np.uint64))
+        ref = O.rx_links(y, np.array(offs[:-1], np.int64), np.diff(offs).astype(np.int64), algo=algo, soft=soft)
+        assert_frames_equal(res, ref)
+        rows, car = h.rows(carrier=True)
+        for i in range(len(ref.frames)):
+            f, g = ref.frames[i], res.frames[i]
+            assert np.array_equal(rows[g["row_off"]:g["row_off"] + g["n_rows"]], ref.rows[f["row_off"]:f["row_off"] + f["n_rows"]]), ("rows", i)
+            assert np.array_equal(car[g["row_off"]:g["row_off"] + g["n_rows"]], ref.carrier[f["row_off"]:f["row_off"] + f["n_rows"]]), ("carrier", i)
+        assert res.pdus() == ref.pdus()
+    finally:
+        h.close()
