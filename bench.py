@@ -439,13 +439,20 @@ def main():
     roof = {"kernel": "k_viterbi", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": vit_alg, "ms_per_launch": vit_ms,
             "note": "integer-ALU-bound kernel (ncu, profiles/r01_ncu_full_top_kernels.json: sm__inst_executed_pipe_alu %s%% of peak, DRAM about 1%%): %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % ("%.0f" % alu_pct if alu_pct is not None else "?", dec_bits * 256 / (vit_ms * 1e-3) / 1e12 if vit_ms else 0.0)}
+    # the streaming front-end (sync_short autocorrelation + plateau flags) is the path's HBM-side kernel: it reads the
+    # whole capture once (8 B per sample) and writes one flag bit per sample
+    det_ms = stage_ms.get("detect", 0.0)
+    det_alg = n_samples * (8 + 1.0 / 8)
+    roof_det = {"kernel": "k_detect", "bound": "hbm", "achieved": det_alg / (det_ms * 1e-3) / 1e9 if det_ms else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (det_alg / (det_ms * 1e-3) / 1e9 / hbm_peak) if det_ms else 0.0, "algorithmic_bytes_per_launch": det_alg, "ms_per_launch": det_ms,
+                "note": "second-largest streaming stage; issue-bound by the oracle's sequential running sums (DESIGN.md 4)"}
     path_alg = n_samples * 8 + n * PSDU_LEN
     step_ms = 1e3 * elapsed_max / args.steps
     line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "decoded_mbps": mbps, "frames_per_step": tot_frames, "crc_ok_per_step": tot_ok,
             "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 12 * args.steps,   # detect, select_spec, select, frames_init, plan_fast, sync_long, demod x2, signal, plan, pack, viterbi
-            "roofline": roof, "stage_ms": stage_ms,
+            "roofline": roof, "roofline_frontend": roof_det, "stage_ms": stage_ms,
             "path_hbm": {"algorithmic_GBps": path_alg / (step_ms * 1e-3) / 1e9, "frac_of_peak": path_alg / (step_ms * 1e-3) / 1e9 / hbm_peak}}
     if not args.no_cpu and world == 1:
         from oracle import oracle as O

@@ -2,6 +2,8 @@
 seeded inputs.  Integer/index/byte results must be identical; fp32 results are identical too
 because both sides follow include/wifi_detmath.h (only the double-precision log10 of the SNR
 estimate is compared with a tolerance, 1e-9 relative)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -498,7 +500,7 @@ def test_sc16_wire_format_ingest_equals_host_conversion(H, O, W):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("WIFI_FUZZ_SEEDS", "8"))))
 def test_fuzz_random_captures(O, W, seed):
     """Random frame mixes (all MCS, lengths 1..1528, tight and wide gaps, 4-34 dB, CFO, 3-tap multipath, every
     equalizer, hard and soft decisions, several links): frame table, rows, equalised points and PSDUs equal the
