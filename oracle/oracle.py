@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  The product package never
-imports this module (tests/test_no_oracle_in_product.py greps for it).
+imports this module (tests/test_abi_and_host.py::test_product_never_touches_the_oracle greps for it).
 """
 import ctypes as C
 import os
