@@ -451,7 +451,7 @@ def main():
     line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "decoded_mbps": mbps, "frames_per_step": tot_frames, "crc_ok_per_step": tot_ok,
-            "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 12 * args.steps,   # detect, select_spec, select, frames_init, plan_fast, sync_long, demod x2, signal, plan, pack, viterbi
+            "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 13 * args.steps,   # detect, select_spec, select, reserve, frames_init, sync_long, demod x2, signal, plan_fast, plan, pack, viterbi
             "roofline": roof, "roofline_frontend": roof_det, "stage_ms": stage_ms,
             "path_hbm": {"algorithmic_GBps": path_alg / (step_ms * 1e-3) / 1e9, "frac_of_peak": path_alg / (step_ms * 1e-3) / 1e9 / hbm_peak}}
     if not args.no_cpu and world == 1:
