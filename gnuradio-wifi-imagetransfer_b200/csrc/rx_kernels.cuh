@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
 // do not overlap, so frame i may start at row floor(t_i / 80) + i of the link's range (its burst_len/80 + 1
 // rows end before the next frame's first row); the range is floor(len / 80) + k + 1 rows.
 __global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, int *counters, unsigned long long *row_counter,
-                                                   int64_t max_frames, int *err)
+                                                   int64_t max_frames, int *err, const int *__restrict__ trig_tmp)
 {
     __shared__ long long s_f[1024], s_r[1024];
     const int tid = threadIdx.x;
@@ -387,6 +387,9 @@ __global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, 
         counters[0] = total_f > 0x7fffffffll ? 0x7fffffff : (int)total_f;
         *row_counter = (unsigned long long)s_r[1023];
         if (ovf) atomicExch(err, WIFI_E_OVERFLOW);
+        // streaming (one link): position of the newest trigger, so the host can tell whether its burst is complete
+        const int k0 = links[0].frame_count;
+        counters[3] = (n_links == 1 && k0 > 0) ? trig_tmp[links[0].chunk_base / 4 + k0 - 1] : -1;
     }
 }
 

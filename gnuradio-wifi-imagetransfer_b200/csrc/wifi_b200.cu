@@ -206,6 +206,8 @@ struct wifi_b200 {
     int64_t s_abs0 = 0;            // absolute index of the first non-history sample in sbuf
     int s_hist = 0;
     int64_t s_prev_trigger = -1;   // absolute
+    int64_t s_batch = 0;           // WIFI_P_STREAM_BATCH: rx_push only buffers until this many new samples wait (0: every push)
+    int64_t s_unprocessed = 0;     // samples appended since the last pipeline run
     float s_fo_carry = 0.f;
     std::vector<wifi_b200_frame> s_meta;
     std::vector<uint8_t> s_bytes;
@@ -338,7 +340,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
     k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->cfg.min_plateau, h->d_trig_tmp,
                                                         h->d_spec_trig, h->d_spec_cnt);
     k_reserve<<<1, 1024, 0, s>>>(h->d_links, n_links, h->d_counters, (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
-                                 h->d_counters + 2);
+                                 h->d_counters + 2, h->d_trig_tmp);
     k_frames_init<<<dim3(8, n_links), 128, 0, s>>>(h->d_links, h->d_trig_tmp, h->d_frames);
     mark(h, ST_SYNC_LONG);
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
@@ -354,8 +356,12 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
         return WIFI_E_OVERFLOW;
     }
     h->n_triggers = nf;
+    // streaming: the newest burst is held back while its end is unknown -- a later trigger may still cut it
+    // short -- i.e. until MAX_SAMPLES of the stream have arrived behind its trigger (then sync_short's COPY
+    // state has ended whatever follows, and the frame is released without waiting for another one)
+    if (hold_last && nf > 0 && h->h_links[0].len - (int64_t)h->h_counters[3] >= SS_MAX_SAMPLES) hold_last = false;
     if (hold_last && nf > 0) {
-        // streaming: the newest burst is not complete yet; single link
+        // single link
         nf = nf - 1;
         h->h_links[0].frame_first = 0;
         h->h_links[0].frame_count = (int)nf;
@@ -578,6 +584,7 @@ int wifi_b200_set_param(wifi_b200_t *h, int id, double v)
     case WIFI_P_ENCODING: if (v < 0 || v > 7) return WIFI_E_ARG; h->cfg.encoding = (int)v; break;
     case WIFI_P_MIN_PLATEAU: if (v < 1 || v > 16) return WIFI_E_ARG; h->cfg.min_plateau = (int)v; break;
     case WIFI_P_SOFT_DECISION: h->cfg.soft_decision = v != 0; break;
+    case WIFI_P_STREAM_BATCH: if (v < 0 || v > (double)h->cfg.max_samples / 2) return WIFI_E_ARG; h->s_batch = (int64_t)v; break;
     case WIFI_P_WANT_CARRIER:
         if (v != 0 && !h->d_carrier) {
             cudaSetDevice(h->device);
@@ -603,6 +610,7 @@ double wifi_b200_get_param(wifi_b200_t *h, int id)
     case WIFI_P_MIN_PLATEAU: return h->cfg.min_plateau;
     case WIFI_P_WANT_CARRIER: return h->cfg.want_carrier;
     case WIFI_P_SOFT_DECISION: return h->cfg.soft_decision;
+    case WIFI_P_STREAM_BATCH: return (double)h->s_batch;
     default: return NAN;
     }
 }
@@ -933,7 +941,7 @@ int wifi_b200_rx_reset(wifi_b200_t *h)
     if (!h) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
     h->sbuf.clear();
-    h->s_abs0 = 0; h->s_hist = 0; h->s_prev_trigger = -1; h->s_fo_carry = 0.f;
+    h->s_abs0 = 0; h->s_hist = 0; h->s_prev_trigger = -1; h->s_fo_carry = 0.f; h->s_unprocessed = 0;
     h->s_meta.clear(); h->s_bytes.clear();
     return WIFI_OK;
 }
@@ -944,9 +952,14 @@ int wifi_b200_rx_push(wifi_b200_t *h, const float *iq, size_t n, int flush)
     std::lock_guard<std::mutex> g(h->mu);
     cudaSetDevice(h->device);
     if (n) h->sbuf.insert(h->sbuf.end(), iq, iq + 2 * n);
+    h->s_unprocessed += (int64_t)n;
     const int64_t have = (int64_t)(h->sbuf.size() / 2) - h->s_hist;   // samples from s_abs0 on
     if (have <= 0) return WIFI_OK;
     if (have + h->s_hist > h->cfg.max_samples) { h->err = "stream backlog exceeds max_samples"; return WIFI_E_OVERFLOW; }
+    // small pushes only buffer: the pipeline has a fixed cost of a millisecond or two per run (one trellis per
+    // thread), so it runs when enough new samples wait, when the workspace is half full, on an empty push, or on flush
+    if (!flush && n != 0 && h->s_unprocessed < h->s_batch && 2 * (have + h->s_hist) < h->cfg.max_samples) return WIFI_OK;   // n == 0: run now
+    h->s_unprocessed = 0;
     int rc = ensure_iq_staging(h);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_iq, h->sbuf.data(), h->sbuf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));

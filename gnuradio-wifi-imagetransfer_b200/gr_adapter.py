@@ -22,6 +22,7 @@ Both call the same facade (`wifi_phy_hier.py`) that the GNU-Radio-free users cal
 libwifi_b200.so.  `grc/ieee802_11_wifi_phy_hier_b200.block.yml` makes the block appear in GRC.
 """
 import collections
+import queue
 import threading
 
 import numpy as np
@@ -33,6 +34,7 @@ except ImportError as e:  # pragma: no cover - exercised by tests/test_gr_adapte
     raise ImportError("wifi_b200.gr_adapter needs GNU Radio 3.10 (gnuradio.gr, pmt); "
                       "use wifi_b200.wifi_phy_hier without GNU Radio") from e
 
+from . import wifi_b200 as _w
 from .wifi_phy_hier import wifi_phy_hier as _facade
 
 _MAC_IN, _MAC_OUT, _CARRIER = "mac_in", "mac_out", "carrier"
@@ -89,32 +91,76 @@ class wifi_tx_b200(gr.basic_block):
 
 
 class wifi_rx_b200(gr.basic_block):
-    """complex stream -> messages `mac_out` and (if connected) `carrier`"""
+    """complex stream -> messages `mac_out` and (if connected) `carrier`.
 
-    def __init__(self, phy):
+    `general_work` only hands the samples to a worker thread, so the scheduler thread never stalls (a live SDR
+    source overflows if its consumer blocks for milliseconds).  The worker pushes them into the library, which
+    buffers until `stream_batch` new samples wait (WIFI_P_STREAM_BATCH): one pipeline run costs 1-3 ms whatever
+    its size, 131072 samples are 6.5 ms of a 20 Msps stream."""
+
+    def __init__(self, phy, stream_batch=131072):
         gr.basic_block.__init__(self, name="wifi_rx_b200", in_sig=[np.complex64], out_sig=None)
         self._phy = phy
         self.message_port_register_out(pmt.intern(_MAC_OUT))
         self.message_port_register_out(pmt.intern(_CARRIER))
         phy.msg_connect_carrier(self._publish_carrier)
+        phy.handle.set_param(_w.P_STREAM_BATCH, int(stream_batch))
+        self._q = queue.Queue()
+        self._worker = None
+        self._error = None
 
     def _publish_carrier(self, pdu):
         _meta, pts = pdu
         self.message_port_pub(pmt.intern(_CARRIER), pmt.cons(pmt.make_dict(), pmt.init_c32vector(len(pts), [complex(v) for v in pts])))
 
+    def _publish(self, pdus):
+        for meta, mpdu in pdus:
+            meta = {k: meta[k] for k in ("snr", "nomfreq", "freqofs", "dlt")}     # upstream decode_mac's dict
+            self.message_port_pub(pmt.intern(_MAC_OUT), pdu_from_python(meta, mpdu))
+
+    def _run(self):
+        try:
+            idle = True
+            while True:
+                try:
+                    x = self._q.get(timeout=0.05)
+                except queue.Empty:
+                    if not idle:                       # the stream paused: decode what is buffered (empty push = run now)
+                        self._publish(self._phy.samp_in(np.zeros(0, np.complex64)))
+                        idle = True
+                    continue
+                if x is None:
+                    break
+                idle = False
+                self._publish(self._phy.samp_in(x))
+            self._publish(self._phy.samp_in(np.zeros(0, np.complex64), flush=True))   # the newest burst is held until flushed
+        except Exception as e:   # surfaced by the next general_work / stop
+            self._error = e
+
+    def start(self):
+        if self._worker is None:
+            self._worker = threading.Thread(target=self._run, name="wifi_rx_b200", daemon=True)
+            self._worker.start()
+        return True
+
     def general_work(self, input_items, output_items):
+        if self._error is not None:
+            raise self._error
+        if self._worker is None:
+            self.start()
         x = input_items[0]
         if len(x):
-            for meta, mpdu in self._phy.samp_in(np.asarray(x, dtype=np.complex64)):
-                meta = {k: meta[k] for k in ("snr", "nomfreq", "freqofs", "dlt")}     # upstream decode_mac's dict
-                self.message_port_pub(pmt.intern(_MAC_OUT), pdu_from_python(meta, mpdu))
+            self._q.put(np.array(x, dtype=np.complex64))      # copy: the scheduler reuses its buffer
             self.consume(0, len(x))
         return 0
 
     def stop(self):
-        for meta, mpdu in self._phy.samp_in(np.zeros(0, np.complex64), flush=True):    # the newest burst is held until flushed
-            meta = {k: meta[k] for k in ("snr", "nomfreq", "freqofs", "dlt")}
-            self.message_port_pub(pmt.intern(_MAC_OUT), pdu_from_python(meta, mpdu))
+        if self._worker is not None:
+            self._q.put(None)
+            self._worker.join()
+            self._worker = None
+        if self._error is not None:
+            raise self._error
         return True
 
 
@@ -122,7 +168,7 @@ class wifi_phy_hier_b200(gr.hier_block2):
     """Drop-in for the GRC-generated `wifi_phy_hier` (same keywords, ports and setters)."""
 
     def __init__(self, bandwidth=10e6, chan_est=0, encoding=0, frequency=5.89e9, sensitivity=0.56, device=0, max_samples=1 << 22,
-                 want_carrier=False):
+                 want_carrier=False, stream_batch=131072):
         gr.hier_block2.__init__(self, "WiFi PHY Hier (B200)",
                                 gr.io_signature(1, 1, gr.sizeof_gr_complex * 1),
                                 gr.io_signature(1, 1, gr.sizeof_gr_complex * 1))
@@ -134,7 +180,7 @@ class wifi_phy_hier_b200(gr.hier_block2):
         self._phy = _facade(bandwidth=bandwidth, chan_est=int(chan_est), encoding=int(encoding), frequency=frequency,
                             sensitivity=sensitivity, device=device, max_samples=max_samples, want_carrier=want_carrier)
         self.tx = wifi_tx_b200(self._phy)
-        self.rx = wifi_rx_b200(self._phy)
+        self.rx = wifi_rx_b200(self._phy, stream_batch)
         self.connect((self, 0), (self.rx, 0))                                  # samp_in   (wifi_phy_hier.grc:762-764)
         self.connect((self.tx, 0), (self, 0))                                  # samp_out  (:752)
         self.msg_connect((self, _MAC_IN), (self.tx, _MAC_IN))                  # mac_in    (:765)

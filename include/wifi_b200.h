@@ -52,7 +52,11 @@ enum { WIFI_BPSK_1_2 = 0, WIFI_BPSK_3_4, WIFI_QPSK_1_2, WIFI_QPSK_3_4, WIFI_QAM1
 enum { WIFI_EQ_LS = 0, WIFI_EQ_LMS = 1, WIFI_EQ_COMB = 2, WIFI_EQ_STA = 3 };
 /* ids for wifi_b200_set_param: the hier block's parameters */
 enum { WIFI_P_BANDWIDTH = 0, WIFI_P_FREQUENCY = 1, WIFI_P_SENSITIVITY = 2, WIFI_P_CHAN_EST = 3, WIFI_P_ENCODING = 4,
-       WIFI_P_MIN_PLATEAU = 5, WIFI_P_WANT_CARRIER = 6, WIFI_P_SOFT_DECISION = 7 };
+       WIFI_P_MIN_PLATEAU = 5, WIFI_P_WANT_CARRIER = 6, WIFI_P_SOFT_DECISION = 7,
+       /* streaming only: wifi_b200_rx_push buffers until this many new samples wait (0 = run on every push).  A run
+        * costs 1-3 ms whatever its size, so a live 20 Msps stream wants 65536 or more; results are unchanged.
+        * An empty push (n = 0, flush = 0) runs the pipeline on whatever is buffered without ending the stream. */
+       WIFI_P_STREAM_BATCH = 8 };
 
 typedef struct wifi_b200_cfg {
     double bandwidth;      /* Hz, hier default 10e6 (wifi_phy_hier.grc:92)                        */

@@ -538,3 +538,58 @@ def test_fuzz_random_captures(O, W, seed):
         assert res.pdus() == ref.pdus()
     finally:
         h.close()
+
+
+@pytest.mark.gpu
+def test_streaming_releases_a_lone_frame_and_batches_small_pushes(O, W):
+    """(1) Sparse traffic: a frame followed by noise only is published once MAX_SAMPLES (43200) of the stream have
+    arrived behind its trigger -- no later frame and no flush needed.  (2) WIFI_P_STREAM_BATCH: small pushes only
+    buffer; the PDUs are those of the whole-capture decode, in order."""
+    rng = np.random.default_rng(77)
+    y1, _ = make_capture(O, rng, [(5, 300)], snr_db=28, cfo=0.004, seed=9, gap=200)
+    noise = O.channel(np.zeros(60000, np.complex64), gain=1.0, noise_sigma=0.6 * 10 ** (-28 / 20), seed=10)
+    y2, _ = make_capture(O, rng, [(3, 500), (7, 900)], snr_db=28, cfo=-0.003, seed=11)
+    y = np.concatenate([y1, noise, y2]).astype(np.complex64)
+    ref = O.rx(y, algo=0)
+    want = [(int(f["trigger"]), ref.psdu(i)[:-4]) for i, f in enumerate(ref.frames) if f["crc_ok"]]
+    assert len(want) == 3
+    # (1) pushes of 4096 samples, never flushed until the very end
+    h = W.Handle(max_samples=1 << 18)
+    got, first_seen_at = [], None
+    for pos in range(0, y.size, 4096):
+        h.rx_push(y[pos:pos + 4096], flush=False)
+        new = h.rx_pop()
+        if new and first_seen_at is None:
+            first_seen_at = pos + 4096
+        got += new
+    t0 = want[0][0]
+    assert first_seen_at is not None and first_seen_at <= t0 + 43200 + 2 * 4096, (first_seen_at, t0)     # before the next frame (y1.size + 60000) arrives
+    assert first_seen_at < y1.size + 60000
+    h.rx_push(np.zeros(0, np.complex64), flush=True)
+    got += h.rx_pop()
+    assert [(int(f["trigger"]), d) for f, d in got] == want
+    h.close()
+    # (2) 1000-sample pushes with a 20000-sample batch threshold
+    h = W.Handle(max_samples=1 << 18)
+    h.set_param(W.wifi_b200.P_STREAM_BATCH, 20000)
+    assert h.get_param(W.wifi_b200.P_STREAM_BATCH) == 20000
+    got, runs = [], 0
+    for pos in range(0, y.size, 1000):
+        before = h.stats()["samples"]
+        h.rx_push(y[pos:pos + 1000], flush=(pos + 1000 >= y.size))
+        runs += h.stats()["samples"] != before
+        got += h.rx_pop()
+    assert [(int(f["trigger"]), d) for f, d in got] == want
+    assert runs <= y.size // 20000 + 2, runs          # the pipeline ran once per batch, not once per push
+    # an empty push runs the pipeline on what is buffered without ending the stream
+    h.rx_reset()
+    h.rx_push(y[:y1.size + 50000], flush=False)       # one push above the threshold: runs, frame 1 is released (43200 behind it)
+    first = h.rx_pop()
+    h.rx_push(y[y1.size + 50000:y1.size + 50000 + 12000], flush=False)    # below the threshold: buffered only
+    before = h.stats()["samples"]
+    h.rx_push(np.zeros(0, np.complex64), flush=False)
+    assert h.stats()["samples"] != before
+    h.rx_push(y[y1.size + 62000:], flush=True)
+    rest = h.rx_pop()
+    assert [(int(f["trigger"]), d) for f, d in first + rest] == want
+    h.close()

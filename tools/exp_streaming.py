@@ -1,0 +1,32 @@
+"""Throughput of the streaming entry point (wifi_b200_rx_push / rx_pop: what the GNU Radio adapter and the UDP
+runner call) for different push sizes, one continuous 64-QAM 3/4 stream from host memory."""
+import sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+import bench as B
+import wifi_b200 as W
+
+B.set_workload("c3")
+fpl = 2048
+flen = B.frame_samples()
+n_samples = B.LEAD + fpl * (flen + B.GAP)
+h = W.Handle(device=0, chan_est=1, encoding=7, max_samples=n_samples + 1024, max_frames=fpl + 1024)
+cap, link_off, psdus = B.build_capture(h, W, torch, 1, fpl, seed=7)
+x = cap.cpu().numpy().view(np.complex64)
+h.close()
+for chunk, batch in ((4096, 0), (16384, 0), (65536, 0), (262144, 0), (1048576, 0), (4096, 65536), (4096, 131072), (4096, 262144), (8192, 1048576)):
+    hs = W.Handle(device=0, chan_est=1, encoding=7, max_samples=2 * max(chunk, batch) + 262144, max_frames=4096)
+    hs.set_param(W.wifi_b200.P_STREAM_BATCH, batch)
+    n_pdu = 0
+    t0 = time.perf_counter()
+    lim = min(x.size, max(chunk, batch) * 24 if batch else chunk * 200)
+    for p in range(0, lim, chunk):
+        hs.rx_push(x[p:p + chunk], flush=(p + chunk >= lim))
+        while True:
+            got = hs.rx_pop()
+            if not got:
+                break
+            n_pdu += len(got)
+    dt = time.perf_counter() - t0
+    print("push %8d samples, batch %8d: %8.1f Msamples/s  (%d pushes, %d PDUs, %.1f us per push)" % (chunk, batch, lim / dt / 1e6, -(-lim // chunk), n_pdu, 1e6 * dt / -(-lim // chunk)))
+    hs.close()
