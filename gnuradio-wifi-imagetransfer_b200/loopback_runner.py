@@ -83,24 +83,19 @@ class IrsTransceiver:
             return
         burst = self.phy.mac_in(pdu)
         self.phy.samp_out.clear()
-        self._emit(self.phy.samp_in(self._through_channel(burst)))
+        # one datagram = one padded burst (100 zeros, frame, 1000 zeros): it is complete, so the stream is flushed
+        # behind it and the patch reaches the viewer now instead of when the next one arrives
+        self._emit(self.phy.samp_in(self._through_channel(burst), flush=True))
 
     def serve(self, max_datagrams=None):
-        pending = False
         n = 0
         while not self._stop.is_set() and (max_datagrams is None or n < max_datagrams):
             try:
                 data, _ = self.rx_sock.recvfrom(65536)
             except socket.timeout:
-                if pending:                          # the newest frame is held until a later trigger or a flush
-                    self._emit(self.phy.samp_in(np.zeros(0, np.complex64), flush=True))
-                    pending = False
                 continue
             self.handle_datagram(data)
-            pending = True
             n += 1
-        if pending:
-            self._emit(self.phy.samp_in(np.zeros(0, np.complex64), flush=True))
 
     def stop(self):
         self._stop.set()
