@@ -33,6 +33,7 @@ GAP = 1100
 SNR_DB = 30.0
 ALGO = 1          # LMS
 LEAD = 128
+TX_INFO = {}
 SC16_SCALE = 1.0 / 4096.0   # int16 wire format of the e2e sc16 line: full scale +-8, quantisation noise ~78 dB below the signal
 
 
@@ -93,6 +94,13 @@ def build_capture(h, W, torch, n_links, fpl, seed):
     tx = torch.empty(2 * n * flen, dtype=torch.float32, device="cuda")
     tot, off = h.tx_dev(psdus, tx.data_ptr(), n * flen, enc=ENC)
     assert tot == n * flen
+    # the TX chain is not on the metric path; its rate is reported beside it (PSDU blob over PCIe, IQ stays on the device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h.tx_dev(psdus, tx.data_ptr(), n * flen, enc=ENC)
+    torch.cuda.synchronize()
+    TX_INFO.update(value=n * flen / (time.perf_counter() - t0) / 1e6, unit="Msamples/s", frames=n,
+                   how="wifi_b200_tx_dev: mapper .. cyclic prefixer for every frame of the capture, host PSDUs in, device IQ out")
     cap = torch.zeros(2 * n_links * link_len, dtype=torch.float32, device="cuda")
     rng = np.random.default_rng(seed + 1)
     seg = np.zeros(n + n_links, W.wifi_b200.CHANSEG_DTYPE)
@@ -452,7 +460,7 @@ def main():
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "decoded_mbps": mbps, "frames_per_step": tot_frames, "crc_ok_per_step": tot_ok,
             "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 13 * args.steps,   # detect, select_spec, select, reserve, frames_init, sync_long, demod x2, signal, plan_fast, plan, pack, viterbi
-            "roofline": roof, "roofline_frontend": roof_det, "stage_ms": stage_ms,
+            "roofline": roof, "roofline_frontend": roof_det, "stage_ms": stage_ms, "tx": dict(TX_INFO),
             "path_hbm": {"algorithmic_GBps": path_alg / (step_ms * 1e-3) / 1e9, "frac_of_peak": path_alg / (step_ms * 1e-3) / 1e9 / hbm_peak}}
     if not args.no_cpu and world == 1:
         from oracle import oracle as O
