@@ -593,3 +593,37 @@ def test_streaming_releases_a_lone_frame_and_batches_small_pushes(O, W):
     rest = h.rx_pop()
     assert [(int(f["trigger"]), d) for f, d in first + rest] == want
     h.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(int(os.environ.get("WIFI_FUZZ_SEEDS", "6"))))
+def test_fuzz_streaming_equals_whole_capture(O, W, seed):
+    """Random streams (frames of every MCS, dead air from 0 to 60000 samples between them so that bursts end by a
+    later trigger, by MAX_SAMPLES or by the flush), pushed in random chunk sizes with a random WIFI_P_STREAM_BATCH:
+    the published PDUs and their absolute trigger positions equal the whole-capture decode."""
+    rng = np.random.default_rng(4200 + seed)
+    parts = [np.zeros(int(rng.integers(0, 300)), np.complex64)]
+    for i in range(int(rng.integers(4, 10))):
+        enc = int(rng.integers(0, 8))
+        ln = int(rng.integers(20, 400 if enc < 2 else 1200))
+        parts.append(0.6 * O.tx_frame(make_psdu(O, rng, ln, seq=i), enc, seed=int(rng.integers(1, 128))))
+        parts.append(np.zeros(int(rng.choice([int(rng.integers(0, 200)), int(rng.integers(500, 3000)), int(rng.integers(44000, 60000))], p=[0.2, 0.5, 0.3])), np.complex64))
+    x = np.concatenate(parts).astype(np.complex64)
+    y = O.channel(x, gain=1.0, cfo=float(rng.uniform(-0.01, 0.01)), noise_sigma=0.6 * 10 ** (-float(rng.uniform(18, 32)) / 20), seed=seed)
+    algo = int(rng.integers(0, 4))
+    ref = O.rx(y, algo=algo)
+    want = [(int(f["trigger"]), ref.psdu(i)[:-4]) for i, f in enumerate(ref.frames) if f["crc_ok"]]
+    h = W.Handle(max_samples=1 << 20, max_frames=256, chan_est=algo)
+    try:
+        h.set_param(W.wifi_b200.P_STREAM_BATCH, int(rng.choice([0, 0, 5000, 40000, 200000])))
+        got, pos = [], 0
+        while pos < y.size:
+            n = int(rng.choice([int(rng.integers(1, 500)), int(rng.integers(500, 20000)), int(rng.integers(20000, 90000))]))
+            h.rx_push(y[pos:pos + n], flush=(pos + n >= y.size))
+            if rng.random() < 0.1:
+                h.rx_push(np.zeros(0, np.complex64))          # "run now"
+            got += h.rx_pop()
+            pos += n
+        assert [(int(f["trigger"]), d) for f, d in got] == want
+    finally:
+        h.close()
