@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
 // do not overlap, so frame i may start at row floor(t_i / 80) + i of the link's range (its burst_len/80 + 1
 // rows end before the next frame's first row); the range is floor(len / 80) + k + 1 rows.
 __global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, int *counters, unsigned long long *row_counter,
-                                                   int64_t max_frames, int *err, const int *__restrict__ trig_tmp)
+                                                   int64_t max_frames, int *err)
 {
     __shared__ long long s_f[1024], s_r[1024];
     const int tid = threadIdx.x;
@@ -387,9 +387,7 @@ __global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, 
         counters[0] = total_f > 0x7fffffffll ? 0x7fffffff : (int)total_f;
         *row_counter = (unsigned long long)s_r[1023];
         if (ovf) atomicExch(err, WIFI_E_OVERFLOW);
-        // streaming (one link): position of the newest trigger, so the host can tell whether its burst is complete
-        const int k0 = links[0].frame_count;
-        counters[3] = (n_links == 1 && k0 > 0) ? trig_tmp[links[0].chunk_base / 4 + k0 - 1] : -1;
+
     }
 }
 
@@ -406,8 +404,13 @@ __global__ void __launch_bounds__(128) k_frames_init(const LinkDesc *__restrict_
         wifi_b200_frame f;
         f.trigger = t; f.link = l;
         f.burst_len = (int)((endp - t) < SS_MAX_SAMPLES ? (endp - t) : SS_MAX_SAMPLES);
+        // Streaming: the newest burst of a link is complete once MAX_SAMPLES of the stream lie behind its trigger
+        // (sync_short's COPY state has ended whatever follows); until then a later trigger may still cut it short,
+        // so it is held: no samples (burst_len 0: every later stage skips it) and n_syms = -1 as the marker.
+        const bool held = L.hold_last && i == k - 1 && (L.len - t) < SS_MAX_SAMPLES;
+        if (held) f.burst_len = 0;
         f.freq_short = 0.f; f.freq_long = 0.f;
-        f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
+        f.found = 0; f.frame_start = SYNC_LENGTH; f.n_syms = held ? -1 : 0; f.sig_ok = 0; f.encoding = 0; f.length = 0;
         f.frame_symbols = 0; f.n_rows = 0; f.accepted = 0; f.decoded = 0; f.crc_ok = 0; f.snr = 0.0;
         f.row_off = L.row_base + t / 80 + i; f.psdu_off = -1;
         frames[L.frame_first + i] = f;
@@ -1037,8 +1040,12 @@ __global__ void __launch_bounds__(128) k_plan_fast(wifi_b200_frame *frames, int 
     frames[fi].psdu_off = (int64_t)fi * PSDU_STRIDE;
 }
 
+// link_open[l]: frame at which the link's decode_mac state was left open at the end of the buffer (a tag waiting for
+// rows, or a collection short of symbols), -1 if closed.  Streaming uses it to defer those frames while the next burst
+// is still held back.
 __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links, int n_links, wifi_b200_frame *frames, JobDesc *jobs,
-                                               int *pack_list, int *n_pack, int *err, int soft, const int *__restrict__ link_dirty)
+                                               int *pack_list, int *n_pack, int *err, int soft, const int *__restrict__ link_dirty,
+                                               int *__restrict__ link_open)
 {
     int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (l >= n_links) return;
@@ -1093,6 +1100,7 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
             // S.J / S.bad of an open collection live in lane 0 only; lane 0 is the one that continues it
         }
     }
+    if (lane == 0) link_open[l] = S.pending >= 0 ? S.pending : ((S.cur >= 0 && S.copied < S.need) ? S.cur : -1);
 }
 
 // ------------------------------------------------------------------ R6 unpack/deinterleave/depuncture

@@ -201,14 +201,17 @@ struct wifi_b200 {
     bool ev_used[ST_COUNT + 1];
     float stage_ms[ST_COUNT];
     wifi_b200_stats stats;
-    // streaming
-    std::vector<float> sbuf;       // pending samples (interleaved), sbuf[0] is absolute index s_abs0 - s_hist
-    int64_t s_abs0 = 0;            // absolute index of the first non-history sample in sbuf
-    int s_hist = 0;
-    int64_t s_prev_trigger = -1;   // absolute
-    int64_t s_batch = 0;           // WIFI_P_STREAM_BATCH: rx_push only buffers until this many new samples wait (0: every push)
-    int64_t s_unprocessed = 0;     // samples appended since the last pipeline run
-    float s_fo_carry = 0.f;
+    // streaming: one state per link (wifi_b200_rx_push = one link, wifi_b200_rx_push_links = many)
+    struct StreamLink {
+        std::vector<float> sbuf;   // pending samples (interleaved), sbuf[0] is absolute index abs0 - hist
+        int64_t abs0 = 0;          // absolute index of the first non-history sample in sbuf
+        int hist = 0;
+        int64_t prev_trigger = -1; // absolute
+        float fo_carry = 0.f;
+    };
+    std::vector<StreamLink> s_links;
+    int64_t s_batch = 0;           // WIFI_P_STREAM_BATCH: a push only buffers until this many new samples per link wait (0: every push)
+    int64_t s_unprocessed = 0;     // samples appended to the fullest link since the last pipeline run
     std::vector<wifi_b200_frame> s_meta;
     std::vector<uint8_t> s_bytes;
 };
@@ -306,7 +309,7 @@ void mark(wifi_b200 *h, int i)
 }
 
 // the receive pipeline over device-resident samples; links already in h->h_links
-int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming: newest burst not complete yet */)
+int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
 {
     const int n_links = (int)h->h_links.size();
     int64_t total_tiles = 0, total = 0;
@@ -340,7 +343,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
     k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->cfg.min_plateau, h->d_trig_tmp,
                                                         h->d_spec_trig, h->d_spec_cnt);
     k_reserve<<<1, 1024, 0, s>>>(h->d_links, n_links, h->d_counters, (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
-                                 h->d_counters + 2, h->d_trig_tmp);
+                                 h->d_counters + 2);
     k_frames_init<<<dim3(8, n_links), 128, 0, s>>>(h->d_links, h->d_trig_tmp, h->d_frames);
     mark(h, ST_SYNC_LONG);
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
@@ -356,20 +359,6 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
         return WIFI_E_OVERFLOW;
     }
     h->n_triggers = nf;
-    // streaming: the newest burst is held back while its end is unknown -- a later trigger may still cut it
-    // short -- i.e. until MAX_SAMPLES of the stream have arrived behind its trigger (then sync_short's COPY
-    // state has ended whatever follows, and the frame is released without waiting for another one)
-    if (hold_last && nf > 0 && h->h_links[0].len - (int64_t)h->h_counters[3] >= SS_MAX_SAMPLES) hold_last = false;
-    if (hold_last && nf > 0) {
-        // single link
-        nf = nf - 1;
-        h->h_links[0].frame_first = 0;
-        h->h_links[0].frame_count = (int)nf;
-        LinkDesc tmp;
-        CK(cudaMemcpy(&tmp, h->d_links, sizeof tmp, cudaMemcpyDeviceToHost));
-        tmp.frame_count = (int)nf;
-        CK(cudaMemcpyAsync(h->d_links, &tmp, sizeof tmp, cudaMemcpyHostToDevice, s));
-    }
     h->n_frames = nf;
     h->n_jobs = nf;       // decode jobs live at the index of their owner frame
     h->n_rows = rows_needed;
@@ -394,9 +383,10 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, bool hold_last /* streaming:
                                                         h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
         mark(h, ST_PLAN);
         CK(cudaMemsetAsync(h->d_link_dirty, 0, (size_t)n_links * sizeof(int), s));
+        CK(cudaMemsetAsync(h->d_link_dirty + MAX_LINKS, 0xff, (size_t)n_links * sizeof(int), s));
         k_plan_fast<<<(unsigned)((nf + 127) / 128), 128, 0, s>>>(h->d_frames, (int)nf, h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_link_dirty, soft);
         k_plan<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_pack_list, h->d_counters + 1,
-                                                          h->d_counters + 2, soft, h->d_link_dirty);
+                                                          h->d_counters + 2, soft, h->d_link_dirty, h->d_link_dirty + MAX_LINKS);
         mark(h, ST_PACK);
         size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256 + 128;   // ring, CRC table, descrambler table, branch words
         if (!soft) {
@@ -443,20 +433,22 @@ int fetch_frames(wifi_b200 *h)
     return WIFI_OK;
 }
 
+void count_frame(wifi_b200_stats &st, const wifi_b200_frame &f)
+{
+    st.frames_detected++;
+    st.signal_ok += f.sig_ok;
+    st.decoded += f.decoded;
+    if (f.crc_ok) {
+        st.crc_ok++;
+        st.pdu_bytes += f.length - 4;
+        st.per_mcs_crc_ok[f.encoding & 7]++;
+    }
+}
+
 void update_stats(wifi_b200 *h)
 {
     h->stats.samples += h->n_samples;
-    h->stats.frames_detected += h->n_frames;
-    for (int64_t i = 0; i < h->n_frames; ++i) {
-        const wifi_b200_frame &f = h->h_frames[i];
-        h->stats.signal_ok += f.sig_ok;
-        h->stats.decoded += f.decoded;
-        if (f.crc_ok) {
-            h->stats.crc_ok++;
-            h->stats.pdu_bytes += f.length - 4;
-            h->stats.per_mcs_crc_ok[f.encoding & 7]++;
-        }
-    }
+    for (int64_t i = 0; i < h->n_frames; ++i) count_frame(h->stats, h->h_frames[i]);
 }
 
 int set_links(wifi_b200 *h, const uint64_t *link_off, int n_links, int final)
@@ -547,7 +539,7 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     A((void **)&h->d_spec_trig, (size_t)h->tile_cap * SEG_CAP * sizeof(int));
     A((void **)&h->d_spec_cnt, (size_t)h->tile_cap * sizeof(int4));
     A((void **)&h->d_pack_list, (size_t)2 * Fm * sizeof(int));
-    A((void **)&h->d_link_dirty, (size_t)MAX_LINKS * sizeof(int));
+    A((void **)&h->d_link_dirty, (size_t)2 * MAX_LINKS * sizeof(int));   // [0, MAX_LINKS): dirty flags, [MAX_LINKS, 2 MAX_LINKS): open decode_mac state
     A((void **)&h->d_links, (size_t)MAX_LINKS * sizeof(LinkDesc));
     A((void **)&h->d_frames, (size_t)Fm * sizeof(wifi_b200_frame));
     A((void **)&h->d_states, (size_t)Fm * sizeof(EqState));
@@ -794,7 +786,7 @@ int wifi_b200_rx_batch_dev(wifi_b200_t *h, const float *iq_dev, const uint64_t *
     int rc = set_links(h, link_off, n_links, final);
     if (rc) return rc;
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
-    rc = run_rx(h, (const cf *)iq_dev, false, false);
+    rc = run_rx(h, (const cf *)iq_dev, false);
     return rc;
 }
 
@@ -820,7 +812,7 @@ int wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *lin
         CK(cudaMemcpyAsync(h->d_iq, iq_host + 2 * base, (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
-    rc = run_rx(h, h->d_iq, true, false);
+    rc = run_rx(h, h->d_iq, true);
     if (rc) return rc;
     update_stats(h);
     return WIFI_OK;
@@ -852,7 +844,7 @@ int wifi_b200_rx_batch_sc16(wifi_b200_t *h, const int16_t *iq_host, float scale,
         if (blocks > 148 * 16) blocks = 148 * 16;
         k_sc16_to_fc32<<<(unsigned)blocks, 256, 0, h->stream>>>(h->d_sc16, h->d_iq, total, scale);
     }
-    rc = run_rx(h, h->d_iq, true, false);
+    rc = run_rx(h, h->d_iq, true);
     if (rc) return rc;
     update_stats(h);
     return WIFI_OK;
@@ -940,9 +932,108 @@ int wifi_b200_rx_reset(wifi_b200_t *h)
 {
     if (!h) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
-    h->sbuf.clear();
-    h->s_abs0 = 0; h->s_hist = 0; h->s_prev_trigger = -1; h->s_fo_carry = 0.f; h->s_unprocessed = 0;
+    h->s_links.clear();
+    h->s_unprocessed = 0;
     h->s_meta.clear(); h->s_bytes.clear();
+    return WIFI_OK;
+}
+
+// Streaming over n_links continuous streams: link l receives iq[link_off[l] .. link_off[l+1]) new samples.
+static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, int n_links, int flush)
+{
+    if (n_links <= 0 || n_links > MAX_LINKS) return WIFI_E_ARG;
+    if (h->s_links.empty()) h->s_links.resize(n_links);
+    if ((int)h->s_links.size() != n_links) { h->err = "the number of streams is fixed until wifi_b200_rx_reset"; return WIFI_E_ARG; }
+    cudaSetDevice(h->device);
+    int64_t total = 0, newest = 0, pushed = 0;
+    for (int l = 0; l < n_links; ++l) {
+        auto &S = h->s_links[l];
+        const int64_t n = (int64_t)(link_off[l + 1] - link_off[l]);
+        if (n) S.sbuf.insert(S.sbuf.end(), iq + 2 * link_off[l], iq + 2 * link_off[l + 1]);
+        pushed += n;
+        if (n > newest) newest = n;
+        total += (int64_t)(S.sbuf.size() / 2);
+    }
+    h->s_unprocessed += newest;
+    int64_t have_all = 0;
+    for (auto &S : h->s_links) have_all += (int64_t)(S.sbuf.size() / 2) - S.hist;
+    if (have_all <= 0) return WIFI_OK;
+    if (total > h->cfg.max_samples) { h->err = "stream backlog exceeds max_samples"; return WIFI_E_OVERFLOW; }
+    // small pushes only buffer: the pipeline has a fixed cost of a millisecond or two per run (one trellis per
+    // thread), so it runs when enough new samples wait, when the workspace is half full, on an empty push, or on flush
+    if (!flush && pushed != 0 && h->s_unprocessed < h->s_batch && 2 * total < h->cfg.max_samples) return WIFI_OK;
+    h->s_unprocessed = 0;
+    int rc = ensure_iq_staging(h);
+    if (rc) return rc;
+    h->h_links.resize(n_links);
+    int64_t pos = 0;
+    for (int l = 0; l < n_links; ++l) {
+        auto &S = h->s_links[l];
+        const int64_t cnt = (int64_t)(S.sbuf.size() / 2);
+        if (cnt) CK(cudaMemcpyAsync(h->d_iq + pos, S.sbuf.data(), S.sbuf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        LinkDesc &L = h->h_links[l];
+        memset(&L, 0, sizeof L);
+        L.x_off = pos + S.hist;
+        L.len = cnt - S.hist;
+        L.is_final = flush ? 1 : 0;
+        L.hold_last = flush ? 0 : 1;     // the newest burst is held back unless flushing (k_frames_init)
+        L.hist = S.hist;
+        L.fo_carry = S.fo_carry;
+        L.min_pos = S.prev_trigger >= 0 ? S.prev_trigger + SS_MIN_GAP + 1 - S.abs0 : 0;
+        pos += cnt;
+    }
+    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
+    rc = run_rx(h, h->d_iq, true);
+    if (rc) return rc;
+    // Frames are ordered by (link, trigger): publish the CRC-ok ones and note from where each link must be kept:
+    // its held burst, or -- when decode_mac's state was left open in front of a held burst (a frame cut short by a
+    // re-trigger whose symbol collection, or pending tag, continues into that burst) -- the frame that opened it.
+    std::vector<int> open_at(n_links, -1);
+    if (!flush && h->n_frames > 0)
+        CK(cudaMemcpy(open_at.data(), h->d_link_dirty + MAX_LINKS, (size_t)n_links * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<char> has_held(n_links, 0);
+    for (int64_t i = 0; i < h->n_frames; ++i)
+        if (h->h_frames[i].n_syms < 0) has_held[h->h_frames[i].link] = 1;
+    std::vector<int64_t> keep(n_links, -1);
+    h->stats.samples += h->n_samples;             // samples this run looked at (a held burst is looked at again)
+    for (int64_t i = 0; i < h->n_frames; ++i) {
+        wifi_b200_frame f = h->h_frames[i];
+        auto &S = h->s_links[f.link];
+        if (keep[f.link] >= 0) continue;          // deferred together with the frame that opened the state
+        if (f.n_syms < 0 || (has_held[f.link] && open_at[f.link] >= 0 && i >= open_at[f.link])) {
+            keep[f.link] = f.trigger + S.abs0;    // held or deferred: re-detected and decoded by a later run
+            continue;
+        }
+        count_frame(h->stats, f);
+        S.prev_trigger = f.trigger + S.abs0;
+        S.fo_carry = f.freq_long;
+        if (!f.crc_ok) continue;
+        const uint8_t *p = h->h_psdu + f.psdu_off;
+        h->s_bytes.insert(h->s_bytes.end(), p, p + (f.length - 4));
+        f.trigger += S.abs0;
+        h->s_meta.push_back(f);
+    }
+    for (int l = 0; l < n_links; ++l) {
+        auto &S = h->s_links[l];
+        const int64_t have = (int64_t)(S.sbuf.size() / 2) - S.hist;
+        const int64_t buf_abs = S.abs0 - S.hist;   // absolute index of sbuf[0]
+        const int64_t end_abs = S.abs0 + have;
+        if (flush) {                               // stream ended: nothing is kept
+            S.sbuf.clear();
+            S.abs0 = (end_abs + FE_CHUNK - 1) / FE_CHUNK * FE_CHUNK;
+            S.hist = 0; S.prev_trigger = -1; S.fo_carry = 0.f;
+            continue;
+        }
+        const int64_t k = keep[l] >= 0 ? keep[l] : end_abs;
+        int64_t new_abs0 = (k - FE_CHUNK) / FE_CHUNK * FE_CHUNK;
+        if (new_abs0 < S.abs0) new_abs0 = S.abs0;
+        int64_t new_hist = new_abs0 - buf_abs;
+        if (new_hist > 256) new_hist = 256;
+        const int64_t drop = (new_abs0 - new_hist) - buf_abs;   // samples to erase from the front
+        if (drop > 0) S.sbuf.erase(S.sbuf.begin(), S.sbuf.begin() + 2 * drop);
+        S.abs0 = new_abs0;
+        S.hist = (int)new_hist;
+    }
     return WIFI_OK;
 }
 
@@ -950,66 +1041,19 @@ int wifi_b200_rx_push(wifi_b200_t *h, const float *iq, size_t n, int flush)
 {
     if (!h || (!iq && n)) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
-    cudaSetDevice(h->device);
-    if (n) h->sbuf.insert(h->sbuf.end(), iq, iq + 2 * n);
-    h->s_unprocessed += (int64_t)n;
-    const int64_t have = (int64_t)(h->sbuf.size() / 2) - h->s_hist;   // samples from s_abs0 on
-    if (have <= 0) return WIFI_OK;
-    if (have + h->s_hist > h->cfg.max_samples) { h->err = "stream backlog exceeds max_samples"; return WIFI_E_OVERFLOW; }
-    // small pushes only buffer: the pipeline has a fixed cost of a millisecond or two per run (one trellis per
-    // thread), so it runs when enough new samples wait, when the workspace is half full, on an empty push, or on flush
-    if (!flush && n != 0 && h->s_unprocessed < h->s_batch && 2 * (have + h->s_hist) < h->cfg.max_samples) return WIFI_OK;   // n == 0: run now
-    h->s_unprocessed = 0;
-    int rc = ensure_iq_staging(h);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_iq, h->sbuf.data(), h->sbuf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    h->h_links.resize(1);
-    LinkDesc &L = h->h_links[0];
-    memset(&L, 0, sizeof L);
-    L.x_off = h->s_hist;
-    L.len = have;
-    L.is_final = flush ? 1 : 0;
-    L.hist = h->s_hist;
-    L.fo_carry = h->s_fo_carry;
-    L.min_pos = h->s_prev_trigger >= 0 ? h->s_prev_trigger + SS_MIN_GAP + 1 - h->s_abs0 : 0;
-    // the newest burst is held back unless flushing: its end is not known before the next
-    // trigger arrives (sync_short retrigger / sync_long RESET decide its length)
-    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
-    rc = run_rx(h, h->d_iq, true, flush == 0);
-    if (rc) return rc;
-    update_stats(h);
-    const int64_t nf = h->n_frames;
-    for (int64_t i = 0; i < nf; ++i) {
-        wifi_b200_frame f = h->h_frames[i];
-        if (!f.crc_ok) continue;
-        const uint8_t *p = h->h_psdu + f.psdu_off;
-        h->s_bytes.insert(h->s_bytes.end(), p, p + (f.length - 4));
-        f.trigger += h->s_abs0;
-        h->s_meta.push_back(f);
-    }
-    if (nf > 0) {
-        h->s_prev_trigger = h->h_frames[nf - 1].trigger + h->s_abs0;
-        h->s_fo_carry = h->h_frames[nf - 1].freq_long;
-    }
-    const int64_t buf_abs = h->s_abs0 - h->s_hist;   // absolute index of sbuf[0]
-    const int64_t end_abs = h->s_abs0 + have;
-    int64_t new_abs0;
-    if (flush) {
-        new_abs0 = (end_abs + FE_CHUNK - 1) / FE_CHUNK * FE_CHUNK;   // stream ended: nothing is kept
-        h->sbuf.clear();
-        h->s_abs0 = new_abs0; h->s_hist = 0; h->s_prev_trigger = -1; h->s_fo_carry = 0.f;
-        return WIFI_OK;
-    }
-    int64_t keep = (h->n_triggers > nf) ? h->h_frames[nf].trigger + h->s_abs0 : end_abs;
-    new_abs0 = (keep - FE_CHUNK) / FE_CHUNK * FE_CHUNK;
-    if (new_abs0 < h->s_abs0) new_abs0 = h->s_abs0;
-    int64_t new_hist = new_abs0 - buf_abs;
-    if (new_hist > 256) new_hist = 256;
-    int64_t drop = (new_abs0 - new_hist) - buf_abs;   // samples to erase from the front
-    if (drop > 0) h->sbuf.erase(h->sbuf.begin(), h->sbuf.begin() + 2 * drop);
-    h->s_abs0 = new_abs0;
-    h->s_hist = (int)new_hist;
-    return WIFI_OK;
+    if (h->s_links.size() > 1) { h->err = "this handle streams several links: use wifi_b200_rx_push_links"; return WIFI_E_ARG; }
+    const uint64_t off[2] = {0, (uint64_t)n};
+    return stream_push(h, iq, off, 1, flush);
+}
+
+int wifi_b200_rx_push_links(wifi_b200_t *h, const float *iq, const uint64_t *link_off, int n_links, int flush)
+{
+    if (!h || !link_off || n_links <= 0) return WIFI_E_ARG;
+    for (int l = 0; l < n_links; ++l)
+        if (link_off[l + 1] < link_off[l]) return WIFI_E_ARG;
+    if (!iq && link_off[n_links] != link_off[0]) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    return stream_push(h, iq, link_off, n_links, flush);
 }
 
 int wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *psdu_buf, size_t psdu_cap, int *n_out)

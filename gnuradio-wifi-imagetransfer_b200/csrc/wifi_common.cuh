@@ -71,7 +71,7 @@ struct LinkDesc {
     float fo_carry;       // sync_long d_freq_offset entering this buffer
     int32_t is_final;
     int32_t hist;         // valid samples stored before x_off (streaming history); older samples read as 0
-    int32_t pad0;
+    int32_t hold_last;    // streaming: the newest burst is held back while a later trigger could still cut it short
     int64_t min_pos;      // first sample index sync_short may trigger on (previous trigger + MIN_GAP + 1)
     int64_t row_base;     // first equalizer row reserved for the link
 };

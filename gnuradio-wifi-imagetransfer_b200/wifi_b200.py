@@ -58,7 +58,7 @@ EXPORTS = [
     "wifi_b200_mac_frame", "wifi_b200_n_sym", "wifi_b200_frame_samples", "wifi_b200_tx", "wifi_b200_tx_dev",
     "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
-    "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
+    "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_rx_push_links", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
 ]
 
 _LIB = None
@@ -101,6 +101,7 @@ def lib():
         L.wifi_b200_rx_soft.argtypes = [vp, vp, i64]
         L.wifi_b200_rx_flags.argtypes = [vp, C.c_int, vp, i64]
         L.wifi_b200_rx_push.argtypes = [vp, vp, C.c_size_t, C.c_int]
+        L.wifi_b200_rx_push_links.argtypes = [vp, vp, vp, C.c_int, C.c_int]
         L.wifi_b200_rx_pop.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_int)]
         L.wifi_b200_rx_reset.argtypes = [vp]
         L.wifi_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -306,6 +307,14 @@ class Handle:
     def rx_push(self, iq, flush=False):
         a = np.ascontiguousarray(iq, np.complex64)
         self._ck(self._L.wifi_b200_rx_push(self._h, _p(a) if a.size else None, a.size, int(flush)))
+
+    def rx_push_links(self, chunks, flush=False):
+        """chunks: one array of new complex samples per stream (empty arrays allowed)."""
+        arrs = [np.ascontiguousarray(c, np.complex64).reshape(-1) for c in chunks]
+        off = np.zeros(len(arrs) + 1, np.uint64)
+        off[1:] = np.cumsum([a.size for a in arrs])
+        blob = np.concatenate(arrs) if arrs and off[-1] else np.zeros(0, np.complex64)
+        self._ck(self._L.wifi_b200_rx_push_links(self._h, _p(blob) if blob.size else None, _p(off), len(arrs), int(flush)))
 
     def rx_pop(self, cap=256):
         meta = np.zeros(cap, FRAME_DTYPE)

@@ -175,6 +175,11 @@ int  wifi_b200_rx_push(wifi_b200_t *h, const float *iq_host, size_t n, int flush
  * meta[i].psdu_off is the offset into psdu_buf, meta[i].length-4 the size; trigger is absolute */
 int  wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *psdu_buf, size_t psdu_cap, int *n_frames);
 int  wifi_b200_rx_reset(wifi_b200_t *h);
+/* The same for n_links continuous streams at once (many live channels on one GPU share one pipeline run): link l
+ * receives iq_host[link_off[l] .. link_off[l+1]) new complex samples (possibly none).  The number of links is fixed by
+ * the first push after create / rx_reset; popped frames carry their link in wifi_b200_frame.link and come out ordered
+ * by (run, link, trigger).  flush ends every stream. */
+int  wifi_b200_rx_push_links(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int flush);
 
 int  wifi_b200_get_stats(wifi_b200_t *h, wifi_b200_stats *out);
 /* device time (ms) of each pipeline stage in the last rx_batch call; names via wifi_b200_stage_name */

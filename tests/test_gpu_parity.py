@@ -669,3 +669,47 @@ def test_ota_runners_record_and_replay(O, W, fmt, tmp_path):
     assert got == [p[24:][4:] for p in ref.pdus()]                   # "Extract Pics" strips the MAC header and 4 more bytes
     assert set(got) <= {p[4:] for p in payloads}
     a.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(int(os.environ.get("WIFI_FUZZ_SEEDS", "4"))))
+def test_fuzz_multi_link_streaming(O, W, seed):
+    """wifi_b200_rx_push_links: several continuous streams in one handle, each fed its own random chunk sizes (some
+    pushes bring nothing for a link): per link, the published PDUs and absolute triggers equal that link's
+    whole-capture decode."""
+    rng = np.random.default_rng(7700 + seed)
+    n_links = int(rng.integers(2, 6))
+    algo = int(rng.integers(0, 4))
+    streams, want = [], []
+    for l in range(n_links):
+        parts = [np.zeros(int(rng.integers(0, 500)), np.complex64)]
+        for i in range(int(rng.integers(2, 7))):
+            enc = int(rng.integers(0, 8))
+            ln = int(rng.integers(20, 300 if enc < 2 else 1000))
+            parts.append(0.6 * O.tx_frame(make_psdu(O, rng, ln, seq=i), enc, seed=int(rng.integers(1, 128))))
+            parts.append(np.zeros(int(rng.choice([int(rng.integers(0, 300)), int(rng.integers(600, 4000)), int(rng.integers(44000, 50000))], p=[0.2, 0.6, 0.2])), np.complex64))
+        x = np.concatenate(parts).astype(np.complex64)
+        y = O.channel(x, gain=1.0, cfo=float(rng.uniform(-0.01, 0.01)), noise_sigma=0.6 * 10 ** (-float(rng.uniform(20, 32)) / 20), seed=10 * seed + l)
+        streams.append(y)
+        ref = O.rx(y, algo=algo)
+        want.append([(int(f["trigger"]), ref.psdu(i)[:-4]) for i, f in enumerate(ref.frames) if f["crc_ok"]])
+    h = W.Handle(max_samples=1 << 21, max_frames=512, chan_est=algo)
+    try:
+        h.set_param(W.wifi_b200.P_STREAM_BATCH, int(rng.choice([0, 8000, 60000])))
+        pos = [0] * n_links
+        got = [[] for _ in range(n_links)]
+        while any(pos[l] < streams[l].size for l in range(n_links)):
+            chunks = []
+            for l in range(n_links):
+                n = 0 if rng.random() < 0.2 else int(rng.choice([int(rng.integers(1, 800)), int(rng.integers(800, 30000))]))
+                chunks.append(streams[l][pos[l]:pos[l] + n])
+                pos[l] += len(chunks[-1])
+            done = all(pos[l] >= streams[l].size for l in range(n_links))
+            h.rx_push_links(chunks, flush=done)
+            for f, d in h.rx_pop():
+                got[int(f["link"])].append((int(f["trigger"]), d))
+        assert got == want
+        with pytest.raises(W.WifiB200Error):
+            h.rx_push(np.zeros(10, np.complex64))          # a multi-link stream is not fed through the one-link call
+    finally:
+        h.close()
