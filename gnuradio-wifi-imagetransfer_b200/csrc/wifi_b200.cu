@@ -203,13 +203,17 @@ struct wifi_b200 {
     wifi_b200_stats stats;
     // streaming: one state per link (wifi_b200_rx_push = one link, wifi_b200_rx_push_links = many)
     struct StreamLink {
-        std::vector<float> sbuf;   // pending samples (interleaved), sbuf[0] is absolute index abs0 - hist
-        int64_t abs0 = 0;          // absolute index of the first non-history sample in sbuf
+        int64_t fill = 0;          // samples in the link's region of the device arena: history + pending
+        int64_t abs0 = 0;          // absolute index of the first non-history sample of the region
         int hist = 0;
         int64_t prev_trigger = -1; // absolute
         float fo_carry = 0.f;
     };
     std::vector<StreamLink> s_links;
+    cf *d_stream = nullptr;        // streaming arena: one region of s_cap samples per link; samples go from the caller's buffer
+    int64_t s_cap = 0;             //   straight to the device and stay there until their burst is decoded
+    struct MoveSeg { int64_t src, dst, n; };
+    MoveSeg *d_moves = nullptr;    // tail compaction descriptors
     int64_t s_batch = 0;           // WIFI_P_STREAM_BATCH: a push only buffers until this many new samples per link wait (0: every push)
     int64_t s_unprocessed = 0;     // samples appended to the fullest link since the last pipeline run
     std::vector<wifi_b200_frame> s_meta;
@@ -249,7 +253,7 @@ int upload_tables(wifi_b200 *h)
 void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
+    void *ptrs[] = {h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
                     h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -300,6 +304,14 @@ __global__ void __launch_bounds__(256) k_sc16_to_fc32(const int16_t *__restrict_
             for (int64_t j = i; j < n && j < i + 4; ++j) out[j] = cf{(float)in[2 * j] * scale, (float)in[2 * j + 1] * scale};
         }
     }
+}
+
+// streaming: dst[m.dst + i] = src[m.src + i] for segment m = blockIdx.y; run twice (arena -> scratch -> arena) to slide
+// every link's retained tail to the front of its region (source and destination ranges of one link may overlap)
+__global__ void __launch_bounds__(256) k_move_segments(const cf *__restrict__ src, cf *__restrict__ dst, const wifi_b200::MoveSeg *__restrict__ segs)
+{
+    const wifi_b200::MoveSeg m = segs[blockIdx.y];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.n; i += (int64_t)gridDim.x * blockDim.x) dst[m.dst + i] = src[m.src + i];
 }
 
 void mark(wifi_b200 *h, int i)
@@ -933,57 +945,74 @@ int wifi_b200_rx_reset(wifi_b200_t *h)
     if (!h) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
     h->s_links.clear();
+    h->s_cap = 0;
     h->s_unprocessed = 0;
     h->s_meta.clear(); h->s_bytes.clear();
     return WIFI_OK;
 }
 
 // Streaming over n_links continuous streams: link l receives iq[link_off[l] .. link_off[l+1]) new samples.
+// Samples are copied once, from the caller's buffer into the link's region of a device arena (pinned caller memory
+// makes that a plain DMA), and stay on the device: a run decodes the regions in place, then every link's retained
+// tail (history + held / deferred bursts) slides to the front of its region.
 static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, int n_links, int flush)
 {
     if (n_links <= 0 || n_links > MAX_LINKS) return WIFI_E_ARG;
-    if (h->s_links.empty()) h->s_links.resize(n_links);
-    if ((int)h->s_links.size() != n_links) { h->err = "the number of streams is fixed until wifi_b200_rx_reset"; return WIFI_E_ARG; }
     cudaSetDevice(h->device);
-    int64_t total = 0, newest = 0, pushed = 0;
+    if (h->s_links.empty()) {
+        h->s_links.resize(n_links);
+        h->s_cap = h->cfg.max_samples / n_links;
+        if (!h->d_stream) CK(cudaMalloc(&h->d_stream, (size_t)(h->cfg.max_samples + 512) * sizeof(cf)));
+        if (!h->d_moves) CK(cudaMalloc(&h->d_moves, (size_t)2 * MAX_LINKS * sizeof(wifi_b200::MoveSeg)));
+    }
+    if ((int)h->s_links.size() != n_links) { h->err = "the number of streams is fixed until wifi_b200_rx_reset"; return WIFI_E_ARG; }
+    int64_t newest = 0, pushed = 0;
+    for (int l = 0; l < n_links; ++l) {
+        const int64_t n = (int64_t)(link_off[l + 1] - link_off[l]);
+        if (h->s_links[l].fill + n > h->s_cap) { h->err = "stream backlog exceeds max_samples / n_links"; return WIFI_E_OVERFLOW; }
+        if (n > newest) newest = n;
+        pushed += n;
+    }
+    int64_t have_all = 0, total = 0, fullest = 0;
     for (int l = 0; l < n_links; ++l) {
         auto &S = h->s_links[l];
         const int64_t n = (int64_t)(link_off[l + 1] - link_off[l]);
-        if (n) S.sbuf.insert(S.sbuf.end(), iq + 2 * link_off[l], iq + 2 * link_off[l + 1]);
-        pushed += n;
-        if (n > newest) newest = n;
-        total += (int64_t)(S.sbuf.size() / 2);
+        if (n) CK(cudaMemcpyAsync(h->d_stream + (int64_t)l * h->s_cap + S.fill, iq + 2 * link_off[l], (size_t)n * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
+        S.fill += n;
+        have_all += S.fill - S.hist;
+        total += S.fill;
+        if (S.fill > fullest) fullest = S.fill;
     }
     h->s_unprocessed += newest;
-    int64_t have_all = 0;
-    for (auto &S : h->s_links) have_all += (int64_t)(S.sbuf.size() / 2) - S.hist;
-    if (have_all <= 0) return WIFI_OK;
-    if (total > h->cfg.max_samples) { h->err = "stream backlog exceeds max_samples"; return WIFI_E_OVERFLOW; }
     // small pushes only buffer: the pipeline has a fixed cost of a millisecond or two per run (one trellis per
-    // thread), so it runs when enough new samples wait, when the workspace is half full, on an empty push, or on flush
-    if (!flush && pushed != 0 && h->s_unprocessed < h->s_batch && 2 * total < h->cfg.max_samples) return WIFI_OK;
+    // thread), so it runs when enough new samples wait, when a region is half full, on an empty push, or on flush
+    if (have_all <= 0 || (!flush && pushed != 0 && h->s_unprocessed < h->s_batch && 2 * fullest < h->s_cap)) {
+        if (pushed) {
+            // The caller's buffer must be free again when the call returns.  A copy from pageable memory has left the
+            // source when cudaMemcpyAsync returns (it is staged); only page-locked sources are read asynchronously.
+            cudaPointerAttributes at;
+            const bool pinned = cudaPointerGetAttributes(&at, iq) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+            cudaGetLastError();
+            if (pinned) CK(cudaStreamSynchronize(h->stream));
+        }
+        return WIFI_OK;
+    }
     h->s_unprocessed = 0;
-    int rc = ensure_iq_staging(h);
-    if (rc) return rc;
     h->h_links.resize(n_links);
-    int64_t pos = 0;
     for (int l = 0; l < n_links; ++l) {
         auto &S = h->s_links[l];
-        const int64_t cnt = (int64_t)(S.sbuf.size() / 2);
-        if (cnt) CK(cudaMemcpyAsync(h->d_iq + pos, S.sbuf.data(), S.sbuf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         LinkDesc &L = h->h_links[l];
         memset(&L, 0, sizeof L);
-        L.x_off = pos + S.hist;
-        L.len = cnt - S.hist;
+        L.x_off = (int64_t)l * h->s_cap + S.hist;
+        L.len = S.fill - S.hist;
         L.is_final = flush ? 1 : 0;
         L.hold_last = flush ? 0 : 1;     // the newest burst is held back unless flushing (k_frames_init)
         L.hist = S.hist;
         L.fo_carry = S.fo_carry;
         L.min_pos = S.prev_trigger >= 0 ? S.prev_trigger + SS_MIN_GAP + 1 - S.abs0 : 0;
-        pos += cnt;
     }
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
-    rc = run_rx(h, h->d_iq, true);
+    int rc = run_rx(h, h->d_stream, true);
     if (rc) return rc;
     // Frames are ordered by (link, trigger): publish the CRC-ok ones and note from where each link must be kept:
     // its held burst, or -- when decode_mac's state was left open in front of a held burst (a frame cut short by a
@@ -1013,13 +1042,16 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
         f.trigger += S.abs0;
         h->s_meta.push_back(f);
     }
+    std::vector<wifi_b200::MoveSeg> moves;         // [0, nm): arena -> scratch, [nm, 2 nm): scratch -> front of the region
+    std::vector<wifi_b200::MoveSeg> back;
+    int64_t scratch = 0, longest = 0;
     for (int l = 0; l < n_links; ++l) {
         auto &S = h->s_links[l];
-        const int64_t have = (int64_t)(S.sbuf.size() / 2) - S.hist;
-        const int64_t buf_abs = S.abs0 - S.hist;   // absolute index of sbuf[0]
+        const int64_t have = S.fill - S.hist;
+        const int64_t buf_abs = S.abs0 - S.hist;   // absolute index of the region's first sample
         const int64_t end_abs = S.abs0 + have;
         if (flush) {                               // stream ended: nothing is kept
-            S.sbuf.clear();
+            S.fill = 0;
             S.abs0 = (end_abs + FE_CHUNK - 1) / FE_CHUNK * FE_CHUNK;
             S.hist = 0; S.prev_trigger = -1; S.fo_carry = 0.f;
             continue;
@@ -1029,10 +1061,33 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
         if (new_abs0 < S.abs0) new_abs0 = S.abs0;
         int64_t new_hist = new_abs0 - buf_abs;
         if (new_hist > 256) new_hist = 256;
-        const int64_t drop = (new_abs0 - new_hist) - buf_abs;   // samples to erase from the front
-        if (drop > 0) S.sbuf.erase(S.sbuf.begin(), S.sbuf.begin() + 2 * drop);
+        const int64_t drop = (new_abs0 - new_hist) - buf_abs;   // samples to discard from the front of the region
+        if (drop > 0) {
+            const int64_t tail = S.fill - drop;
+            if (tail > 0) {
+                moves.push_back({(int64_t)l * h->s_cap + drop, scratch, tail});
+                back.push_back({scratch, (int64_t)l * h->s_cap, tail});
+                scratch += tail;
+                if (tail > longest) longest = tail;
+            }
+            S.fill = tail;
+        }
         S.abs0 = new_abs0;
         S.hist = (int)new_hist;
+    }
+    if (!moves.empty()) {
+        rc = ensure_iq_staging(h);                 // the batch staging buffer is the scratch space
+        if (rc) return rc;
+        const int nm = (int)moves.size();
+        moves.insert(moves.end(), back.begin(), back.end());
+        unsigned bx = (unsigned)((longest + 2047) / 2048);
+        if (bx > 64) bx = 64;
+        if (bx < 1) bx = 1;
+        CK(cudaMemcpyAsync(h->d_moves, moves.data(), moves.size() * sizeof(wifi_b200::MoveSeg), cudaMemcpyHostToDevice, h->stream));
+        k_move_segments<<<dim3(bx, nm), 256, 0, h->stream>>>(h->d_stream, h->d_iq, h->d_moves);
+        k_move_segments<<<dim3(bx, nm), 256, 0, h->stream>>>(h->d_iq, h->d_stream, h->d_moves + nm);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
     }
     return WIFI_OK;
 }

@@ -316,6 +316,13 @@ class Handle:
         blob = np.concatenate(arrs) if arrs and off[-1] else np.zeros(0, np.complex64)
         self._ck(self._L.wifi_b200_rx_push_links(self._h, _p(blob) if blob.size else None, _p(off), len(arrs), int(flush)))
 
+    def rx_push_links_blob(self, blob, link_off, flush=False):
+        """Zero-copy form: `blob` holds every link's new samples back to back (complex64, ideally pinned memory),
+        link l = blob[link_off[l]:link_off[l+1]]."""
+        a = blob if (isinstance(blob, np.ndarray) and blob.dtype == np.complex64 and blob.flags.c_contiguous) else np.ascontiguousarray(blob, np.complex64)
+        off = np.ascontiguousarray(link_off, np.uint64)
+        self._ck(self._L.wifi_b200_rx_push_links(self._h, _p(a) if a.size else None, _p(off), off.size - 1, int(flush)))
+
     def rx_pop(self, cap=256):
         meta = np.zeros(cap, FRAME_DTYPE)
         buf = np.zeros(cap * 1528, np.uint8)
@@ -326,6 +333,18 @@ class Handle:
             f = meta[i]
             out.append((f.copy(), buf[f["psdu_off"]:f["psdu_off"] + f["length"] - 4].tobytes()))
         return out
+
+    def rx_pop_arrays(self, cap=4096):
+        """Bulk form of rx_pop for many live links: (frame records, PSDU bytes back to back); record i's PSDU is
+        blob[rec["psdu_off"] : rec["psdu_off"] + rec["length"] - 4].  No per-frame Python objects."""
+        if getattr(self, "_pop_meta", None) is None or self._pop_meta.size < cap:
+            self._pop_meta = np.zeros(cap, FRAME_DTYPE)
+            self._pop_buf = np.zeros(cap * 1528, np.uint8)
+        n = C.c_int()
+        self._ck(self._L.wifi_b200_rx_pop(self._h, _p(self._pop_meta), cap, _p(self._pop_buf), self._pop_buf.size, C.byref(n)))
+        k = n.value
+        used = int(self._pop_meta["psdu_off"][k - 1] + self._pop_meta["length"][k - 1] - 4) if k else 0
+        return self._pop_meta[:k].copy(), self._pop_buf[:used].copy()
 
     def rx_reset(self):
         self._ck(self._L.wifi_b200_rx_reset(self._h))

@@ -706,8 +706,13 @@ def test_fuzz_multi_link_streaming(O, W, seed):
                 pos[l] += len(chunks[-1])
             done = all(pos[l] >= streams[l].size for l in range(n_links))
             h.rx_push_links(chunks, flush=done)
-            for f, d in h.rx_pop():
-                got[int(f["link"])].append((int(f["trigger"]), d))
+            if seed & 1:                                     # bulk pop: records + one blob
+                meta, blob = h.rx_pop_arrays()
+                for f in meta:
+                    got[int(f["link"])].append((int(f["trigger"]), blob[f["psdu_off"]:f["psdu_off"] + f["length"] - 4].tobytes()))
+            else:
+                for f, d in h.rx_pop():
+                    got[int(f["link"])].append((int(f["trigger"]), d))
         assert got == want
         with pytest.raises(W.WifiB200Error):
             h.rx_push(np.zeros(10, np.complex64))          # a multi-link stream is not fed through the one-link call
