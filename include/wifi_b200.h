@@ -178,7 +178,9 @@ int  wifi_b200_rx_reset(wifi_b200_t *h);
 /* The same for n_links continuous streams at once (many live channels on one GPU share one pipeline run): link l
  * receives iq_host[link_off[l] .. link_off[l+1]) new complex samples (possibly none).  The number of links is fixed by
  * the first push after create / rx_reset; popped frames carry their link in wifi_b200_frame.link and come out ordered
- * by (run, link, trigger).  flush ends every stream. */
+ * by (run, link, trigger).  flush ends every stream.  Every link owns max_samples / n_links samples of a device
+ * arena: size max_samples >= n_links * (largest push or stream batch + 2 * 43200 + 512) so that a held burst, a
+ * deferred one in front of it and the next push fit (WIFI_E_OVERFLOW otherwise; nothing is dropped silently). */
 int  wifi_b200_rx_push_links(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int flush);
 
 int  wifi_b200_get_stats(wifi_b200_t *h, wifi_b200_stats *out);
