@@ -411,6 +411,36 @@ def main():
         mode["sc16"] = None
         for x_ in hs:
             x_.close()
+        # live form: every link of the capture as a continuous stream, pushed chunk by chunk into ONE handle
+        # (wifi_b200_rx_push_links, pinned input, bulk pop) -- what many SDR front-ends feeding one GPU look like
+        try:
+            chunk, pushes = 262144, 6
+            link_len = int(link_off[1] - link_off[0])
+            if link_len >= chunk * pushes and world >= 1:
+                hl = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=n_links * (chunk + 131072) + 1024,
+                              max_frames=n_links * (chunk // 4096 + 16), soft_decision=args.soft)
+                pin = torch.empty(2 * n_links * chunk, dtype=torch.float32, pin_memory=True)
+                blob = pin.numpy().view(np.complex64)
+                off = (np.arange(n_links + 1) * chunk).astype(np.uint64)
+                hv = hn.reshape(n_links, link_len)
+                t_lib, n_pdu = 0.0, 0
+                for k in range(pushes):
+                    blob.reshape(n_links, chunk)[:] = hv[:, k * chunk:(k + 1) * chunk]      # the radios filling their buffers: not timed
+                    t0 = time.perf_counter()
+                    hl.rx_push_links_blob(blob, off, flush=(k == pushes - 1))
+                    while True:
+                        meta, _pd = hl.rx_pop_arrays(cap=8192)
+                        if not len(meta):
+                            break
+                        n_pdu += len(meta)
+                    t_lib += time.perf_counter() - t0
+                e2e["streaming"] = {"value": n_links * chunk * pushes / t_lib / 1e6, "unit": "Msamples/s", "links": n_links, "samples_per_push_per_link": chunk,
+                                    "pushes": pushes, "pdus": n_pdu, "realtime_factor_per_20Msps_link": chunk * pushes / t_lib / 20e6,
+                                    "how": "wifi_b200_rx_push_links + rx_pop per push, pinned host chunks, one handle, per-rank figure"}
+                hl.close()
+                del pin
+        except Exception as ex:
+            e2e["streaming"] = {"error": repr(ex)}
         del host
 
     if rank != 0:
