@@ -1210,6 +1210,102 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     frames[J.frame].crc_ok = sink.crc_ok();
 }
 
+// ------------------------------------------------------------------ R6a-c, low-latency form for small batches
+// One trellis per WARP: lane l owns states l and l + 32 -- exactly the two inputs of butterfly l -- and the survivors
+// 2l, 2l + 1 travel to their new owners by shuffle (state n lives in lane n % 32).  Per-frame latency is a third of the
+// one-trellis-per-thread kernel's (whose decode of a 1528-byte frame takes ~1.4 ms however idle the GPU is), at six
+// times the instructions per decoded bit: it serves the streaming path, where a run holds a handful of frames.
+// Same decoder: agreement metrics (kept as plain ints: only differences matter, so no renormalisation), tie -> the
+// predecessor k + 32, one path byte per state and chunk, traceback over ntb snapshots from the first best state.
+#define VW_WARPS 4
+__global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *__restrict__ jobs, int n_frames, const uint32_t *__restrict__ vit_in,
+                                                               uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
+{
+    __shared__ uint8_t s_ring[VW_WARPS][VIT_NTB_MAX][64];
+    __shared__ uint32_t s_crc[256];
+    __shared__ uint16_t s_scr[128];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = c_tab.crc_tab[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_scr[i] = c_tab.scr_tab[i];
+    __syncthreads();
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int job = blockIdx.x * VW_WARPS + wib;
+    if (job >= n_frames) return;
+    const JobDesc J = jobs[job];
+    if (J.n_sym == 0) return;
+    const int punct = c_tab.mcs[J.enc].punct;
+    const int ntb = punct == 0 ? 5 : (punct == 1 ? 9 : 10);
+    const int nw = (J.n_sym * c_tab.mcs[J.enc].n_dbps + 7) >> 3;
+    const uint32_t *in = vit_in + (int64_t)job * VIT_MAXW;
+    const int L = J.len;
+    const int last_chunk = L + 1 + ntb;
+    uint8_t (*ring)[64] = s_ring[wib];
+    // this lane's butterfly: expected symbols on the branch from state `lane` to state 2 * lane
+    const uint32_t A = vit_par((2u * lane) & 0x6du), B = vit_par((2u * lane) & 0x4fu);
+    const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
+    const bool odd = lane & 1;
+    uint32_t mlo = 0, mhi = 0, plo = 0, phi = 0;
+    auto step = [&](uint32_t nib, uint32_t bit) {
+        const uint32_t s0 = nib & 3u, s1 = (nib >> 2) & 3u;
+        const uint32_t e0 = s0 != 2u, e1 = s1 != 2u;
+        const uint32_t svm = (e0 & (s0 ^ A)) + (e1 & (s1 ^ B));      // disagreements with (A, B); erasures count for nothing
+        const uint32_t sv = e0 + e1 - svm;                            // agreements
+        const uint32_t m0 = mlo + sv, m1 = mhi + svm, m2 = mlo + svm, m3 = mhi + sv;
+        const bool k0 = m0 > m1, k1 = m2 > m3;                        // tie -> the predecessor k + 32
+        const uint32_t pb = phi | bit;
+        const uint32_t w0 = ((k0 ? m0 : m1) << 8) | (k0 ? plo : pb);
+        const uint32_t w1 = ((k1 ? m2 : m3) << 8) | (k1 ? plo : pb);
+        const uint32_t a0 = __shfl_sync(0xffffffffu, w0, src_lo), a1 = __shfl_sync(0xffffffffu, w1, src_lo);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, w0, src_hi), b1 = __shfl_sync(0xffffffffu, w1, src_hi);
+        const uint32_t nlo = odd ? a1 : a0, nhi = odd ? b1 : b0;
+        mlo = nlo >> 8; plo = nlo & 0xffu;
+        mhi = nhi >> 8; phi = nhi & 0xffu;
+    };
+    // snapshot of the path bytes into ring slot `slot`, first best state (largest metric, smallest state)
+    auto snapshot_best = [&](int slot) {
+        ring[slot][lane] = (uint8_t)plo;
+        ring[slot][lane + 32] = (uint8_t)phi;
+        uint32_t key = max((mlo << 6) | (uint32_t)(63 - lane), (mhi << 6) | (uint32_t)(31 - lane));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+        plo = phi = 0;
+        __syncwarp();
+        return 63 - (int)(key & 63u);
+    };
+    uint32_t w = in[0];
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) step((w >> (4 * k)) & 0xfu, 1u << (5 - k));
+    int slot = 1 % ntb;
+    int bs = snapshot_best(slot), sl = slot;          // the first chunk's traceback result is discarded
+    PsduSink sink;
+    sink.init(psdu + (int64_t)job * (PSDU_STRIDE / 4), L, s_crc, s_scr);
+    uint32_t next = 1 < nw ? in[1] : 0u;
+#pragma unroll 1
+    for (int chunk = 1; chunk <= last_chunk; ++chunk) {
+        const uint32_t bits = __funnelshift_r(w, next, 24);
+        w = next;
+        next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
+        // the traceback of the previous chunk (ntb - 1 dependent reads) rides along with this chunk's eight steps
+        int left = ntb - 1;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (left > 0) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; --left; }
+            step((bits >> (4 * s)) & 0xfu, 0x80u >> s);
+        }
+        while (left > 0) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; --left; }
+        const uint32_t byte = ring[sl][bs];
+        if (lane == 0 && chunk - 1 >= ntb && chunk > 1) sink.push(byte, chunk - 1 - ntb);
+        __syncwarp();                                  // every lane has read the slot the next snapshot overwrites
+        slot = (slot + 1 == ntb) ? 0 : slot + 1;
+        bs = snapshot_best(slot);
+        sl = slot;
+    }
+    if (last_chunk >= ntb) {
+        for (int i = 0; i < ntb - 1; ++i) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; }
+        if (lane == 0) sink.push(ring[sl][bs], last_chunk - ntb);
+    }
+    if (lane == 0) frames[J.frame].crc_ok = sink.crc_ok();
+}
+
 // ------------------------------------------------------------------ soft-decision variants
 // trellis words for gathered jobs in soft mode: word = 2 steps x 2 int8 soft symbols, erasure = 0
 __global__ void __launch_bounds__(256) k_pack_soft(const JobDesc *__restrict__ jobs, const int *__restrict__ pack_list, const int *__restrict__ n_pack,

@@ -144,6 +144,9 @@ enum { ST_H2D = 0, ST_DETECT, ST_SELECT, ST_SYNC_LONG, ST_DEMOD_HEAD, ST_SIGNAL,
 const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "demod_head", "signal", "demod_data", "plan", "pack", "viterbi", "d2h"};
 
 #define MAX_LINKS 16384
+#ifndef VW_SWITCH
+#define VW_SWITCH 1184          // frames per call up to which the warp-per-frame Viterbi is used (148 SMs x 8 warps)
+#endif
 #define DET_SMEM (DET_ROWS * 65 * (int)sizeof(cf))
 
 } // namespace
@@ -404,7 +407,9 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
         if (!soft) {
             k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in);
             mark(h, ST_VITERBI);
-            k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
+            // a handful of frames (streaming runs): one trellis per warp, a third of the latency; else one per thread
+            if (nf <= VW_SWITCH) k_viterbi_warp<<<(unsigned)((nf + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
+            else k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
         } else {
             k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in);
             mark(h, ST_VITERBI);
