@@ -718,3 +718,44 @@ def test_fuzz_multi_link_streaming(O, W, seed):
             h.rx_push(np.zeros(10, np.complex64))          # a multi-link stream is not fed through the one-link call
     finally:
         h.close()
+
+
+@pytest.mark.gpu
+def test_library_matches_the_committed_digests(O, W):
+    """The CUDA library against tests/golden/oracle_regression.json directly: TX IQ of every MCS, and for the golden
+    capture the frame table, decisions, equalised points and PSDUs under every equalizer, hard and soft."""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_regression.json")))
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    rng = np.random.default_rng(2024)
+    h = W.Handle(max_samples=1 << 20, max_frames=256, want_carrier=True)
+    try:
+        for enc in range(8):
+            psdu = make_psdu(O, rng, 100 + 150 * enc, seq=enc)
+            iq, _ = h.tx([psdu], enc=enc, seed=[17 + enc])
+            assert sha(iq) == gold["tx"][str(enc)]["iq_sha256"], enc
+        specs = [(e, 60 + 90 * e) for e in range(8)] + [(7, 1528), (3, 296)]
+        taps = ((0, 1.0), (1, 0.4 * np.exp(1j * 1.0)), (3, 0.2 * np.exp(-2j)))
+        y, _ = make_capture(O, np.random.default_rng(7), specs, snr_db=24, cfo=0.009, taps=taps, seed=5, gap=900)
+        assert sha(y) == gold["capture_sha256"]
+        for algo in range(4):
+            for soft in (False, True):
+                h.set_param(W.wifi_b200.P_CHAN_EST, algo)
+                h.set_param(W.wifi_b200.P_SOFT_DECISION, int(soft))
+                res = h.rx_batch(y)
+                g = gold["rx"]["algo%d_%s" % (algo, "soft" if soft else "hard")]
+                f = res.frames
+                for k, name in (("trigger", "triggers"), ("frame_start", "frame_start"), ("encoding", "encoding"), ("length", "length"), ("crc_ok", "crc_ok")):
+                    assert [int(v) for v in f[k]] == g[name], (algo, soft, k)
+                assert sha(np.stack([f["freq_short"], f["freq_long"]])) == g["freq_sha256"]
+                rows, car = h.rows(carrier=True)
+                # the library reserves row ranges per frame; the oracle's rows are the used ones back to back
+                used = np.concatenate([np.arange(int(r["row_off"]), int(r["row_off"]) + int(r["n_rows"])) for r in f]) if len(f) else np.zeros(0, int)
+                assert sha(rows[used]) == g["rows_sha256"] and sha(car[used]) == g["carrier_sha256"], (algo, soft)
+                assert hashlib.sha256(b"".join(res.pdus())).hexdigest() == g["pdus_sha256"]
+    finally:
+        h.close()

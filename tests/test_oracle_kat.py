@@ -184,3 +184,24 @@ def test_annex_g_message_fcs_geometry_and_loopback(O):
     assert r.pdus() == [psdu[:-4]]
     f = r.frames[np.nonzero(r.frames["crc_ok"])[0][0]]
     assert (int(f["encoding"]), int(f["length"]), int(f["frame_symbols"])) == (5, 100, 6)
+
+
+def test_oracle_matches_its_committed_digests(O):
+    """The oracle defines parity for the CUDA library: its outputs for fixed seeds are pinned by digests
+    (tests/golden/oracle_regression.json, regenerated only by tests/golden/make_oracle_regression.py), so a change of
+    the numerical contract cannot slip in unnoticed between rounds."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_regression", os.path.join(here, "golden", "make_oracle_regression.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "golden", "oracle_regression.json")))
+    got = mod.build()
+    assert got["tx"] == want["tx"]
+    assert got["capture_sha256"] == want["capture_sha256"]
+    assert set(got["rx"]) == set(want["rx"])
+    for k in want["rx"]:
+        assert got["rx"][k] == want["rx"][k], k
+    assert sum(want["rx"]["algo0_hard"]["crc_ok"]) >= 8
