@@ -759,3 +759,34 @@ def test_library_matches_the_committed_digests(O, W):
                 assert hashlib.sha256(b"".join(res.pdus())).hexdigest() == g["pdus_sha256"]
     finally:
         h.close()
+
+
+@pytest.mark.gpu
+def test_maximum_and_minimum_frame_sizes(O, W):
+    """The limits of [UPSTREAM] utils.h: MAX_PSDU_SIZE 1528 at BPSK 1/2 is MAX_SYM 511 symbols (41281 samples, the longest
+    PPDU: its burst fills sync_short's 43200-sample COPY almost completely); BPSK 3/4 goes through k_pack (36 data bits
+    per symbol do not fill whole trellis words); the shortest PSDUs (an FCS alone: 4 bytes, and 5 bytes).  Batch and streaming."""
+    rng = np.random.default_rng(123)
+    specs = [(0, 1528), (1, 1528), (0, 1), (5, 2), (7, 5), (6, 1528)]
+    y, psdus = make_capture(O, rng, specs, snr_db=26, cfo=0.005, seed=2, gap=1500)
+    assert O.n_sym(0, 1528) == 511
+    ref = O.rx(y, algo=0)
+    h = W.Handle(max_samples=1 << 18, max_frames=64, want_carrier=True)
+    try:
+        res = h.rx_batch(y)
+        assert_frames_equal(res, ref)
+        assert res.pdus() == ref.pdus()
+        ok = {int(f["length"]) for f in res.frames if f["crc_ok"]}
+        assert {1528, 4, 5} <= ok
+        assert int(res.frames["frame_symbols"].max()) == 511 and int(res.frames["burst_len"].max()) >= 41281
+        want = [(int(f["trigger"]), ref.psdu(i)[:-4]) for i, f in enumerate(ref.frames) if f["crc_ok"]]
+        got = []
+        for pos in range(0, y.size, 30000):
+            h.rx_push(y[pos:pos + 30000], flush=(pos + 30000 >= y.size))
+            got += h.rx_pop()
+        assert [(int(f["trigger"]), d) for f, d in got] == want
+        # one byte more than the mapper accepts
+        with pytest.raises(W.WifiB200Error):
+            h.tx([bytes(1529)], enc=0)
+    finally:
+        h.close()
