@@ -1243,31 +1243,32 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
     const uint32_t A = vit_par((2u * lane) & 0x6du), B = vit_par((2u * lane) & 0x4fu);
     const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
     const bool odd = lane & 1;
-    uint32_t mlo = 0, mhi = 0, plo = 0, phi = 0;
+    // A survivor is one word: (metric << 9) | path byte, bit 8 free.  The candidate that comes from state k + 32
+    // carries bit 8 (and the step's decision bit in its path byte), so ONE unsigned maximum performs compare, tie rule
+    // (equal metrics: the k + 32 candidate is larger) and the selection of metric and path together.
+    uint32_t wlo = 0, whi = 0;
     auto step = [&](uint32_t nib, uint32_t bit) {
         const uint32_t s0 = nib & 3u, s1 = (nib >> 2) & 3u;
         const uint32_t e0 = s0 != 2u, e1 = s1 != 2u;
         const uint32_t svm = (e0 & (s0 ^ A)) + (e1 & (s1 ^ B));      // disagreements with (A, B); erasures count for nothing
         const uint32_t sv = e0 + e1 - svm;                            // agreements
-        const uint32_t m0 = mlo + sv, m1 = mhi + svm, m2 = mlo + svm, m3 = mhi + sv;
-        const bool k0 = m0 > m1, k1 = m2 > m3;                        // tie -> the predecessor k + 32
-        const uint32_t pb = phi | bit;
-        const uint32_t w0 = ((k0 ? m0 : m1) << 8) | (k0 ? plo : pb);
-        const uint32_t w1 = ((k1 ? m2 : m3) << 8) | (k1 ? plo : pb);
-        const uint32_t a0 = __shfl_sync(0xffffffffu, w0, src_lo), a1 = __shfl_sync(0xffffffffu, w1, src_lo);
-        const uint32_t b0 = __shfl_sync(0xffffffffu, w0, src_hi), b1 = __shfl_sync(0xffffffffu, w1, src_hi);
-        const uint32_t nlo = odd ? a1 : a0, nhi = odd ? b1 : b0;
-        mlo = nlo >> 8; plo = nlo & 0xffu;
-        mhi = nhi >> 8; phi = nhi & 0xffu;
+        const uint32_t hb = 0x100u | bit;
+        const uint32_t v0 = max(wlo + (sv << 9), whi + (svm << 9) + hb);     // new state 2 * lane
+        const uint32_t v1 = max(wlo + (svm << 9), whi + (sv << 9) + hb);     // new state 2 * lane + 1
+        const uint32_t a0 = __shfl_sync(0xffffffffu, v0, src_lo), a1 = __shfl_sync(0xffffffffu, v1, src_lo);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, v0, src_hi), b1 = __shfl_sync(0xffffffffu, v1, src_hi);
+        wlo = (odd ? a1 : a0) & ~0x100u;
+        whi = (odd ? b1 : b0) & ~0x100u;
     };
     // snapshot of the path bytes into ring slot `slot`, first best state (largest metric, smallest state)
     auto snapshot_best = [&](int slot) {
-        ring[slot][lane] = (uint8_t)plo;
-        ring[slot][lane + 32] = (uint8_t)phi;
-        uint32_t key = max((mlo << 6) | (uint32_t)(63 - lane), (mhi << 6) | (uint32_t)(31 - lane));
+        ring[slot][lane] = (uint8_t)wlo;
+        ring[slot][lane + 32] = (uint8_t)whi;
+        uint32_t key = max(((wlo >> 9) << 6) | (uint32_t)(63 - lane), ((whi >> 9) << 6) | (uint32_t)(31 - lane));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
-        plo = phi = 0;
+        wlo &= ~0xffu;
+        whi &= ~0xffu;
         __syncwarp();
         return 63 - (int)(key & 63u);
     };
@@ -1278,6 +1279,7 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
     int bs = snapshot_best(slot), sl = slot;          // the first chunk's traceback result is discarded
     PsduSink sink;
     sink.init(psdu + (int64_t)job * (PSDU_STRIDE / 4), L, s_crc, s_scr);
+    sink.writer = lane == 0;                          // every lane runs the sink (no divergence), lane 0 stores
     uint32_t next = 1 < nw ? in[1] : 0u;
 #pragma unroll 1
     for (int chunk = 1; chunk <= last_chunk; ++chunk) {
@@ -1285,6 +1287,8 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
         w = next;
         next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
         // the traceback of the previous chunk (ntb - 1 dependent reads) rides along with this chunk's eight steps
+        // (measured: spreading it over two chunks with a deeper ring does not help -- ptxas clusters the dependent
+        // reads whatever the source order, and a warp issues in order)
         int left = ntb - 1;
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
@@ -1292,8 +1296,7 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
             step((bits >> (4 * s)) & 0xfu, 0x80u >> s);
         }
         while (left > 0) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; --left; }
-        const uint32_t byte = ring[sl][bs];
-        if (lane == 0 && chunk - 1 >= ntb && chunk > 1) sink.push(byte, chunk - 1 - ntb);
+        if (chunk - 1 >= ntb) sink.push(ring[sl][bs], chunk - 1 - ntb);
         __syncwarp();                                  // every lane has read the slot the next snapshot overwrites
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
         bs = snapshot_best(slot);
@@ -1301,7 +1304,7 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
     }
     if (last_chunk >= ntb) {
         for (int i = 0; i < ntb - 1; ++i) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; }
-        if (lane == 0) sink.push(ring[sl][bs], last_chunk - ntb);
+        sink.push(ring[sl][bs], last_chunk - ntb);
     }
     if (lane == 0) frames[J.frame].crc_ok = sink.crc_ok();
 }

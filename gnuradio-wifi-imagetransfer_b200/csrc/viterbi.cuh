@@ -308,6 +308,7 @@ struct VitCore {
 // (MSB = earliest bit) of decoded byte index m.
 struct PsduSink {
     uint32_t state, crc, accw;
+    bool writer = true;            // warp-per-frame decoder: every lane runs the sink, one stores
     uint32_t *out;
     int L;
     const uint32_t *s_crc;
@@ -332,7 +333,7 @@ struct PsduSink {
         if (pidx >= 0) {
             crc = s_crc[(crc ^ byte) & 0xffu] ^ (crc >> 8);
             accw |= byte << (8 * (pidx & 3));
-            if ((pidx & 3) == 3 || pidx == L - 1) { out[pidx >> 2] = accw; accw = 0; }
+            if ((pidx & 3) == 3 || pidx == L - 1) { if (writer) out[pidx >> 2] = accw; accw = 0; }
         }
     }
     __device__ __forceinline__ int crc_ok() const { return ((crc ^ 0xffffffffu) == 558161692u) ? 1 : 0; }
