@@ -1212,16 +1212,21 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
 
 // ------------------------------------------------------------------ R6a-c, low-latency form for small batches
 // One trellis per WARP: lane l owns states l and l + 32 -- exactly the two inputs of butterfly l -- and the survivors
-// 2l, 2l + 1 travel to their new owners by shuffle (state n lives in lane n % 32).  Per-frame latency is a third of the
-// one-trellis-per-thread kernel's (whose decode of a 1528-byte frame takes ~1.4 ms however idle the GPU is), at six
-// times the instructions per decoded bit: it serves the streaming path, where a run holds a handful of frames.
+// 2l, 2l + 1 travel to their new owners by shuffle (state n lives in lane n % 32).  Per-frame latency is a fraction of
+// the one-trellis-per-thread kernel's (whose decode of a 1528-byte frame takes ~1.4 ms however idle the GPU is), at
+// several times the instructions per decoded bit: it serves the streaming path, where a run holds a handful of frames.
 // Same decoder: agreement metrics (kept as plain ints: only differences matter, so no renormalisation), tie -> the
 // predecessor k + 32, one path byte per state and chunk, traceback over ntb snapshots from the first best state.
+// The tracebacks are DEFERRED and run 32 at a time, one chunk per lane: a traceback is a chain of ntb dependent
+// shared-memory reads, a warp issues in order, so doing it after every chunk costs more than the eight trellis steps;
+// with the last 32 + ntb snapshots and the per-lane best-state keys parked in shared memory, 32 chains run in lock step.
 #define VW_WARPS 4
+#define VW_RING 48            // snapshots kept per frame: >= 32 + VIT_NTB_MAX - 1
 __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *__restrict__ jobs, int n_frames, const uint32_t *__restrict__ vit_in,
                                                                uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
 {
-    __shared__ uint8_t s_ring[VW_WARPS][VIT_NTB_MAX][64];
+    __shared__ uint8_t s_ring[VW_WARPS][VW_RING][64];
+    __shared__ uint32_t s_keys[VW_WARPS][32 * 33];      // [lane][chunk % 32], rows padded: conflict-free both ways
     __shared__ uint32_t s_crc[256];
     __shared__ uint16_t s_scr[128];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = c_tab.crc_tab[i];
@@ -1239,6 +1244,7 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
     const int L = J.len;
     const int last_chunk = L + 1 + ntb;
     uint8_t (*ring)[64] = s_ring[wib];
+    uint32_t *keys = s_keys[wib];
     // this lane's butterfly: expected symbols on the branch from state `lane` to state 2 * lane
     const uint32_t A = vit_par((2u * lane) & 0x6du), B = vit_par((2u * lane) & 0x4fu);
     const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
@@ -1260,52 +1266,51 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
         wlo = (odd ? a1 : a0) & ~0x100u;
         whi = (odd ? b1 : b0) & ~0x100u;
     };
-    // snapshot of the path bytes into ring slot `slot`, first best state (largest metric, smallest state)
-    auto snapshot_best = [&](int slot) {
-        ring[slot][lane] = (uint8_t)wlo;
-        ring[slot][lane + 32] = (uint8_t)whi;
-        uint32_t key = max(((wlo >> 9) << 6) | (uint32_t)(63 - lane), ((whi >> 9) << 6) | (uint32_t)(31 - lane));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+    // end of chunk c: park the path bytes (slot c % VW_RING) and this lane's best-state key (largest metric, smallest
+    // state of its two), clear the path bytes
+    auto park = [&](int c) {
+        ring[c % VW_RING][lane] = (uint8_t)wlo;
+        ring[c % VW_RING][lane + 32] = (uint8_t)whi;
+        keys[lane * 33 + (c & 31)] = max(((wlo >> 9) << 6) | (uint32_t)(63 - lane), ((whi >> 9) << 6) | (uint32_t)(31 - lane));
         wlo &= ~0xffu;
         whi &= ~0xffu;
+    };
+    PsduSink sink;
+    sink.init(psdu + (int64_t)job * (PSDU_STRIDE / 4), L, s_crc, s_scr);
+    sink.writer = lane == 0;                          // every lane runs the sink (no divergent region), lane 0 stores
+    // tracebacks of chunks base .. base + 31 (those in [1, last_chunk]), lane g takes chunk base + g
+    auto trace32 = [&](int base) {
         __syncwarp();
-        return 63 - (int)(key & 63u);
+        const int k = base + lane;
+        uint32_t key = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) key = max(key, keys[j * 33 + (k & 31)]);
+        int bs = 63 - (int)(key & 63u), sl = k % VW_RING;
+        for (int i = 0; i < ntb - 1; ++i) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? VW_RING : sl) - 1; }
+        const uint32_t byte = ring[sl][bs];
+        for (int g = 0; g < 32; ++g) {
+            const uint32_t bg = __shfl_sync(0xffffffffu, byte, g);
+            const int kg = base + g;
+            if (kg >= ntb && kg <= last_chunk) sink.push(bg, kg - ntb);
+        }
+        __syncwarp();
     };
     uint32_t w = in[0];
 #pragma unroll 1
     for (int k = 0; k < 6; ++k) step((w >> (4 * k)) & 0xfu, 1u << (5 - k));
-    int slot = 1 % ntb;
-    int bs = snapshot_best(slot), sl = slot;          // the first chunk's traceback result is discarded
-    PsduSink sink;
-    sink.init(psdu + (int64_t)job * (PSDU_STRIDE / 4), L, s_crc, s_scr);
-    sink.writer = lane == 0;                          // every lane runs the sink (no divergence), lane 0 stores
+    park(0);                                          // chunk 0 is never traced back (upstream discards its output)
     uint32_t next = 1 < nw ? in[1] : 0u;
 #pragma unroll 1
     for (int chunk = 1; chunk <= last_chunk; ++chunk) {
         const uint32_t bits = __funnelshift_r(w, next, 24);
         w = next;
         next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
-        // the traceback of the previous chunk (ntb - 1 dependent reads) rides along with this chunk's eight steps
-        // (measured: spreading it over two chunks with a deeper ring does not help -- ptxas clusters the dependent
-        // reads whatever the source order, and a warp issues in order)
-        int left = ntb - 1;
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            if (left > 0) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; --left; }
-            step((bits >> (4 * s)) & 0xfu, 0x80u >> s);
-        }
-        while (left > 0) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; --left; }
-        if (chunk - 1 >= ntb) sink.push(ring[sl][bs], chunk - 1 - ntb);
-        __syncwarp();                                  // every lane has read the slot the next snapshot overwrites
-        slot = (slot + 1 == ntb) ? 0 : slot + 1;
-        bs = snapshot_best(slot);
-        sl = slot;
+        for (int s = 0; s < 8; ++s) step((bits >> (4 * s)) & 0xfu, 0x80u >> s);
+        park(chunk);
+        if ((chunk & 31) == 31) trace32(chunk - 31);
     }
-    if (last_chunk >= ntb) {
-        for (int i = 0; i < ntb - 1; ++i) { bs = ring[sl][bs] >> 2; sl = (sl == 0 ? ntb : sl) - 1; }
-        sink.push(ring[sl][bs], last_chunk - ntb);
-    }
+    if ((last_chunk & 31) != 31) trace32(last_chunk & ~31);
     if (lane == 0) frames[J.frame].crc_ok = sink.crc_ok();
 }
 
