@@ -545,6 +545,20 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     for (int i = 0; i <= ST_COUNT; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) return fail(WIFI_E_CUDA);
     if (upload_tables(h) != WIFI_OK) return fail(WIFI_E_CUDA);
     if (cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM) != cudaSuccess) return fail(WIFI_E_CUDA);
+    {
+        // CUDA loads a kernel on its first launch (milliseconds): do it here, not inside the first live run
+        const void *kernels[] = {(const void *)k_detect, (const void *)k_select_spec, (const void *)k_select, (const void *)k_reserve,
+                                 (const void *)k_frames_init, (const void *)k_sync_long, (const void *)k_signal, (const void *)k_plan_fast,
+                                 (const void *)k_plan, (const void *)k_pack, (const void *)k_viterbi, (const void *)k_viterbi_warp,
+                                 (const void *)k_move_segments, (const void *)k_sc16_to_fc32, (const void *)k_tx, (const void *)k_channel,
+                                 (const void *)k_demod<false, WIFI_EQ_LS, 0>, (const void *)k_demod<false, WIFI_EQ_LS, 1>,
+                                 (const void *)k_demod<false, WIFI_EQ_LMS, 0>, (const void *)k_demod<false, WIFI_EQ_LMS, 1>,
+                                 (const void *)k_demod<false, WIFI_EQ_COMB, 0>, (const void *)k_demod<false, WIFI_EQ_COMB, 1>,
+                                 (const void *)k_demod<false, WIFI_EQ_STA, 0>, (const void *)k_demod<false, WIFI_EQ_STA, 1>};
+        cudaFuncAttributes fa;
+        for (const void *k : kernels)
+            if (cudaFuncGetAttributes(&fa, k) != cudaSuccess) return fail(WIFI_E_CUDA);
+    }
     const int64_t S = cfg.max_samples, Fm = cfg.max_frames;
     h->row_cap = S / 80 + Fm + MAX_LINKS + 64;
     bool ok = true;
