@@ -992,19 +992,18 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
         if (n > newest) newest = n;
         pushed += n;
     }
-    int64_t have_all = 0, total = 0, fullest = 0;
+    int64_t have_all = 0, fullest = 0;
     for (int l = 0; l < n_links; ++l) {
         auto &S = h->s_links[l];
         const int64_t n = (int64_t)(link_off[l + 1] - link_off[l]);
         if (n) CK(cudaMemcpyAsync(h->d_stream + (int64_t)l * h->s_cap + S.fill, iq + 2 * link_off[l], (size_t)n * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
         S.fill += n;
         have_all += S.fill - S.hist;
-        total += S.fill;
         if (S.fill > fullest) fullest = S.fill;
     }
     h->s_unprocessed += newest;
-    // small pushes only buffer: the pipeline has a fixed cost of a millisecond or two per run (one trellis per
-    // thread), so it runs when enough new samples wait, when a region is half full, on an empty push, or on flush
+    // small pushes only buffer: a pipeline run has a fixed cost of about a millisecond (the decoder's latency for the
+    // longest frame), so it runs when enough new samples wait, when a region is half full, on an empty push, or on flush
     if (have_all <= 0 || (!flush && pushed != 0 && h->s_unprocessed < h->s_batch && 2 * fullest < h->s_cap)) {
         if (pushed) {
             // The caller's buffer must be free again when the call returns.  A copy from pageable memory has left the
