@@ -968,7 +968,7 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_signal(wifi_b200_frame *frames, i
 // its symbols: then it resets the collection state whatever came before (unless an older tag is
 // still pending) and forms a job on its own.  Groups of 32 frames that are all regular or
 // SIGNAL-less are planned in parallel; any other group falls back to the sequential machine.
-struct PlanState { int cur, copied, need, pending; JobDesc J; bool bad; };
+struct PlanState { int cur, copied, need, pending; JobDesc J; };
 
 __device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *frames, JobDesc *jobs, int *pack_list, int *n_pack, int *err, int soft)
 {
@@ -988,20 +988,18 @@ __device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *f
             S.copied = 0;
             S.need = t_sym;
             S.J.frame = tagf; S.J.enc = frames[tagf].encoding; S.J.len = t_len; S.J.n_sym = t_sym; S.J.n_seg = 0; S.J.need_pack = 0;
-            S.bad = false;
         }
         if (S.cur < 0 || S.copied >= S.need) continue;
         int take = F.n_rows < S.need - S.copied ? F.n_rows : S.need - S.copied;
         if (S.J.n_seg < 4) {
             S.J.seg_row[S.J.n_seg] = (int32_t)F.row_off;
             S.J.seg_cnt[S.J.n_seg] = take;
-            S.J.n_seg++;
-        } else {
-            S.bad = true;
         }
+        S.J.n_seg++;              // beyond four the packer walks the frame records (job_row)
         S.copied += take;
         if (S.copied == S.need) {
-            if (S.bad) { atomicExch(err, WIFI_E_OVERFLOW); continue; }
+            S.J.last_frame = fi;
+            S.J.pad0 = 0;
             for (int s = S.J.n_seg; s < 4; ++s) { S.J.seg_row[s] = 0; S.J.seg_cnt[s] = 0; }
             bool own = (S.J.n_seg == 1 && fi == S.cur);
             S.J.need_pack = (!own || (!soft && (c_tab.mcs[S.J.enc].n_dbps & 7) != 0)) ? 1 : 0;
@@ -1033,6 +1031,7 @@ __global__ void __launch_bounds__(128) k_plan_fast(wifi_b200_frame *frames, int 
     J.seg_row[0] = (int32_t)F->row_off; J.seg_cnt[0] = fsym;
     for (int s = 1; s < 4; ++s) { J.seg_row[s] = 0; J.seg_cnt[s] = 0; }
     J.need_pack = (!soft && (c_tab.mcs[enc].n_dbps & 7) != 0) ? 1 : 0;
+    J.last_frame = fi; J.pad0 = 0;
     jobs[fi] = J;
     if (J.need_pack) pack_list[atomicAdd(n_pack, 1)] = fi;
     frames[fi].accepted = 1;
@@ -1052,7 +1051,7 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
     if (!link_dirty[l]) return;          // every frame of the link was regular or SIGNAL-less: k_plan_fast is exact
     const LinkDesc L = links[l];
     PlanState S;
-    S.cur = -1; S.copied = 0; S.need = 0; S.pending = -1; S.bad = false; S.J.n_seg = 0;
+    S.cur = -1; S.copied = 0; S.need = 0; S.pending = -1; S.J.n_seg = 0;
     const int fend = L.frame_first + L.frame_count;
     for (int f0 = L.frame_first; f0 < fend; f0 += 32) {
         int fi = f0 + lane;
@@ -1075,6 +1074,7 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
                 J.seg_row[0] = (int32_t)row_off; J.seg_cnt[0] = fsym;
                 for (int s = 1; s < 4; ++s) { J.seg_row[s] = 0; J.seg_cnt[s] = 0; }
                 J.need_pack = (!soft && (c_tab.mcs[enc].n_dbps & 7) != 0) ? 1 : 0;
+                J.last_frame = fi; J.pad0 = 0;
                 jobs[fi] = J;
                 if (J.need_pack) pack_list[atomicAdd(n_pack, 1)] = fi;
                 frames[fi].accepted = 1;
@@ -1088,7 +1088,6 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
                 S.need = __shfl_sync(0xffffffffu, fsym, lastl);
                 S.copied = S.need;
                 S.J.n_seg = 0;
-                S.bad = false;
             }
         } else {
             __syncwarp();   // the jobs[].n_sym = 0 defaults above must land before the sequential writes
@@ -1097,7 +1096,7 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
             S.copied = __shfl_sync(0xffffffffu, S.copied, 0);
             S.need = __shfl_sync(0xffffffffu, S.need, 0);
             S.pending = __shfl_sync(0xffffffffu, S.pending, 0);
-            // S.J / S.bad of an open collection live in lane 0 only; lane 0 is the one that continues it
+            // S.J of an open collection lives in lane 0 only; lane 0 is the one that continues it
         }
     }
     if (lane == 0) link_open[l] = S.pending >= 0 ? S.pending : ((S.cur >= 0 && S.copied < S.need) ? S.cur : -1);
@@ -1107,7 +1106,8 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
 // Only for the jobs k_demod could not pack itself (pack_list): gathered rows, BPSK 3/4.
 // depunct_lut[enc][q] for q in [0, 2*n_dbps): 0xffff = erasure, else (carrier << 3) | bit
 __global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, const int *__restrict__ pack_list, const int *__restrict__ n_pack,
-                                               const uint8_t *__restrict__ rows, const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in)
+                                               const uint8_t *__restrict__ rows, const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in,
+                                               const wifi_b200_frame *__restrict__ frames)
 {
     const int np = *n_pack;
     for (int e = blockIdx.y; e < np; e += gridDim.y) {
@@ -1123,9 +1123,7 @@ __global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, 
             int tstep = 8 * w;
             int q = 2 * tstep;
             int s = q / per, qi = q - s * per;
-            int seg = 0, sbase = 0;
-            while (seg < J.n_seg - 1 && s >= sbase + J.seg_cnt[seg]) { sbase += J.seg_cnt[seg]; ++seg; }
-            const uint8_t *rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
+            const uint8_t *rp = rows + job_row(J, frames, s) * 48;
             uint32_t word = 0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -1138,8 +1136,7 @@ __global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, 
                 if (++qi == per) {
                     qi = 0;
                     ++s;
-                    if (s - sbase >= J.seg_cnt[seg] && seg < J.n_seg - 1) { sbase += J.seg_cnt[seg]; ++seg; }
-                    rp = rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * 48;
+                    if (s < J.n_sym) rp = rows + job_row(J, frames, s) * 48;
                 }
             }
             vw[w] = word;
@@ -1318,7 +1315,7 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
 // trellis words for gathered jobs in soft mode: word = 2 steps x 2 int8 soft symbols, erasure = 0
 __global__ void __launch_bounds__(256) k_pack_soft(const JobDesc *__restrict__ jobs, const int *__restrict__ pack_list, const int *__restrict__ n_pack,
                                                     const int8_t *__restrict__ soft_rows, const uint16_t *__restrict__ depunct_lut,
-                                                    uint32_t *__restrict__ vit_soft_in)
+                                                    uint32_t *__restrict__ vit_soft_in, const wifi_b200_frame *__restrict__ frames)
 {
     const int np = *n_pack;
     for (int e = blockIdx.y; e < np; e += gridDim.y) {
@@ -1332,9 +1329,7 @@ __global__ void __launch_bounds__(256) k_pack_soft(const JobDesc *__restrict__ j
         for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
             int q = 4 * w;
             int s = q / per, qi = q - s * per;   // 4 positions never straddle a symbol (per % 4 == 0)
-            int seg = 0, sbase = 0;
-            while (seg < J.n_seg - 1 && s >= sbase + J.seg_cnt[seg]) { sbase += J.seg_cnt[seg]; ++seg; }
-            const int8_t *rp = soft_rows + (int64_t)(J.seg_row[seg] + (s - sbase)) * SOFT_ROW;
+            const int8_t *rp = soft_rows + job_row(J, frames, s) * SOFT_ROW;
             uint32_t word = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

@@ -405,13 +405,13 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
         mark(h, ST_PACK);
         size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256 + 128;   // ring, CRC table, descrambler table, branch words
         if (!soft) {
-            k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in);
+            k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in, h->d_frames);
             mark(h, ST_VITERBI);
             // a handful of frames (streaming runs): one trellis per warp, a third of the latency; else one per thread
             if (nf <= VW_SWITCH) k_viterbi_warp<<<(unsigned)((nf + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
             else k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
         } else {
-            k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in);
+            k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in, h->d_frames);
             mark(h, ST_VITERBI);
             k_viterbi_soft<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_soft_in, h->d_psdu, h->d_frames);
         }
@@ -426,7 +426,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (h->h_counters[2] != 0) {
-        h->err = "decode_mac symbol collection spans more than 4 bursts";
+        h->err = "receive pipeline reported an internal overflow";
         return WIFI_E_OVERFLOW;
     }
     h->host_mirror = mirror;
@@ -1031,7 +1031,19 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
     }
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
     int rc = run_rx(h, h->d_stream, true);
-    if (rc) return rc;
+    if (rc) {
+        // The run failed (more triggers than max_frames, a CUDA error ...).  Keeping the samples would make every later
+        // push re-run them and fail again until the backlog overflows, so the buffered region is dropped: the streams
+        // continue behind it as after a flush and the caller sees the error code once.
+        for (auto &S : h->s_links) {
+            const int64_t end_abs = S.abs0 + (S.fill - S.hist);
+            S.fill = 0;
+            S.abs0 = (end_abs + FE_CHUNK - 1) / FE_CHUNK * FE_CHUNK;
+            S.hist = 0; S.prev_trigger = -1; S.fo_carry = 0.f;
+        }
+        h->err += " (streaming: the buffered samples were discarded)";
+        return rc;
+    }
     // Frames are ordered by (link, trigger): publish the CRC-ok ones and note from where each link must be kept:
     // its held burst, or -- when decode_mac's state was left open in front of a held burst (a frame cut short by a
     // re-trigger whose symbol collection, or pending tag, continues into that burst) -- the frame that opened it.

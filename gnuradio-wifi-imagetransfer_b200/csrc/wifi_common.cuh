@@ -93,11 +93,33 @@ struct EqState {
 struct JobDesc {
     int32_t frame;        // owner (tag) frame
     int32_t enc, len, n_sym;
-    int32_t n_seg;
+    int32_t n_seg;        // bursts the symbols were collected from; the first 4 are listed below
     int32_t seg_row[4];   // first row of each segment
     int32_t seg_cnt[4];   // rows in each segment
     int32_t need_pack;    // trellis words not already written by k_demod (gathered rows, BPSK 3/4)
+    int32_t last_frame;   // frame that delivered the last symbol (n_seg > 4: the segments are found by walking the frames)
+    int32_t pad0;
 };
+
+// Row of data symbol s of a decode job.  Up to four bursts are listed in the job; a collection that spans more
+// (decode_mac keeps collecting through any number of bursts whose tags it refuses) is located by walking the frame
+// records from the tag frame: every burst in between that delivered rows contributed all of them, in order.
+__device__ __forceinline__ int64_t job_row(const JobDesc &J, const wifi_b200_frame *__restrict__ frames, int s)
+{
+    if (J.n_seg <= 4) {
+        int seg = 0, sbase = 0;
+        while (seg < J.n_seg - 1 && s >= sbase + J.seg_cnt[seg]) { sbase += J.seg_cnt[seg]; ++seg; }
+        return (int64_t)J.seg_row[seg] + (s - sbase);
+    }
+    int left = s;
+    for (int g = J.frame; g < J.last_frame; ++g) {
+        const int nr = frames[g].n_rows;
+        if (nr <= 0) continue;
+        if (left < nr) return frames[g].row_off + left;
+        left -= nr;
+    }
+    return frames[J.last_frame].row_off + left;
+}
 
 __device__ __forceinline__ int dev_decide(int nb, cf s)
 {

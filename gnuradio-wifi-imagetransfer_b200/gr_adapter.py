@@ -62,6 +62,7 @@ class wifi_tx_b200(gr.basic_block):
         self._phy = phy
         self._q = collections.deque()      # [burst ndarray, samples already written]
         self._lock = threading.Lock()
+        self._ready = threading.Event()    # set while bursts wait: an idle work() call sleeps on it instead of spinning
         self.message_port_register_in(pmt.intern(_MAC_IN))
         self.set_msg_handler(pmt.intern(_MAC_IN), self.handle_mac_in)
 
@@ -71,10 +72,15 @@ class wifi_tx_b200(gr.basic_block):
         self._phy.samp_out.clear()
         with self._lock:
             self._q.append([burst, 0])
+            self._ready.set()
 
     def general_work(self, input_items, output_items):
         out = output_items[0]
         produced = 0
+        # A source block that returns 0 is called again at once by GNU Radio's thread-per-block scheduler: with no PDU
+        # queued, wait (bounded, so stop() is honoured) the way pdu_to_tagged_stream blocks on its message queue.
+        if not self._q:
+            self._ready.wait(0.01)
         with self._lock:
             while self._q and produced < len(out):
                 burst, done = self._q[0]
@@ -87,6 +93,8 @@ class wifi_tx_b200(gr.basic_block):
                     self._q.popleft()
                 else:
                     self._q[0][1] = done + n
+            if not self._q:
+                self._ready.clear()
         return produced
 
 
@@ -115,7 +123,7 @@ class wifi_rx_b200(gr.basic_block):
 
     def _publish(self, pdus):
         for meta, mpdu in pdus:
-            meta = {k: meta[k] for k in ("snr", "nomfreq", "freqofs", "dlt")}     # upstream decode_mac's dict
+            meta = {k: meta[k] for k in ("snr", "nomfreq", "freqofs", "dlt", "encoding")}     # upstream decode_mac's dict (+ the MCS)
             self.message_port_pub(pmt.intern(_MAC_OUT), pdu_from_python(meta, mpdu))
 
     def _run(self):

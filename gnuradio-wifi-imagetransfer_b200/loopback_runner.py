@@ -63,7 +63,9 @@ class IrsTransceiver:
         gain = 0.6 * math.sqrt(10 ** (self.snr / 10.0))
         n_out = 100 + burst.size + 1000
         x = np.concatenate([np.zeros(100, np.complex64), burst, np.zeros(1000, np.complex64)]).astype(np.complex64)
-        cfo = 2 * math.pi * self.epsilon * self.freq / 10e6 / self.samp_rate if self.epsilon else 0.0
+        # channel_model(frequency_offset = epsilon * freq / 10e6) (IRS_tranceiver.py:284,425,434): GNU Radio reads that
+        # value as normalised cycles per sample, i.e. a phase step of 2 pi frequency_offset; the library's cfo is rad/sample
+        cfo = 2 * math.pi * self.epsilon * self.freq / 10e6
         y = self.phy.handle.channel(x, n_out=n_out, n0=self._n0, gain=gain, cfo=cfo, noise_sigma=math.sqrt(2.0), seed=self.seed)
         self._n0 += n_out
         return y

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from util import assert_frames_equal, make_capture, make_psdu
+from util import assert_frames_equal, capture_with_collection_over_many_bursts, make_capture, make_psdu
 
 pytestmark = pytest.mark.gpu
 
@@ -349,6 +349,65 @@ def test_udp_runner_speaks_the_apps_contract(O, W):
     assert all(np.array_equal(g[1], p[1]) for g, p in zip(got, pieces))
     assert t.stats["pdus_out"] == len(pieces)
     t.close()
+
+
+def test_loopback_epsilon_is_the_channel_models_frequency_offset(O, W):
+    """channel_model(frequency_offset = epsilon * freq / 10e6) is cycles per sample (IRS_tranceiver.py:284,434): with the
+    slider at its end stop (20e-6) the receiver must report 2 pi * 0.01178 = 0.074 rad/sample, not a 2e7 times smaller one."""
+    import math
+    t = W.loopback_runner.IrsTransceiver(in_port=0, out_addr=("127.0.0.1", 9), snr=27.0, epsilon=20e-6, encoding=3)
+    try:
+        want = 2 * math.pi * 20e-6 * 5.89e9 / 10e6
+        burst = t.phy.mac_in(t.mac.app_in(b"x" * 300))
+        y = t._through_channel(burst)
+        pdus, res = t.phy.rx(y)
+        assert len(pdus) == 1 and pdus[0][1][24:] == b"x" * 300
+        f = res.frames[0]
+        assert abs((float(f["freq_short"]) - float(f["freq_long"])) - want) < 2e-3, (f["freq_short"], f["freq_long"], want)
+        assert abs(pdus[0][0]["freqofs"] - want * 20e6 / (2 * math.pi)) < 2e-3 * 20e6 / (2 * math.pi)
+        t.set_epsilon(0.0)
+        _, res0 = t.phy.rx(t._through_channel(burst))
+        assert abs(float(res0.frames[0]["freq_short"]) - float(res0.frames[0]["freq_long"])) < 2e-3
+    finally:
+        t.close()
+
+
+@pytest.mark.parametrize("soft", [False, True])
+def test_collection_through_more_than_four_bursts(O, W, soft):
+    """decode_mac keeps collecting a frame's symbols through any number of bursts whose tags it refuses (oversize
+    SIGNAL fields); the library used to give up beyond four and fail the whole call."""
+    y = capture_with_collection_over_many_bursts(O, np.random.default_rng(5))
+    ref = O.rx(y, algo=0, soft=soft)
+    assert ref.frames[0]["decoded"] == 1 and int((ref.frames["n_rows"] > 0).sum()) >= 6 and int(ref.frames["accepted"].sum()) == 1
+    h = W.Handle(max_samples=1 << 16, max_frames=64, soft_decision=soft)
+    try:
+        assert_frames_equal(h.rx_batch(y), ref)
+        # streamed: the open collection is carried from run to run with the held bursts
+        want = [(int(f["trigger"]), ref.psdu(i)[:-4]) for i, f in enumerate(ref.frames) if f["crc_ok"]]
+        got = []
+        for pos in range(0, y.size, 3000):
+            h.rx_push(y[pos:pos + 3000], flush=(pos + 3000 >= y.size))
+            got += h.rx_pop()
+        assert [(int(f["trigger"]), d) for f, d in got] == want
+    finally:
+        h.close()
+
+
+def test_streaming_recovers_after_a_failed_run(O, W):
+    """A run that fails (here: more triggers than max_frames) drops the buffered region instead of re-running it on
+    every later push; the stream decodes what follows."""
+    rng = np.random.default_rng(77)
+    y, _ = make_capture(O, rng, [(3, 60)] * 12, snr_db=30, gap=700, seed=1)
+    z, psdus = make_capture(O, rng, [(3, 200)] * 2, snr_db=30, seed=2)
+    h = W.Handle(max_samples=1 << 18, max_frames=4)
+    try:
+        with pytest.raises(W.WifiB200Error) as e:
+            h.rx_push(y, flush=False)
+        assert e.value.code == W.wifi_b200.E_OVERFLOW
+        h.rx_push(z, flush=True)
+        assert [d for _, d in h.rx_pop()] == [p[:-4] for p in psdus]
+    finally:
+        h.close()
 
 
 @pytest.mark.parametrize("algo", [0, 1, 3])

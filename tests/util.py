@@ -38,3 +38,40 @@ def assert_frames_equal(gpu, ref, float_exact=True):
     for i in range(len(ref.frames)):
         if ref.frames[i]["decoded"]:
             assert gpu.psdu(i) == ref.psdu(i), ("psdu", i)
+
+
+def oversize_burst(rng, n_data_syms=30, length=4000, enc=0):
+    """Preamble + a SIGNAL field announcing `length` bytes (more than decode_mac accepts: its tag is refused and the rows
+    behind it feed whatever collection is open) + BPSK data symbols; built with the independent numpy model."""
+    import ref_model as M
+    S = np.zeros(64, complex)
+    for k, s in M.STS_POS.items():
+        S[k % 64] = s * np.sqrt(13 / 6) * (1 + 1j)
+    L = np.zeros(64, complex)
+    for i, k in enumerate(range(-26, 27)):
+        L[k % 64] = M.LTS[i]
+    sts_t, lts_t = M.time_symbol(S), M.time_symbol(L)
+    parts = [np.tile(sts_t, 3)[:160], np.concatenate([lts_t[32:], lts_t, lts_t])]
+    sig = np.zeros(48, np.uint8)
+    sig[M.interleave_perm(0)] = M.conv_encode(M.signal_bits(enc, length))
+    t = M.time_symbol(M.ofdm_symbol(M.map_bits(sig, 0), M.PILOT_POLARITY[0]))
+    parts.append(np.concatenate([t[48:], t]))
+    for n in range(n_data_syms):
+        t = M.time_symbol(M.ofdm_symbol(M.map_bits(rng.integers(0, 2, 48), 0), M.PILOT_POLARITY[(n + 1) % 127]))
+        parts.append(np.concatenate([t[48:], t]))
+    return np.concatenate(parts).astype(np.complex64)
+
+
+def capture_with_collection_over_many_bursts(O, rng, n_interferers=6, spacing=1100):
+    """One BPSK 1/2 frame cut short again and again by stronger bursts whose SIGNAL fields announce oversize PSDUs:
+    decode_mac refuses their tags and keeps collecting the first frame's symbols through all of them."""
+    p = make_psdu(O, rng, 230, seq=1)                      # 79 symbols
+    a = O.tx_frame(p, 0, seed=5)
+    x = np.zeros(100 + a.size + spacing * (n_interferers + 2) + 3000, np.complex64)
+    x[100:100 + a.size] += 0.25 * a
+    pos = 100 + 1300
+    for _ in range(n_interferers):
+        b = oversize_burst(rng, n_data_syms=(spacing - 500) // 80)
+        x[pos:pos + b.size] += b
+        pos += spacing
+    return O.channel(x, gain=0.6, cfo=0.002, noise_sigma=0.003, seed=12)
