@@ -13,12 +13,8 @@
 #include "viterbi.cuh"
 
 // ------------------------------------------------------------------ R1 front-end
-__device__ __forceinline__ cf fe_prod(const cf *x, int64_t j, int hist)
-{
-    if (j - 16 < -(int64_t)hist) return {0.f, 0.f};
-    cf a = x[j], d = x[j - 16];
-    return {a.re * d.re + a.im * d.im, a.im * d.re - a.re * d.im};
-}
+// sample j of a link; samples before the start of the stream (beyond the stored history) are zeros
+__device__ __forceinline__ cf fe_at(const cf *x, int64_t j, int hist) { return j < -(int64_t)hist ? cf{0.f, 0.f} : x[j]; }
 
 __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int64_t chunk)
 {
@@ -38,7 +34,7 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
 // of the stream are zeros, which makes every "index < 0" special case of the oracle an exact
 // no-op (x + 0 == x), so the inner loop is branch free.
 #define DET_ROWS (DET_THREADS + 2)
-struct DetState { float sar, sai, sp; };
+struct DetState { cf sa; float sp; };
 
 // the oracle's expression c = |a| / p > thr; out of line: it runs for a handful of samples per tile and its
 // square root / division slow paths would otherwise be replicated in every unrolled copy of the walk
@@ -54,15 +50,12 @@ __device__ __forceinline__ void det_segment(const cf *base, DetState &st, float 
 #pragma unroll 4
     for (int i = I0; i < I1; ++i) {
         const cf xn = base[i], xd = base[i + OD], xo = base[i + OO], xod = base[i + OOD];
-        st.sar += xn.re * xd.re + xn.im * xd.im;
-        st.sai += xn.im * xd.re - xn.re * xd.im;
-        const float ar = st.sar, ai = st.sai;
-        st.sar -= xo.re * xod.re + xo.im * xod.im;
-        st.sai -= xo.im * xod.re - xo.re * xod.im;
-        st.sp += xn.re * xn.re + xn.im * xn.im;
+        st.sa = wdm_cmacc(st.sa, xn, xd);          // fused multiply-add chains, as the oracle's FrontEnd::step
+        const float m2 = wdm_norm(st.sa);
+        st.sa = wdm_cmsubc(st.sa, xo, xod);
+        st.sp = wdm_norm_add(st.sp, xn);
         const float p = st.sp;
-        st.sp -= xod.re * xod.re + xod.im * xod.im;
-        const float m2 = ar * ar + ai * ai;
+        st.sp = wdm_norm_sub(st.sp, xod);
         // c = sqrt(m2)/p > thr.  Decide from the squares when the margin (1e-4) dwarfs the rounding of
         // the exact expression (< 3e-7); evaluate the oracle's expression only inside the margin or when
         // p is outside the range where the squares are safe.
@@ -108,19 +101,13 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
     uint32_t w0 = 0u, w1 = 0u;
     if (T0 + (int64_t)tid * FE_CHUNK < hi) {
         DetState st;
-        st.sar = st.sai = st.sp = 0.f;
+        st.sa = cf{0.f, 0.f};
+        st.sp = 0.f;
         // the 47 (63) samples before the chunk live in the previous padded row: element -k sits at base - k - 1
 #pragma unroll 4
-        for (int k = 47; k >= 1; --k) {
-            const cf a = base[-k - 1], d = base[-k - 17];
-            st.sar += a.re * d.re + a.im * d.im;
-            st.sai += a.im * d.re - a.re * d.im;
-        }
+        for (int k = 47; k >= 1; --k) st.sa = wdm_cmacc(st.sa, base[-k - 1], base[-k - 17]);
 #pragma unroll 4
-        for (int k = 63; k >= 1; --k) {
-            cf a = base[-k - 1];
-            st.sp += a.re * a.re + a.im * a.im;
-        }
+        for (int k = 63; k >= 1; --k) st.sp = wdm_norm_add(st.sp, base[-k - 1]);
         const float thr2 = thr_f * thr_f;
         det_segment<0, 16, -17, -48, -64>(base, st, thr_f, thr2, w0);
         det_segment<16, 32, -16, -48, -64>(base, st, thr_f, thr2, w0);
@@ -438,22 +425,21 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
     int64_t t = F.trigger;
     {
         // a[t]: the moving_average_cc value sync_short sees on its port 1 at the trigger, recomputed on
-        // the oracle's chunk grid.  The products are formed in parallel, the running sum (whose order
-        // of additions is the contract) by one thread from shared memory.
+        // the oracle's chunk grid: the samples are staged in parallel, the running sum (a chain of fused
+        // multiply-adds whose order is the contract) is walked by one thread from shared memory.
         const int64_t i0 = t & ~(int64_t)(FE_CHUNK - 1);
-        const int cnt = (int)(t - i0) + 48;
-        cf *sprod = scorr;   // scratch, reused later
-        for (int q = tid; q < cnt; q += blockDim.x) sprod[q] = fe_prod(x, i0 - 47 + q, hist);
+        cf *sx = sb;         // scratch, reused later: samples i0 - 63 .. t
+        const int cnt = (int)(t - i0) + 64;
+        for (int q = tid; q < cnt; q += blockDim.x) sx[q] = fe_at(x, i0 - 63 + q, hist);
         __syncthreads();
         if (tid == 0) {
-            float sar = 0.f, sai = 0.f;
-            for (int q = 0; q < 47; ++q) { sar += sprod[q].re; sai += sprod[q].im; }
-            for (int q = 47; q < cnt; ++q) {
-                sar += sprod[q].re;
-                sai += sprod[q].im;
-                if (q < cnt - 1) { sar -= sprod[q - 47].re; sai -= sprod[q - 47].im; }
+            cf sa = {0.f, 0.f};
+            for (int q = 16; q < 63; ++q) sa = wdm_cmacc(sa, sx[q], sx[q - 16]);                  // seed: lags i0-47 .. i0-1
+            for (int q = 63; q < cnt; ++q) {
+                sa = wdm_cmacc(sa, sx[q], sx[q - 16]);
+                if (q < cnt - 1) sa = wdm_cmsubc(sa, sx[q - 47], sx[q - 63]);
             }
-            s_freq = wdm_atan2f(sai, sar) / 16;
+            s_freq = wdm_atan2f(sa.im, sa.re) / 16;
         }
     }
     __syncthreads();
@@ -469,9 +455,9 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
     for (int i = tid; i < SYNC_LENGTH; i += blockDim.x) {
         cf acc = {0.f, 0.f};
 #pragma unroll 8
-        for (int m = 0; m < 64; ++m) acc = cadd(acc, cmul(c_tab.long_taps[63 - m], sb[i + m]));
+        for (int m = 0; m < 64; ++m) acc = wdm_cmac(acc, c_tab.long_taps[63 - m], sb[i + m]);
         scorr[i] = acc;
-        smag[i] = acc.re * acc.re + acc.im * acc.im;
+        smag[i] = wdm_norm(acc);
     }
     __syncthreads();
     // four largest |corr|^2, earlier index first on ties (stable descending sort)
@@ -506,7 +492,7 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
                 int diff = hi - lo;
                 if (diff == 63 || diff == 64 || diff == 65) {
                     cf first = scorr[lo], second = scorr[hi];
-                    cf pr = cmul(first, cf{second.re, -second.im});
+                    cf pr = wdm_cmulc(first, second);
                     fs = lo;
                     fo = wdm_atan2f(pr.im, pr.re) / (float)diff;
                     found = diff;
@@ -577,6 +563,8 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
     const int fs = F.frame_start;
     const int n_syms = emitted_symbols(avail, fs, last);
     const float fshort = F.freq_short;
+    const float delta = fo - fshort;
+    const cf w1 = crot(delta);
     const int64_t t = F.trigger;
     const int hist = L.hist;
 
@@ -670,18 +658,12 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
             const int j0 = sym_j0(n);
             const cf s0 = raw[0], s1 = raw[1];
             if (n + 1 < n_end) fetch_raw(n + 1, raw);
-            cf v[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = j0 + u;
-                if (j < avail) {
-                    cf bj = cmul(u ? s1 : s0, crot(-fshort * (float)j));
-                    v[u] = cmul(bj, crot((float)j * fo));
-                } else {
-                    v[u] = {0.f, 0.f};
-                }
-            }
-            a = v[0]; b = v[1];
+            // one rotation by delta = freq_long - freq_short: the even sample by exp(j delta j0), the odd one behind
+            // it by that times exp(j delta) (oracle: sync_long COPY)
+            const cf r0 = crot(delta * (float)j0);
+            const cf r1 = cmul(r0, w1);
+            a = (j0 < avail) ? cmul(s0, r0) : cf{0.f, 0.f};
+            b = (j0 + 1 < avail) ? cmul(s1, r1) : cf{0.f, 0.f};
         }
         warp_fft64(a, b, lane, tw);
         // a = cur[iA], b = cur[iB] (fftshift)
@@ -708,7 +690,7 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
         cf ser = {0.f, 0.f};
         if (n >= 2) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) ser = cadd(ser, cmul(cf{pp[q].re, -pp[q].im}, pil[q]));
+            for (int q = 0; q < 4; ++q) ser = wdm_cmacc(ser, pil[q], pp[q]);
         }
         const bool up = lane >= 16;
         const float at = wdm_atan2f(up ? ser.im : sbeta.im, up ? ser.re : sbeta.re);

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_channel(const cf *__restrict__ in, cf *
         for (int t = 0; t < S.n_taps; ++t) {
             int64_t j = i - S.delay[t];
             if (j < 0 || j >= S.in_len) continue;
-            acc = cadd(acc, cmul(cf{S.tap_re[t], S.tap_im[t]}, in[S.in_off + j]));
+            acc = wdm_cmac(acc, cf{S.tap_re[t], S.tap_im[t]}, in[S.in_off + j]);
         }
         acc = cscale(acc, S.gain);
         cf w = crot(S.cfo * (float)i + S.phase0);

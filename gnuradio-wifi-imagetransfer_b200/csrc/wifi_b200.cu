@@ -317,6 +317,46 @@ __global__ void __launch_bounds__(256) k_move_segments(const cf *__restrict__ sr
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.n; i += (int64_t)gridDim.x * blockDim.x) dst[m.dst + i] = src[m.src + i];
 }
 
+// element-wise evaluation of the numerical contract on the device (tests/test_detmath.py)
+__global__ void __launch_bounds__(256) k_detmath(int fn, const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c,
+                                                  const float *__restrict__ d, float *o0, float *o1, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float r0 = o0[i], r1 = o1[i];
+        wdm_selftest(fn, a[i], b[i], c[i], d[i], &r0, &r1);
+        o0[i] = r0;
+        o1[i] = r1;
+    }
+}
+
+// Issue-rate probe of the integer ALU pipe (the pipe k_viterbi is bound by): every thread runs eight independent
+// chains of LOP3 (64 alu-pipe instructions per loop iteration, pinned with asm volatile), enough warps per
+// scheduler to hide the pipe latency.  warp-instructions / time = the ceiling bench.py's Viterbi roofline is quoted against.
+#define ALU_PROBE_OPS 64
+__global__ void __launch_bounds__(256) k_alu_peak(int iters, uint32_t seed, uint32_t *sink)
+{
+    uint32_t r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = seed * (threadIdx.x + 1u) + (uint32_t)k;
+    const uint32_t m = seed | 1u;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < ALU_PROBE_OPS / 16; ++u) {
+            // (ptxas turns plain integer adds into IMAD.IADD on the fma pipe when the alu pipe is the busier one, so the
+            // probe sticks to three-input logic ops, which only the alu pipe executes)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[k]) : "r"(r[(k + 3) & 7]), "r"(m));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(r[k]) : "r"(r[(k + 5) & 7]), "r"(m));
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x ^= r[k];
+    if (x == 0x12345u) sink[0] = x;      // keeps the chains alive; practically never taken
+}
+
 void mark(wifi_b200 *h, int i)
 {
     cudaEventRecord(h->ev[i], h->stream);
@@ -1161,6 +1201,56 @@ int wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *ps
     h->s_meta.erase(h->s_meta.begin(), h->s_meta.begin() + k);
     h->s_bytes.erase(h->s_bytes.begin(), h->s_bytes.begin() + consumed_bytes);
     *n_out = k;
+    return WIFI_OK;
+}
+
+int wifi_b200_selftest_detmath(wifi_b200_t *h, int fn, const float *a, const float *b, const float *c, const float *d, float *o0, float *o1, int64_t n)
+{
+    if (!h || !a || !b || !c || !d || !o0 || !o1 || n < 0 || fn < 0 || fn >= WDM_T_COUNT) return WIFI_E_ARG;
+    if (n == 0) return WIFI_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    float *dv = nullptr;
+    const size_t bytes = (size_t)n * sizeof(float);
+    CK(cudaMalloc(&dv, 6 * bytes));
+    const float *src[6] = {a, b, c, d, o0, o1};
+    int rc = WIFI_OK;
+    for (int k = 0; k < 6 && rc == WIFI_OK; ++k)
+        if (cudaMemcpyAsync(dv + (size_t)k * n, src[k], bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = WIFI_E_CUDA;
+    if (rc == WIFI_OK) {
+        k_detmath<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, h->stream>>>(fn, dv, dv + n, dv + 2 * n, dv + 3 * n, dv + 4 * n, dv + 5 * n, n);
+        if (cudaMemcpyAsync(o0, dv + 4 * n, bytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaMemcpyAsync(o1, dv + 5 * n, bytes, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = WIFI_E_CUDA;
+    }
+    cudaFree(dv);
+    if (rc) h->err = "selftest_detmath: CUDA error";
+    return rc;
+}
+
+int wifi_b200_alu_peak(wifi_b200_t *h, int iters, double *warp_inst_per_s, double *ms_out)
+{
+    if (!h || iters <= 0 || !warp_inst_per_s) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;      // 64 warps per SM, 16 per scheduler
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    k_alu_peak<<<blocks, threads, 0, h->stream>>>(iters / 8 + 1, 12345u, (uint32_t *)h->d_counters + 12);   // warm-up
+    cudaEventRecord(e0, h->stream);
+    k_alu_peak<<<blocks, threads, 0, h->stream>>>(iters, 12345u, (uint32_t *)h->d_counters + 12);
+    cudaEventRecord(e1, h->stream);
+    int rc = WIFI_OK;
+    float ms = 0.f;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) rc = WIFI_E_CUDA;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) { h->err = "alu_peak: CUDA error"; return rc; }
+    *warp_inst_per_s = (double)blocks * (threads / 32) * (double)iters * ALU_PROBE_OPS / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
     return WIFI_OK;
 }
 

@@ -1,8 +1,9 @@
 // wifi_common.cuh -- shared device types, constant tables and the fp32 helper
 // ops of libwifi_b200.so.  Numerical contract: every float expression here and
 // in the kernels is written in the same order as oracle/wifi_oracle.cpp and the
-// translation unit is compiled with -fmad=false, so results are bit-identical
-// to the oracle (see include/wifi_detmath.h).
+// translation unit is compiled with -fmad=false (the only fused multiply-adds are
+// the explicit fmaf() of include/wifi_detmath.h), so results are bit-identical
+// to the oracle.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,15 +23,12 @@
 #define SOFT_MAXW 6240          // soft mode: one word = 2 trellis steps x 2 int8 soft symbols
 #define SOFT_ROW 288            // soft values reserved per data symbol (N_CBPS <= 288)
 
-struct cf { float re, im; };
+// complex products, multiply-accumulates and divisions are the fused sequences of include/wifi_detmath.h
+typedef wdm_cf cf;
 __device__ __forceinline__ cf cadd(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
 __device__ __forceinline__ cf csub(cf a, cf b) { return {a.re - b.re, a.im - b.im}; }
-__device__ __forceinline__ cf cmul(cf a, cf b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
-__device__ __forceinline__ cf cdiv(cf a, cf b)
-{
-    float den = b.re * b.re + b.im * b.im;
-    return {(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
-}
+__device__ __forceinline__ cf cmul(cf a, cf b) { return wdm_cmul(a, b); }
+__device__ __forceinline__ cf cdiv(cf a, cf b) { return wdm_cdiv(a, b); }
 __device__ __forceinline__ cf cscale(cf a, float s) { return {a.re * s, a.im * s}; }
 __device__ __forceinline__ cf crot(float phase)
 {

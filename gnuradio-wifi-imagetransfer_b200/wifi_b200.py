@@ -59,6 +59,7 @@ EXPORTS = [
     "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_rx_push_links", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
+    "wifi_b200_selftest_detmath", "wifi_b200_alu_peak",
 ]
 
 _LIB = None
@@ -107,6 +108,8 @@ def lib():
         L.wifi_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.wifi_b200_stage_times.argtypes = [vp, vp, C.c_int]
         L.wifi_b200_stage_name.restype = C.c_char_p
+        L.wifi_b200_selftest_detmath.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, i64]
+        L.wifi_b200_alu_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
 
@@ -355,6 +358,22 @@ class Handle:
         d = {k: getattr(s, k) for k, _ in Stats._fields_ if k != "per_mcs_crc_ok"}
         d["per_mcs_crc_ok"] = list(s.per_mcs_crc_ok)
         return d
+
+    def detmath(self, fn, a, b=None, c=None, d=None, o0=None, o1=None):
+        """wdm_selftest(fn, ...) of include/wifi_detmath.h evaluated element-wise on the GPU; returns (o0, o1)."""
+        a = np.ascontiguousarray(a, np.float32)
+        z = np.zeros_like(a)
+        b, c, d = [z if v is None else np.ascontiguousarray(v, np.float32) for v in (b, c, d)]
+        o0 = np.zeros_like(a) if o0 is None else np.array(o0, np.float32)
+        o1 = np.zeros_like(a) if o1 is None else np.array(o1, np.float32)
+        self._ck(self._L.wifi_b200_selftest_detmath(self._h, int(fn), _p(a), _p(b), _p(c), _p(d), _p(o0), _p(o1), a.size))
+        return o0, o1
+
+    def alu_peak(self, iters=4096):
+        """Measured issue rate of the integer ALU pipe: (warp-instructions per second, milliseconds of the probe)."""
+        v, ms = C.c_double(), C.c_double()
+        self._ck(self._L.wifi_b200_alu_peak(self._h, int(iters), C.byref(v), C.byref(ms)))
+        return v.value, ms.value
 
     def stage_times(self):
         ms = np.zeros(16, np.float32)

@@ -188,6 +188,15 @@ int  wifi_b200_get_stats(wifi_b200_t *h, wifi_b200_stats *out);
 int  wifi_b200_stage_times(wifi_b200_t *h, float *ms, int cap);
 const char *wifi_b200_stage_name(int i);
 
+/* ---- diagnostics (no reference counterpart) ----
+ * Element-wise evaluation of the numerical contract (include/wifi_detmath.h, wdm_selftest(fn, ...)) on the GPU with host
+ * buffers: tests/test_detmath.py asks for bit equality with the same call on the host.  o0 / o1 are in-out. */
+int  wifi_b200_selftest_detmath(wifi_b200_t *h, int fn, const float *a, const float *b, const float *c, const float *d,
+                                float *o0, float *o1, int64_t n);
+/* Measured issue rate of the integer ALU pipe (independent LOP3 / IADD3 chains on every SM, `iters` x 64 instructions
+ * per thread): warp-instructions per second.  bench.py quotes the Viterbi kernel's roofline against it. */
+int  wifi_b200_alu_peak(wifi_b200_t *h, int iters, double *warp_inst_per_s, double *ms);
+
 #ifdef __cplusplus
 }
 #endif

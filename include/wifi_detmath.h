@@ -36,6 +36,69 @@
 #define WDM_FN static inline
 #endif
 
+/* ---- complex arithmetic: fixed sequences of IEEE-754 multiplies and fused multiply-adds ----
+ * The reference multiplies complex numbers through VOLK / std::complex, whose rounding depends on the SIMD kernel the
+ * machine dispatches to (SSE: separate multiplies and adds; AVX2+FMA builds: fused).  The contract fixes ONE sequence
+ * per operation -- the fused one: it is the more accurate of the two (one rounding less per term) and costs 4
+ * instructions per complex multiply on the GPU instead of 6.  Every complex product, multiply-accumulate and division
+ * of the oracle and of the CUDA library goes through these functions. */
+typedef struct wdm_cf { float re, im; } wdm_cf;
+
+/* a * b */
+WDM_FN wdm_cf wdm_cmul(wdm_cf a, wdm_cf b)
+{
+    wdm_cf r;
+    r.re = fmaf(a.re, b.re, -(a.im * b.im));
+    r.im = fmaf(a.re, b.im, a.im * b.re);
+    return r;
+}
+/* a * conj(b) */
+WDM_FN wdm_cf wdm_cmulc(wdm_cf a, wdm_cf b)
+{
+    wdm_cf r;
+    r.re = fmaf(a.re, b.re, a.im * b.im);
+    r.im = fmaf(a.im, b.re, -(a.re * b.im));
+    return r;
+}
+/* acc + a * b */
+WDM_FN wdm_cf wdm_cmac(wdm_cf acc, wdm_cf a, wdm_cf b)
+{
+    wdm_cf r;
+    r.re = fmaf(-a.im, b.im, fmaf(a.re, b.re, acc.re));
+    r.im = fmaf(a.im, b.re, fmaf(a.re, b.im, acc.im));
+    return r;
+}
+/* acc + a * conj(b) */
+WDM_FN wdm_cf wdm_cmacc(wdm_cf acc, wdm_cf a, wdm_cf b)
+{
+    wdm_cf r;
+    r.re = fmaf(a.im, b.im, fmaf(a.re, b.re, acc.re));
+    r.im = fmaf(-a.re, b.im, fmaf(a.im, b.re, acc.im));
+    return r;
+}
+/* acc - a * conj(b) */
+WDM_FN wdm_cf wdm_cmsubc(wdm_cf acc, wdm_cf a, wdm_cf b)
+{
+    wdm_cf r;
+    r.re = fmaf(-a.im, b.im, fmaf(-a.re, b.re, acc.re));
+    r.im = fmaf(a.re, b.im, fmaf(-a.im, b.re, acc.im));
+    return r;
+}
+/* |a|^2 */
+WDM_FN float wdm_norm(wdm_cf a) { return fmaf(a.re, a.re, a.im * a.im); }
+/* acc + |a|^2, acc - |a|^2 */
+WDM_FN float wdm_norm_add(float acc, wdm_cf a) { return fmaf(a.im, a.im, fmaf(a.re, a.re, acc)); }
+WDM_FN float wdm_norm_sub(float acc, wdm_cf a) { return fmaf(-a.im, a.im, fmaf(-a.re, a.re, acc)); }
+/* a / b = a * conj(b) * (1 / |b|^2): one IEEE division */
+WDM_FN wdm_cf wdm_cdiv(wdm_cf a, wdm_cf b)
+{
+    const float inv = 1.0f / wdm_norm(b);
+    wdm_cf n = wdm_cmulc(a, b), r;
+    r.re = n.re * inv;
+    r.im = n.im * inv;
+    return r;
+}
+
 /* sin and cos of x (radians).  |x| up to ~1e5 keeps abs error < 2e-7;
  * the PHY's largest argument is pi/16 * 43200 ~ 8.5e3.                      */
 WDM_FN void wdm_sincosf(float x, float *s, float *c)
@@ -163,6 +226,40 @@ WDM_FN void wdm_box_muller(uint32_t w0, uint32_t w1, float *z0, float *z1)
     wdm_sincosf(6.283185307179586f * u2, &s, &c);
     *z0 = rad * c;
     *z1 = rad * s;
+}
+
+/* ---- self-test dispatch: one element of tests/test_detmath.py (host: orc_detmath, device: wifi_b200_selftest_detmath).
+ * o0/o1 are in-out (the accumulator of the multiply-accumulate forms). ---- */
+enum { WDM_T_SINCOS = 0, WDM_T_ATAN2, WDM_T_LOG, WDM_T_CMUL, WDM_T_CMULC, WDM_T_CDIV, WDM_T_BOX_MULLER, WDM_T_CMAC,
+       WDM_T_CMACC, WDM_T_CMSUBC, WDM_T_NORM_ADD, WDM_T_NORM_SUB, WDM_T_PHILOX, WDM_T_COUNT };
+WDM_FN void wdm_selftest(int fn, float a, float b, float c, float d, float *o0, float *o1)
+{
+    wdm_cf x, y, acc, r;
+    x.re = a; x.im = b; y.re = c; y.im = d; acc.re = *o0; acc.im = *o1;
+    union { float f; uint32_t u; } ua, ub, uc, ud;
+    ua.f = a; ub.f = b; uc.f = c; ud.f = d;
+    switch (fn) {
+    case WDM_T_SINCOS: wdm_sincosf(a, o0, o1); break;
+    case WDM_T_ATAN2: *o0 = wdm_atan2f(a, b); break;
+    case WDM_T_LOG: *o0 = wdm_logf(a); break;
+    case WDM_T_CMUL: r = wdm_cmul(x, y); *o0 = r.re; *o1 = r.im; break;
+    case WDM_T_CMULC: r = wdm_cmulc(x, y); *o0 = r.re; *o1 = r.im; break;
+    case WDM_T_CDIV: r = wdm_cdiv(x, y); *o0 = r.re; *o1 = r.im; break;
+    case WDM_T_BOX_MULLER: wdm_box_muller(ua.u, ub.u, o0, o1); break;           /* a, b carry the two 32-bit words */
+    case WDM_T_CMAC: r = wdm_cmac(acc, x, y); *o0 = r.re; *o1 = r.im; break;
+    case WDM_T_CMACC: r = wdm_cmacc(acc, x, y); *o0 = r.re; *o1 = r.im; break;
+    case WDM_T_CMSUBC: r = wdm_cmsubc(acc, x, y); *o0 = r.re; *o1 = r.im; break;
+    case WDM_T_NORM_ADD: *o0 = wdm_norm_add(acc.re, x); break;
+    case WDM_T_NORM_SUB: *o0 = wdm_norm_sub(acc.re, x); break;
+    case WDM_T_PHILOX: {                                                        /* counter (a, b), key (c, d) as bit patterns */
+        uint32_t w[4];
+        wdm_philox4x32(ua.u, ub.u, 0u, 0u, uc.u, ud.u, w);
+        ua.u = w[0] ^ w[2]; ub.u = w[1] ^ w[3];
+        *o0 = ua.f; *o1 = ub.f;
+        break;
+    }
+    default: break;
+    }
 }
 
 #endif /* WIFI_DETMATH_H */

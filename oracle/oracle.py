@@ -281,6 +281,17 @@ def rx(x, link=0, **kw):
     return _collect(C.c_void_p(h), bool(cfg.want_carrier), bool(cfg.soft))
 
 
+def detmath(fn, a, b=None, c=None, d=None, o0=None, o1=None):
+    """Element-wise wdm_selftest(fn, ...) of include/wifi_detmath.h on the host; returns (o0, o1)."""
+    a = np.ascontiguousarray(a, np.float32)
+    z = np.zeros_like(a)
+    b, c, d = [z if v is None else np.ascontiguousarray(v, np.float32) for v in (b, c, d)]
+    o0 = np.zeros_like(a) if o0 is None else np.array(o0, np.float32)
+    o1 = np.zeros_like(a) if o1 is None else np.array(o1, np.float32)
+    lib().orc_detmath(C.c_int(fn), _p(a), _p(b), _p(c), _p(d), _p(o0), _p(o1), C.c_int64(a.size))
+    return o0, o1
+
+
 def rx_links(x, offsets, lengths, n_threads=1, **kw):
     cfg = rx_cfg(**kw)
     a = np.ascontiguousarray(x, np.complex64)

@@ -25,6 +25,12 @@
  *      defines "symbols past the end read as 0" for every frame.
  *  (3) FFTW/VOLK summation orders are machine dependent; the oracle fixes a
  *      radix-2 DIT network and ascending-index accumulation.
+ *  (6) Complex products are the fused sequences of wifi_detmath.h (VOLK's rounding
+ *      depends on the SIMD kernel it dispatches to); the running sums of the
+ *      front-end are fused multiply-add chains; sync_short's and sync_long's two
+ *      derotations are applied as one rotation by freq_long - freq_short.  Each
+ *      differs from the literal upstream float sequence by a few 1e-7 relative,
+ *      against a 2e-3 tolerance on equalised points.
  */
 #include "wifi_oracle.h"
 #include "../include/wifi_detmath.h"
@@ -39,15 +45,12 @@
 
 namespace {
 
-struct cf { float re, im; };
+/* complex products, multiply-accumulates and divisions are the fused sequences of include/wifi_detmath.h */
+typedef wdm_cf cf;
 static inline cf cadd(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
 static inline cf csub(cf a, cf b) { return {a.re - b.re, a.im - b.im}; }
-static inline cf cmul(cf a, cf b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
-static inline cf cdiv(cf a, cf b)
-{
-    float den = b.re * b.re + b.im * b.im;
-    return {(a.re * b.re + a.im * b.im) / den, (a.im * b.re - a.re * b.im) / den};
-}
+static inline cf cmul(cf a, cf b) { return wdm_cmul(a, b); }
+static inline cf cdiv(cf a, cf b) { return wdm_cdiv(a, b); }
 static inline cf cscale(cf a, float s) { return {a.re * s, a.im * s}; }
 static inline cf crot(float phase)
 {
@@ -527,7 +530,7 @@ static void channel(const cf *in, cf *out, int64_t n, int64_t n0, const orc_chan
         for (int t = 0; t < c.n_taps; ++t) {
             int64_t j = i - c.delay[t];
             if (j < 0 || j >= n) continue;
-            acc = cadd(acc, cmul(cf{c.tap_re[t], c.tap_im[t]}, in[j]));
+            acc = wdm_cmac(acc, cf{c.tap_re[t], c.tap_im[t]}, in[j]);
         }
         acc = cscale(acc, c.gain);
         cf w = crot(c.cfo * (float)i + c.phase0);
@@ -553,44 +556,29 @@ static void channel(const cf *in, cf *out, int64_t n, int64_t n0, const orc_chan
 struct FrontEnd {
     const cf *x;
     int64_t n;
-    float sar = 0, sai = 0, sp = 0;
-    inline cf prod(int64_t j) const
-    {
-        if (j < 16) return {0.f, 0.f};
-        cf a = x[j], d = x[j - 16];
-        return {a.re * d.re + a.im * d.im, a.im * d.re - a.re * d.im};
-    }
-    inline float pw(int64_t j) const { return j < 0 ? 0.f : x[j].re * x[j].re + x[j].im * x[j].im; }
+    cf sa = {0.f, 0.f};
+    float sp = 0;
+    /* samples before the start of the stream are zeros (GNU Radio history) */
+    inline cf at(int64_t j) const { return j < 0 ? cf{0.f, 0.f} : x[j]; }
     void seed(int64_t i0)
     {
-        sar = sai = sp = 0.f;
-        for (int64_t j = i0 - 47; j < i0; ++j) {
-            if (j < 0) continue;
-            cf p = prod(j);
-            sar += p.re;
-            sai += p.im;
-        }
-        for (int64_t j = i0 - 63; j < i0; ++j) {
-            if (j < 0) continue;
-            sp += pw(j);
-        }
+        sa = {0.f, 0.f};
+        sp = 0.f;
+        for (int64_t j = i0 - 47; j < i0; ++j) sa = wdm_cmacc(sa, at(j), at(j - 16));
+        for (int64_t j = i0 - 63; j < i0; ++j) sp = wdm_norm_add(sp, at(j));
     }
+    /* running sums as fused multiply-add chains: a[i] = sum of x[j] conj(x[j-16]) over the last 48 lags, p[i] = sum of
+     * |x[j]|^2 over the last 64 samples; the term leaving the window is subtracted after the output is taken */
     inline void step(int64_t i, cf &a, float &p, float &c)
     {
         if ((i & 63) == 0) seed(i);
-        cf pr = prod(i);
-        sar += pr.re;
-        sai += pr.im;
-        a = {sar, sai};
-        if (i - 47 >= 0) {
-            cf po = prod(i - 47);
-            sar -= po.re;
-            sai -= po.im;
-        }
-        sp += pw(i);
+        sa = wdm_cmacc(sa, at(i), at(i - 16));
+        a = sa;
+        sa = wdm_cmsubc(sa, at(i - 47), at(i - 63));
+        sp = wdm_norm_add(sp, at(i));
         p = sp;
-        if (i - 63 >= 0) sp -= pw(i - 63);
-        c = sqrtf(a.re * a.re + a.im * a.im) / p;
+        sp = wdm_norm_sub(sp, at(i - 63));
+        c = sqrtf(wdm_norm(a)) / p;
     }
 };
 
@@ -823,9 +811,9 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
             R.frames.push_back(F);
             continue;
         }
-        /* sync_short COPY output: b[j] = xd[t+j] * exp(-j*freq*j) */
-        b.resize(B.len);
-        for (int j = 0; j < B.len; ++j) {
+        /* sync_short COPY output: b[j] = xd[t+j] * exp(-j*freq*j); the matched filter looks at the first 320 + 63 */
+        b.resize(SYNC_LENGTH + 63);
+        for (int j = 0; j < SYNC_LENGTH + 63; ++j) {
             int64_t src = B.t + j - 16;
             cf s = src >= 0 ? x[src] : cf{0.f, 0.f};
             b[j] = cmul(s, crot(-B.freq * (float)j));
@@ -835,9 +823,9 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
         float mag[SYNC_LENGTH];
         for (int i = 0; i < SYNC_LENGTH; ++i) {
             cf acc = {0.f, 0.f};
-            for (int m = 0; m < 64; ++m) acc = cadd(acc, cmul(t.long_taps[63 - m], b[i + m]));
+            for (int m = 0; m < 64; ++m) acc = wdm_cmac(acc, t.long_taps[63 - m], b[i + m]);
             corr[i] = acc;
-            mag[i] = acc.re * acc.re + acc.im * acc.im;
+            mag[i] = wdm_norm(acc);
         }
         int top[4];
         {
@@ -856,7 +844,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
                 int diff = hi - lo;
                 if (diff == 63 || diff == 64 || diff == 65) {
                     cf first = corr[lo], second = corr[hi];
-                    cf pr = cmul(first, cf{second.re, -second.im});
+                    cf pr = wdm_cmulc(first, second);
                     F.frame_start = lo;
                     fo_carry = wdm_atan2f(pr.im, pr.re) / (float)diff;
                     F.found = diff;
@@ -864,12 +852,30 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
                 }
             }
         F.freq_long = fo_carry;
-        /* sync_long COPY: samples j in [0, len-320), CP dropped */
+        /* sync_long COPY: samples j in [0, len-320), CP dropped: symbol n starts at burst position
+         * frame_start + 64 n (the two LTS symbols) or frame_start + 128 + 80 (n - 2) + 16 (SIGNAL, data).
+         * Upstream rotates every sample twice (sync_short: exp(-j freq_short j), sync_long: exp(+j freq_long j), each
+         * phase a float product); the contract rotates once by delta = freq_long - freq_short: even samples of a
+         * symbol by exp(j delta j), the odd one behind it by that times exp(j delta) (choice 6). */
         int avail = B.len - SYNC_LENGTH;
         std::vector<cf> sy;
-        for (int j = 0; j < avail; ++j) {
-            int rel = j - F.frame_start;
-            if (rel >= 0 && (rel < 128 || ((rel - 128) % 80) > 15)) sy.push_back(cmul(b[j], crot((float)j * F.freq_long)));
+        {
+            const float delta = F.freq_long - B.freq;
+            const cf w1 = crot(delta);
+            int R = avail - F.frame_start;
+            int E = R <= 0 ? 0 : (R <= 128 ? R : 128 + 64 * ((R - 128) / 80) + std::max(0, ((R - 128) % 80) - 16));
+            sy.resize((size_t)E);
+            cf rot_even = {1.f, 0.f};
+            for (int k = 0; k < E; ++k) {
+                int nn = k / 64, m = k % 64;
+                int j = F.frame_start + (nn < 2 ? 64 * nn + m : 128 + 80 * (nn - 2) + 16 + m);
+                int64_t src = B.t + j - 16;
+                cf xs = src >= 0 ? x[src] : cf{0.f, 0.f};
+                cf rot;
+                if ((m & 1) == 0) { rot_even = crot(delta * (float)j); rot = rot_even; }
+                else rot = cmul(rot_even, w1);
+                sy[(size_t)k] = cmul(xs, rot);
+            }
         }
         /* a later tag sends sync_long through RESET, which zero-pads the open symbol; the
          * last burst of a finished stream never sees that tag, its partial symbol is never
@@ -915,7 +921,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
             double er = 0;
             if (nn >= 2) {
                 cf s = {0.f, 0.f};
-                for (int q = 0; q < 4; ++q) s = cadd(s, cmul(cf{prev_pil[q].re, -prev_pil[q].im}, pil[q]));
+                for (int q = 0; q < 4; ++q) s = wdm_cmacc(s, pil[q], prev_pil[q]);
                 er = (double)wdm_atan2f(s.im, s.re);
                 er *= cfg.bw / (2 * M_PI * cfg.freq * 80);
             }
@@ -1139,5 +1145,9 @@ void orc_rx_copy(const orc_rx_result *r, orc_frame *frames, uint8_t *rows, float
 void orc_rx_copy_soft(const orc_rx_result *r, int8_t *soft) { std::memcpy(soft, r->r.soft.data(), r->r.soft.size()); }
 int orc_viterbi_soft(const int8_t *dep, int n_avail, int n_bits, int ntb, uint8_t *out_bits) { return viterbi_soft(dep, n_avail, n_bits, ntb, out_bits); }
 void orc_rx_free(orc_rx_result *r) { delete r; }
+void orc_detmath(int fn, const float *a, const float *b, const float *c, const float *d, float *o0, float *o1, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) wdm_selftest(fn, a[i], b[i], c[i], d[i], &o0[i], &o1[i]);
+}
 
 } // extern "C"

@@ -108,6 +108,8 @@ void orc_rx_copy(const orc_rx_result *r, orc_frame *frames, uint8_t *rows, float
 void orc_rx_copy_soft(const orc_rx_result *r, int8_t *soft);
 int  orc_viterbi_soft(const int8_t *depunctured, int n_avail, int n_bits, int ntraceback, uint8_t *out_bits);
 void orc_rx_free(orc_rx_result *r);
+/* element-wise evaluation of the numerical contract (include/wifi_detmath.h wdm_selftest) for tests/test_detmath.py */
+void orc_detmath(int fn, const float *a, const float *b, const float *c, const float *d, float *o0, float *o1, int64_t n);
 
 #ifdef __cplusplus
 }

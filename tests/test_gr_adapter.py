@@ -102,7 +102,7 @@ def test_hier_block_ports_against_the_oracle(O):
         ref = O.rx(y, algo=1, want_carrier=True)
         pdus = [g.pdu_to_python(p) for p in blk.rx.published["mac_out"]]
         assert [p[1] for p in pdus] == ref.pdus() == [p[:-4] for p in psdus]
-        assert all(set(p[0]) == {"snr", "nomfreq", "freqofs", "dlt"} and p[0]["dlt"] == 105 for p in pdus)
+        assert all(set(p[0]) == {"snr", "nomfreq", "freqofs", "dlt", "encoding"} and p[0]["dlt"] == 105 for p in pdus)
         car = np.array([pmt.cdr(c) for c in blk.rx.published["carrier"]])
         ok = np.nonzero(ref.frames["crc_ok"])[0]
         want = np.concatenate([ref.carrier[int(ref.frames["row_off"][i]):int(ref.frames["row_off"][i]) + int(ref.frames["n_rows"][i])] for i in ok])
