@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--workload", default="c3", choices=["c3", "c2"], help="c3 = BASELINE configs[2] (metric workload); c2 = configs[1]: one 10 s 20 Msps stream, 16-QAM 1/2, CFO + 3-tap multipath")
     ap.add_argument("--soft", action="store_true", help="soft-decision mode (extension, DESIGN.md 9)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-time-shard", action="store_true", help="skip the time-sharded section (one capture cut into overlapping segments across the ranks)")
+    ap.add_argument("--ts-frames", type=int, default=32768, help="frames of the single-link capture the time-sharded section cuts across the ranks")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8192, help="frames of the cpu_baseline sample")
     return ap.parse_args()
@@ -136,6 +138,81 @@ def build_capture(h, W, torch, n_links, fpl, seed):
     return cap, link_off, psdus
 
 
+def run_time_sharded(W, torch, dist, args, rank, world, local):
+    """SURVEY 8e (ii) on hardware: ONE long single-link capture (the same on every rank: the TX chain and the Philox channel
+    are deterministic) is cut into `world` overlapping segments (sharding.shard_stream, overlap 44128 samples); every rank
+    decodes its segment, the frame records are all-gathered over NCCL, every rank checks that it joined the sequential
+    receiver's state (sharding.reconcile; a rank that did not decodes again from a known state), frames are owned by the
+    segment whose core region holds their trigger.  Rank 0 also decodes the whole capture alone and asserts that the union
+    of the owned frames IS that table.  Strong scaling: the total work is fixed."""
+    S = W.sharding
+    fpl = args.ts_frames
+    flen = frame_samples()
+    n_total = LEAD + fpl * (flen + GAP)
+    h = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=n_total + 1024, max_frames=fpl + 1024, soft_decision=args.soft)
+    cap, link_off, _ = build_capture(h, W, torch, 1, fpl, seed=2000)          # identical on every rank
+    torch.cuda.synchronize()
+    segs = S.shard_stream(n_total, world)
+    dev = torch.device("cuda", local)
+    decode_ms = [0.0]
+
+    def decode(lo, end, st, final):
+        off = np.array([lo, end], np.uint64)
+        if st is None:
+            h.rx_batch_dev(cap.data_ptr(), off, final=final, fetch=False)
+        else:
+            state = np.zeros(1, W.wifi_b200.LINK_STATE_DTYPE)
+            state["min_pos"], state["fo_carry"], state["hist"] = st["min_pos"], st["fo_carry"], st["hist"]
+            h.rx_batch_dev_state(cap.data_ptr(), off, state, final=final, fetch=False)
+        decode_ms[0] += sum(h.stage_times().values())
+        return h.frames()                                                        # 96 bytes per trigger; PSDUs stay on the device
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    reps, warm = 5, 2
+    own = owned_all = None
+    rounds = 0
+    for it in range(warm + reps):
+        if it == warm:
+            barrier()
+            decode_ms[0] = 0.0
+            t0 = time.perf_counter()
+        own, owned_all, rounds = S.reconcile(decode, segs, rank, n_total, device=dev if world > 1 else None)
+    barrier()
+    t_sh = (time.perf_counter() - t0) / reps
+    dec_sh = decode_ms[0] / reps
+    # the sequential answer: the whole capture in one call on one GPU (rank 0 checks, every rank times it)
+    for _ in range(warm):
+        h.rx_batch_dev(cap.data_ptr(), link_off, final=True, fetch=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        h.rx_batch_dev(cap.data_ptr(), link_off, final=True, fetch=False)
+        whole = h.frames()
+    t_one = (time.perf_counter() - t0) / reps
+    equal = None
+    if rank == 0:
+        equal = bool(np.array_equal(np.concatenate(owned_all), S.records(whole, 0)))
+    tv = torch.tensor([t_sh, dec_sh, t_one], dtype=torch.float64, device="cuda")
+    cnt = S.allreduce_stats(np.array([len(own), int(own[:, S.CRC].sum())], np.int64), device=dev if world > 1 else None)
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    h.close()
+    del cap
+    assert equal is not False, "time-sharded frame table differs from the single-GPU table"      # after the collectives: no rank is left waiting
+    t_sh, dec_sh, t_one = [float(v) for v in tv.tolist()]
+    return {"capture": "one link, %d frames, %d samples (%.2f GB), the same on every rank" % (fpl, n_total, n_total * 8 / 1e9),
+            "ranks": world, "overlap_samples": S.OVERLAP, "sharded_ms": 1e3 * t_sh, "sharded_decode_device_ms": dec_sh,
+            "single_gpu_ms": 1e3 * t_one, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
+            "value_msamples_per_s": n_total / t_sh / 1e6, "frames_owned_total": int(cnt[0]), "crc_ok_total": int(cnt[1]),
+            "re_decode_rounds": rounds, "union_equals_single_gpu_table": equal, "scaling": "strong",
+            "collective": "NCCL all_gather of the frame records (12 x int64 per frame) + counter all_reduce" if world > 1 else "none (one rank)",
+            "timing": "wall clock around sharding.reconcile (decode, record all-gather, join check), barrier + synchronize on both sides, max over ranks, mean of %d" % reps}
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -189,27 +266,48 @@ def config_dict(args, n_links, fpl):
             "parallelism": "links sharded across GPUs, no data-path collective"}
 
 
+def build_capture_cpu(O, n_links, fpl, seed):
+    """The b200 arm's capture recipe (build_capture) restated with the oracle's TX and Philox channel: the same frame
+    layout, per-frame CFO / phase (/ taps) drawn the same way, the same noise convention."""
+    n = n_links * fpl
+    flen = frame_samples()
+    stride = flen + GAP
+    link_len = LEAD + fpl * stride
+    psdus = make_psdus(n, seed)
+    rng = np.random.default_rng(seed + 1)
+    cfo = rng.uniform(-0.0025 * 2 * np.pi, 0.0025 * 2 * np.pi, n)
+    ph0 = rng.uniform(-np.pi, np.pi, n)
+    if TAPS:
+        p1, p2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+        nrm = 1.0 / np.sqrt(1 + 0.16 + 0.04)
+    sigma = 0.6 * 10 ** (-SNR_DB / 20)
+    x = np.zeros(n_links * link_len, np.complex64)
+    for l in range(n_links):
+        x[l * link_len:l * link_len + LEAD] = O.channel(np.zeros(LEAD, np.complex64), n0=l * link_len, gain=0.6, noise_sigma=sigma, seed=seed)
+    buf = np.zeros(stride, np.complex64)
+    for f in range(n):
+        buf[:flen] = O.tx_frame(psdus[f], ENC, 1 + f % 127)
+        taps = ((0, 1.0),)
+        if TAPS:
+            taps = ((0, nrm), (1, 0.4 * nrm * np.exp(1j * p1[f])), (3, 0.2 * nrm * np.exp(1j * p2[f])))
+        o = (f // fpl) * link_len + LEAD + (f % fpl) * stride
+        x[o:o + stride] = O.channel(buf, n0=o, gain=0.6, cfo=float(cfo[f]), phase0=float(ph0[f]), noise_sigma=sigma, taps=taps, seed=seed)
+    off = (np.arange(n_links) * link_len).astype(np.int64)
+    return x, off, np.full(n_links, link_len, np.int64), psdus
+
+
 def run_reference(args, out_fd):
-    """CPU arm: the oracle (port of the reference algorithm) on all host threads, bounded sample."""
+    """CPU arm: the oracle (a port of the reference algorithm; gr-ieee802-11 itself cannot be built here) on all host
+    threads.  Each step is a BOUNDED sample of the b200 arm's workload -- the same frames, gaps, SNR and per-frame CFO,
+    one link per host thread, fewer frames per link -- and the line's config says what ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
     threads = os.cpu_count() or 1
-    flen = frame_samples()
-    fpl = 96
+    fpl = min(args.frames_per_link, 96)
     n_links = max(threads, 1)
-    rng = np.random.default_rng(0)
-    # one link built with the oracle TX + channel, replicated with different noise per link
-    psdus = make_psdus(fpl, 0)
-    parts = [np.zeros(LEAD, np.complex64)]
-    for i, p in enumerate(psdus):
-        parts += [O.tx_frame(p, ENC, 1 + i % 127), np.zeros(GAP, np.complex64)]
-    clean = np.concatenate(parts).astype(np.complex64)
-    links = [O.channel(clean, gain=0.6, cfo=float(rng.uniform(-0.015, 0.015)), noise_sigma=0.6 * 10 ** (-SNR_DB / 20), seed=l) for l in range(n_links)]
-    x = np.concatenate(links)
-    off = np.arange(n_links) * clean.size
-    ln = np.full(n_links, clean.size)
+    x, off, ln, _ = build_capture_cpu(O, n_links, fpl, seed=1000)
     times = []
     ok = 0
     for it in range(args.warmup + args.steps):
@@ -221,14 +319,19 @@ def run_reference(args, out_fd):
             ok = int(r.frames["crc_ok"].sum())
     t = float(np.sum(times))
     msps = x.size * len(times) / t / 1e6
+    cfg = config_dict(args, n_links, fpl)
+    cfg["l2_policy"] = "CPU arm: not applicable"
+    cfg["parallelism"] = "one link per host thread (%d threads)" % threads
+    cfg["bounded_sample_of"] = "the b200 arm's %d links x %d frames per GPU: same frame layout, SNR, per-frame CFO and phase, %d links x %d frames here" % (
+        args.links, args.frames_per_link, n_links, fpl)
     line = {"impl": "reference", "metric": "rx_msamples_per_s", "value": msps, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
-            "config": config_dict(args, args.links, args.frames_per_link),
+            "config": cfg,
             "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": "port",
                              "sample": "%d links x %d frames (%d samples) per step, one link per host thread" % (n_links, fpl, x.size)},
             "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "crc_ok_per_step": ok, "frames_per_step": n_links * fpl}
     line["decoded_mbps"] = ok * (PSDU_LEN - 4) * 8 / (t / len(times)) / 1e6
     _emit(out_fd, line)
 
@@ -452,6 +555,15 @@ def main():
             e2e["streaming"] = {"error": repr(ex)}
         del host
 
+    tsh = None
+    if not args.no_time_shard and args.workload == "c3":
+        try:
+            tsh = run_time_sharded(W, torch, dist, args, rank, world, local)
+        except AssertionError:
+            raise
+        except Exception as ex:       # the headline must not depend on this section
+            tsh = {"error": repr(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -466,40 +578,60 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
     n_jobs = st_ok if st_ok else n
-    # algorithmic bytes per launch of the dominant kernel (Viterbi): N_CBPS coded bits in + PSDU bytes out per frame
     n_sym_w = -(-(16 + 8 * PSDU_LEN + 6) // N_DBPS)
-    vit_alg = n * (n_sym_w * {216: 288, 96: 192}[N_DBPS] / 8 + PSDU_LEN)
+    n_cbps = {216: 288, 96: 192}[N_DBPS]
     vit_ms = stage_ms.get("viterbi", 0.0)
-    achieved = vit_alg / (vit_ms * 1e-3) / 1e9 if vit_ms > 0 else 0.0
-    # integer work of the kernel: 64 ACS x 4 int-ops per decoded bit
-    dec_bits = n * (PSDU_LEN + 2) * 8
-    traffic, alu_pct = None, None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of k_viterbi from the committed ncu --set full capture (same workload)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_top_kernels.json")))
-        for kk in prof["kernels"]:
-            if kk["kernel"] == "k_viterbi":
-                u = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-                traffic = sum(float(kk[m]["value"]) * u[kk[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-                alu_pct = float(kk["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]["value"])
+    # ---- dominant kernel (k_viterbi): bound by the integer ALU pipe, not by memory.  achieved = the
+    # kernel's alu-pipe warp-instructions (ncu's dynamic count per decoded frame of this workload, committed under
+    # profiles/ -- the count is a property of the code and the frame length, not of the run) x frames decoded here
+    # / the kernel's CUDA-event time measured in this run; peak = the alu pipe's issue rate measured in this run by the
+    # library's probe kernel (independent LOP3 chains on every SM).
+    alu_peak, alu_probe_ms = h.alu_peak(8192)
+    pipe = None
+    try:
+        pipe = json.load(open(os.path.join(ROOT, "profiles", "r02_viterbi_pipe_counts.json")))
     except Exception:
         pass
-    roof = {"kernel": "k_viterbi", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": vit_alg, "ms_per_launch": vit_ms,
-            "note": "integer-ALU-bound kernel (ncu, profiles/r01_ncu_full_top_kernels.json: sm__inst_executed_pipe_alu %s%% of peak, DRAM about 1%%): %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % ("%.0f" % alu_pct if alu_pct is not None else "?", dec_bits * 256 / (vit_ms * 1e-3) / 1e12 if vit_ms else 0.0)}
-    # the streaming front-end (sync_short autocorrelation + plateau flags) is the path's HBM-side kernel: it reads the
-    # whole capture once (8 B per sample) and writes one flag bit per sample
-    det_ms = stage_ms.get("detect", 0.0)
-    det_alg = n_samples * (8 + 1.0 / 8)
-    roof_det = {"kernel": "k_detect", "bound": "hbm", "achieved": det_alg / (det_ms * 1e-3) / 1e9 if det_ms else 0.0, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (det_alg / (det_ms * 1e-3) / 1e9 / hbm_peak) if det_ms else 0.0, "algorithmic_bytes_per_launch": det_alg, "ms_per_launch": det_ms,
-                "note": "second-largest streaming stage; issue-bound by the oracle's sequential running sums (DESIGN.md 4)"}
+    dec_bits = n * (PSDU_LEN + 2) * 8
+    vit_alg_bytes = n * (n_sym_w * n_cbps / 8 + PSDU_LEN)
+    if pipe and vit_ms > 0 and pipe.get("psdu_len") == PSDU_LEN and pipe.get("n_dbps") == N_DBPS:
+        alu_inst = pipe["alu_warp_inst_per_frame"] * st_frames
+        achieved = alu_inst / (vit_ms * 1e-3)
+        roof = {"kernel": "k_viterbi", "bound": "alu", "achieved": achieved / 1e9, "peak": alu_peak / 1e9, "unit": "Gwarp-inst/s",
+                "frac": achieved / alu_peak, "traffic": pipe.get("dram_bytes_per_frame", 0) * st_frames or None,
+                "peak_source": "measured in this run: wifi_b200_alu_peak (LOP3 issue probe, %.2f ms)" % alu_probe_ms,
+                "instruction_count_source": "committed ncu (%s): smsp__inst_executed_pipe_alu.sum per decoded frame" % pipe.get("source", "profiles/"),
+                "alu_warp_inst_per_launch": alu_inst, "ms_per_launch": vit_ms,
+                "algorithmic_bytes_per_launch": vit_alg_bytes, "hbm_frac_for_reference": vit_alg_bytes / (vit_ms * 1e-3) / 1e9 / hbm_peak,
+                "note": "one trellis per thread, 64 byte-packed path metrics in 16 registers; %.2f Tint-op/s algorithmic (256 int-op per decoded bit, four states per 32-bit word)" % (
+                    dec_bits * 256 / (vit_ms * 1e-3) / 1e12)}
+    else:
+        roof = {"kernel": "k_viterbi", "bound": "alu", "achieved": None, "peak": alu_peak / 1e9, "unit": "Gwarp-inst/s", "frac": None, "traffic": None,
+                "peak_source": "measured in this run: wifi_b200_alu_peak", "ms_per_launch": vit_ms,
+                "note": "no committed instruction count for this workload shape (profiles/r02_viterbi_pipe_counts.json is for the default workload)"}
+    # ---- the HBM-side stages: algorithmic bytes per launch / CUDA-event time of this run, against the measured copy peak
+    n_frames_w, n_rows_w = st_frames, st_frames * n_sym_w
+    stage_alg = {
+        "detect": ("k_detect", n_samples * (8 + 1.0 / 8 + 1.0 / 512)),
+        "sync_long": ("k_sync_long", n_frames_w * ((320 + 63) * 8 + 16)),
+        "demod_head": ("k_demod phase 0", n_frames_w * (3 * 64 * 8 + 624)),
+        "demod_data": ("k_demod phase 1", n_rows_w * (64 * 8 + 48 + (N_DBPS // 8) * 4)),
+    }
+    roof_stages = {}
+    for key, (kname, bytes_) in stage_alg.items():
+        ms = stage_ms.get(key, 0.0)
+        gbs = bytes_ / (ms * 1e-3) / 1e9 if ms else 0.0
+        roof_stages[key] = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                            "algorithmic_bytes_per_launch": bytes_, "ms_per_launch": ms}
+    roof_det = dict(roof_stages["detect"], peak_source=peak_src,
+                    note="the streaming front-end reads the whole capture once (8 B per sample) and writes one flag bit per sample")
     path_alg = n_samples * 8 + n * PSDU_LEN
     step_ms = 1e3 * elapsed_max / args.steps
     line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "decoded_mbps": mbps, "frames_per_step": tot_frames, "crc_ok_per_step": tot_ok,
             "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 13 * args.steps,   # detect, select_spec, select, reserve, frames_init, sync_long, demod x2, signal, plan_fast, plan, pack, viterbi
-            "roofline": roof, "roofline_frontend": roof_det, "stage_ms": stage_ms, "tx": dict(TX_INFO),
+            "roofline": roof, "roofline_frontend": roof_det, "roofline_stages": roof_stages, "stage_ms": stage_ms, "tx": dict(TX_INFO), "time_sharded": tsh,
             "path_hbm": {"algorithmic_GBps": path_alg / (step_ms * 1e-3) / 1e9, "frac_of_peak": path_alg / (step_ms * 1e-3) / 1e9 / hbm_peak}}
     if not args.no_cpu and world == 1:
         from oracle import oracle as O

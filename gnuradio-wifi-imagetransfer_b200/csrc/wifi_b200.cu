@@ -196,7 +196,8 @@ struct wifi_b200 {
     const cf *cur_iq = nullptr;
     std::vector<LinkDesc> h_links;
     int64_t n_frames = 0, n_jobs = 0, n_rows = 0, n_samples = 0, n_triggers = 0;
-    bool host_mirror = false;      // frames/psdu already copied to host
+    bool host_mirror = false;      // frame table already copied to host
+    bool psdu_mirror = false;      // PSDU store already copied to host
     wifi_b200_frame *h_frames = nullptr;   // pinned
     uint8_t *h_psdu = nullptr;             // pinned
     float *h_iq = nullptr;                 // pinned staging for host input
@@ -377,7 +378,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
     h->cur_iq = iq;
     h->n_frames = h->n_jobs = h->n_rows = 0;
     h->n_samples = total;
-    h->host_mirror = false;
+    h->host_mirror = h->psdu_mirror = false;
     bool h2d_marked = h->ev_used[ST_H2D];
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
     h->ev_used[ST_H2D] = h2d_marked;
@@ -469,7 +470,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
         h->err = "receive pipeline reported an internal overflow";
         return WIFI_E_OVERFLOW;
     }
-    h->host_mirror = mirror;
+    h->host_mirror = h->psdu_mirror = mirror;
     // stage times: difference between consecutive recorded events
     int prev = -1;
     for (int i = 0; i <= ST_COUNT; ++i) {
@@ -484,9 +485,17 @@ int fetch_frames(wifi_b200 *h)
 {
     if (h->host_mirror || h->n_frames == 0) return WIFI_OK;
     CK(cudaMemcpyAsync(h->h_frames, h->d_frames, h->n_frames * sizeof(wifi_b200_frame), cudaMemcpyDeviceToHost, h->stream));
-    if (h->n_jobs > 0) CK(cudaMemcpyAsync(h->h_psdu, h->d_psdu, (size_t)h->n_jobs * PSDU_STRIDE, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->host_mirror = true;
+    return WIFI_OK;
+}
+
+int fetch_psdus(wifi_b200 *h)
+{
+    if (h->psdu_mirror || h->n_jobs == 0) return WIFI_OK;
+    CK(cudaMemcpyAsync(h->h_psdu, h->d_psdu, (size_t)h->n_jobs * PSDU_STRIDE, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->psdu_mirror = true;
     return WIFI_OK;
 }
 
@@ -861,6 +870,28 @@ int wifi_b200_rx_batch_dev(wifi_b200_t *h, const float *iq_dev, const uint64_t *
     return rc;
 }
 
+int wifi_b200_rx_batch_dev_state(wifi_b200_t *h, const float *iq_dev, const uint64_t *link_off, int n_links, int final,
+                                 const wifi_b200_link_state *state)
+{
+    if (!h || !iq_dev || !state) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    int rc = set_links(h, link_off, n_links, final);
+    if (rc) return rc;
+    for (int l = 0; l < n_links; ++l) {
+        if (state[l].hist < 0 || state[l].hist > 256 || (uint64_t)state[l].hist > link_off[l] || state[l].min_pos < 0) {
+            h->err = "bad link state (hist must be 0..256 samples that exist in front of the link)";
+            return WIFI_E_ARG;
+        }
+        LinkDesc &L = h->h_links[l];
+        L.hist = state[l].hist;
+        L.min_pos = state[l].min_pos;
+        L.fo_carry = state[l].fo_carry;
+    }
+    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
+    return run_rx(h, (const cf *)iq_dev, false);
+}
+
 int wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int final)
 {
     if (!h || !iq_host) return WIFI_E_ARG;
@@ -980,7 +1011,7 @@ int wifi_b200_rx_psdus(wifi_b200_t *h, uint8_t *store, size_t cap)
     std::lock_guard<std::mutex> g(h->mu);
     cudaSetDevice(h->device);
     if (cap < (size_t)h->n_jobs * PSDU_STRIDE) return WIFI_E_OVERFLOW;
-    int rc = fetch_frames(h);
+    int rc = fetch_psdus(h);
     if (rc) return rc;
     memcpy(store, h->h_psdu, (size_t)h->n_jobs * PSDU_STRIDE);
     return WIFI_OK;

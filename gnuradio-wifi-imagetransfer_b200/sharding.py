@@ -1,7 +1,11 @@
 """Multi-GPU host logic: the path shards into independent units, so there is no
 data-path collective.  Links are dealt round-robin to ranks; one long capture is cut into
 overlapping segments, each frame is owned by the segment whose core region holds its trigger.
-Only counters cross ranks (one all-reduce over NCCL on GPUs, gloo in the CPU tests)."""
+What crosses ranks is small: one all-reduce of a counter vector and, for time sharding, an
+all-gather of the per-segment frame records with which every rank checks that its segment joined
+the sequential receiver's state before its core region began (`reconcile`); a rank whose check
+fails decodes again from a point where that state is known (NCCL over NVLink on GPUs, gloo in the
+CPU tests)."""
 import numpy as np
 
 # sync_short MAX_SAMPLES + sync_long window + FFT + MIN_GAP look-back + window warm-up
@@ -55,3 +59,234 @@ def allreduce_stats(vec, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Time sharding, exactness.  A segment decoded from `start` (OVERLAP before its core) has the sequential receiver's
+# frames in its core region iff its state at `core_start` is the sequential one: sync_short's last trigger (MIN_GAP
+# rule), sync_long's carried frequency offset, decode_mac's collection.  With idle air between frames all three join
+# within a frame or two; back-to-back traffic without a single idle gap can keep two trigger chains apart for ever.
+# `boundary_check` decides from the frame records alone whether the segment joined; `resume_point` gives the place
+# and the state from which to decode again when it did not.
+# A frame record is one row of 12 int64 (what the all-gather moves); column names:
+REC_NAMES = ("trigger", "burst_len", "found", "freq_bits", "sig_ok", "encoding", "length", "frame_symbols", "n_rows", "accepted", "decoded", "crc_ok")
+TRIG, BURST, FOUND, FREQ, SIG, ENC, LEN, FSYM, NROWS, ACC, DEC, CRC = range(12)
+REC_FIELDS = len(REC_NAMES)
+SS_MIN_GAP = 480
+HIST = 128          # front-end history a resumed segment is given (two FE_CHUNKs: the running sums re-seed inside it)
+
+
+def records(frames, offset):
+    """Frame table -> int64 [n, 12] records ordered by absolute trigger position (freq_long travels as its bit pattern)."""
+    r = np.empty((len(frames), REC_FIELDS), np.int64)
+    for k, name in enumerate(REC_NAMES):
+        if name == "trigger":
+            r[:, k] = frames["trigger"]
+            r[:, k] += offset
+        elif name == "freq_bits":
+            r[:, k] = np.ascontiguousarray(frames["freq_long"], np.float32).view(np.int32)
+        else:
+            r[:, k] = frames[name]
+    if len(r) > 1 and np.any(np.diff(r[:, TRIG]) < 0):
+        r = r[np.argsort(r[:, TRIG], kind="stable")]
+    return r
+
+
+def _regular(r):
+    """decode_mac's state is closed behind such a frame: own tag accepted, all of its symbols delivered by its own burst."""
+    return (r[:, SIG] == 1) & (r[:, DEC] == 1) & (r[:, ACC] == 1) & (r[:, NROWS] >= r[:, FSYM]) & (r[:, FSYM] > 0)
+
+
+def open_state(rec):
+    """decode_mac's state behind the last record (the machine of decode_mac.cc / k_plan, replayed from the last closed
+    point): trigger of the frame whose tag is still pending or whose symbol collection is still open, or None."""
+    reg = _regular(rec)
+    idx = np.nonzero(reg[:-1] & reg[1:])[0] if len(rec) >= 2 else np.zeros(0, int)
+    start = int(idx[-1]) + 2 if len(idx) else 0
+    cur, copied, need, pending = -1, 0, 0, -1
+    for i in range(start, len(rec)):
+        r = rec[i]
+        if r[SIG] != 1:
+            continue
+        if r[NROWS] == 0:
+            if pending < 0:
+                pending = i
+            continue
+        tag = pending if pending >= 0 else i
+        pending = -1
+        if rec[tag, FSYM] <= 511 and rec[tag, LEN] <= 1528:
+            cur, copied, need = tag, 0, int(rec[tag, FSYM])
+        if cur < 0 or copied >= need:
+            continue
+        copied += min(int(r[NROWS]), need - copied)
+    if pending >= 0:
+        return int(rec[pending, TRIG])
+    if cur >= 0 and copied < need:
+        return int(rec[cur, TRIG])
+    return None
+
+
+def _f32_bits(x):
+    return int(np.array([x], np.float32).view(np.int32)[0])
+
+
+def _bits_f32(b):
+    return float(np.array([b], np.int64).astype(np.int32).view(np.float32)[0])
+
+
+def boundary_check(truth, local, carry_bits, seg_start, core_start):
+    """truth: records of the sequential receiver's frames with trigger < core_start (what the lower ranks own);
+    local: this segment's records; carry_bits: the sync_long frequency offset the segment's decode started with.
+    True iff the segment's receiver is in the sequential state at core_start:
+      * the two tables end (before core_start) with the same frames and that common tail holds two consecutive regular
+        frames (behind the first no tag is pending, behind the second the collection is closed), or
+      * the air was silent over the whole look-back, decode_mac was closed before it and the segment started with the
+        frequency offset the sequential receiver carried into it."""
+    t = truth[truth[:, TRIG] < core_start]
+    l = local[local[:, TRIG] < core_start]
+    if len(l) == 0 and (len(t) == 0 or t[-1, TRIG] < seg_start):
+        if len(t) == 0:
+            return carry_bits == _f32_bits(0.0)
+        last_sig = t[t[:, SIG] == 1]
+        closed = len(last_sig) == 0 or bool(_regular(last_sig[-1:])[0])
+        return closed and carry_bits == int(t[-1, FREQ])
+    m = min(len(t), len(l))
+    if m < 2:
+        return False
+    same = np.all(t[len(t) - m:] == l[len(l) - m:], axis=1)[::-1]       # common tail, newest frame first
+    n = m if same.all() else int(np.argmin(same))
+    if n < 2:
+        return False
+    reg = _regular(t[len(t) - n:])
+    return bool(np.any(reg[:-1] & reg[1:]))
+
+
+def resume_point(truth, seg_start, core_start):
+    """Where to decode again from, and with which state.  Returns (sample index `lo` the decode starts at -- its history
+    lies in front of it --, state fields, records to put in front of the new table) or None.
+      * silent look-back: the same start, carrying the sequential receiver's frequency offset;
+      * else the last two consecutive regular frames (F1, F2) of the sequential table before core_start: start at
+        F2's chunk, first possible trigger F2 itself, frequency offset as left by F1."""
+    t = truth[truth[:, TRIG] < core_start]
+    if len(t) and t[-1, TRIG] < seg_start:
+        last_sig = t[t[:, SIG] == 1]
+        if len(last_sig) == 0 or bool(_regular(last_sig[-1:])[0]):
+            return seg_start, {"min_pos": max(0, int(t[-1, TRIG]) + SS_MIN_GAP + 1 - seg_start), "fo_carry": _bits_f32(t[-1, FREQ]),
+                               "hist": min(HIST, seg_start)}, t[:0]
+    reg = _regular(t)
+    idx = np.nonzero(reg[:-1] & reg[1:])[0] if len(t) >= 2 else np.zeros(0, int)
+    if len(idx) == 0:
+        return None
+    f1, f2 = t[idx[-1]], t[idx[-1] + 1]
+    start = int(f2[TRIG]) // FE_CHUNK * FE_CHUNK
+    return start, {"min_pos": int(f2[TRIG]) - start, "fo_carry": _bits_f32(f1[FREQ]), "hist": min(HIST, start)}, t[idx[-1]:idx[-1] + 1]
+
+
+def gather_records(rec, device=None):
+    """All ranks' record arrays (NCCL all_gather of padded int64 tensors on GPUs, gloo on CPU); list indexed by rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [rec]
+    world = dist.get_world_size()
+    n = torch.tensor([len(rec)], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    buf = torch.zeros((cap, REC_FIELDS), dtype=torch.int64, device=device)
+    if len(rec):
+        buf[:len(rec)] = torch.from_numpy(np.ascontiguousarray(rec)).to(buf.device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    return [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
+
+
+def _with_header(rec, lo, carry_bits):
+    """First row of what a rank sends: where its decode started and the frequency offset it started with."""
+    h = np.zeros((1, REC_FIELDS), np.int64)
+    h[0, TRIG], h[0, BURST], h[0, FREQ] = -1, lo, carry_bits
+    return np.concatenate([h, rec])
+
+
+def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gather=None):
+    """Time-sharded receive with an exact result.  `decode(lo, end, state, final)` runs this rank's receiver over
+    samples [lo, end) of the capture -- state None: a stream start at lo; else the wifi_b200_link_state fields, with
+    state["hist"] samples of history in front of lo (the callee reads them from lo - hist) -- and returns its frame
+    table (triggers relative to lo).
+    Every rank decodes its segment; the records are all-gathered; every rank walks the same check from rank 0 upwards;
+    the lowest rank that has not joined the sequential state decodes again from a known one; repeated until all have.
+    Returns (records this rank owns, every rank's owned records, number of re-decoding rounds)."""
+    seg = segs[rank]
+
+    def decode_closed(lo, st):
+        """Decode [lo, end); while a frame this rank owns leaves decode_mac open at the end of the segment (a tag pending,
+        a collection short of symbols: state the sequential receiver keeps for as long as it takes), decode further."""
+        end, grow = seg["end"], OVERLAP
+        while True:
+            rec = records(decode(lo, end, st, end == n_samples), lo)
+            opener = None if end == n_samples else open_state(rec)
+            if opener is None or opener >= seg["core_end"]:
+                return rec
+            end, grow = min(n_samples, end + grow), 2 * grow
+
+    lo, carry = seg["start"], _f32_bits(0.0)
+    local = decode_closed(lo, None)
+    rounds = 0
+    while True:
+        allrec = (gather or gather_records)(_with_header(local, lo, carry), device)
+        truth = np.zeros((0, REC_FIELDS), np.int64)
+        bad = None
+        owned_all = []
+        for r, sr in enumerate(segs):
+            hdr, rec = allrec[r][0], allrec[r][1:]
+            if r > 0 and not boundary_check(truth, rec, int(hdr[FREQ]), int(hdr[BURST]), sr["core_start"]):
+                bad = r
+                break
+            own = rec[(rec[:, TRIG] >= sr["core_start"]) & (rec[:, TRIG] < sr["core_end"])]
+            owned_all.append(own)
+            truth = np.concatenate([truth, own])
+        if bad is None:
+            return owned_all[rank], owned_all, rounds
+        rounds += 1
+        if max_rounds is not None and rounds > max_rounds:
+            raise RuntimeError("time sharding did not reconcile in %d rounds" % max_rounds)
+        if bad == rank:
+            rp = resume_point(truth, seg["start"], seg["core_start"])
+            if rp is None:                                # nothing is known but the start of the capture
+                lo, carry = 0, _f32_bits(0.0)
+                local = decode_closed(0, None)
+            else:
+                lo, st, front = rp
+                carry = _f32_bits(st["fo_carry"])
+                local = np.concatenate([front, decode_closed(lo, st)])
+
+
+def simulate_ranks(decode, segs, n_samples):
+    """All ranks of `reconcile` in one process (threads and a barrier where the all-gather is): what the single-GPU
+    tests use.  Returns (every rank's owned records, rounds)."""
+    import threading
+    world = len(segs)
+    slots, out, bar, errs = [None] * world, [None] * world, threading.Barrier(world), []
+
+    def run(rank):
+        def gather(rec, device=None):
+            slots[rank] = rec
+            bar.wait()
+            res = list(slots)
+            bar.wait()
+            return res
+        try:
+            out[rank] = reconcile(decode, segs, rank, n_samples, gather=gather, max_rounds=world + 1)
+        except Exception as e:        # a failing rank must not leave the others at the barrier
+            errs.append(e)
+            bar.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out[0][1], out[0][2]

@@ -41,6 +41,9 @@ CHANSEG_DTYPE = np.dtype([
 assert CHANSEG_DTYPE.itemsize == C.sizeof(ChanSeg), (CHANSEG_DTYPE.itemsize, C.sizeof(ChanSeg))
 
 
+LINK_STATE_DTYPE = np.dtype([("min_pos", "<i8"), ("fo_carry", "<f4"), ("hist", "<i4")], align=True)
+
+
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_int64), ("frames_detected", C.c_int64), ("signal_ok", C.c_int64), ("decoded", C.c_int64),
                 ("crc_ok", C.c_int64), ("pdu_bytes", C.c_int64), ("per_mcs_crc_ok", C.c_int64 * 8)]
@@ -56,7 +59,7 @@ EXPORTS = [
     "wifi_b200_abi_version", "wifi_b200_device_count", "wifi_b200_create", "wifi_b200_destroy", "wifi_b200_set_param",
     "wifi_b200_get_param", "wifi_b200_last_error", "wifi_b200_strerror", "wifi_b200_stream", "wifi_b200_sync",
     "wifi_b200_mac_frame", "wifi_b200_n_sym", "wifi_b200_frame_samples", "wifi_b200_tx", "wifi_b200_tx_dev",
-    "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
+    "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_dev_state", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_rx_push_links", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
     "wifi_b200_selftest_detmath", "wifi_b200_alu_peak",
@@ -94,6 +97,7 @@ def lib():
         L.wifi_b200_channel.argtypes = [vp, vp, i64, vp, i64, vp, C.c_int]
         for f in ("wifi_b200_rx_batch", "wifi_b200_rx_batch_dev"):
             getattr(L, f).argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.wifi_b200_rx_batch_dev_state.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         L.wifi_b200_rx_batch_sc16.argtypes = [vp, vp, C.c_float, vp, C.c_int, C.c_int]
         L.wifi_b200_rx_counts.argtypes = [vp, vp, vp, vp, vp]
         L.wifi_b200_rx_frames.argtypes = [vp, vp, i64]
@@ -274,6 +278,14 @@ class Handle:
         self._ck(self._L.wifi_b200_rx_batch_dev(self._h, C.c_void_p(iq_ptr), _p(lo), lo.size - 1, int(final)))
         return self.results() if fetch else None
 
+    def rx_batch_dev_state(self, iq_ptr, link_off, state, final=True, fetch=False):
+        """Resumed streams: `state` is a LINK_STATE_DTYPE array (min_pos, fo_carry, hist) with one entry per link."""
+        lo = np.ascontiguousarray(link_off, np.uint64)
+        st = np.ascontiguousarray(state, LINK_STATE_DTYPE)
+        assert st.size == lo.size - 1
+        self._ck(self._L.wifi_b200_rx_batch_dev_state(self._h, C.c_void_p(iq_ptr), _p(lo), lo.size - 1, int(final), _p(st)))
+        return self.results() if fetch else None
+
     def counts(self):
         v = [C.c_int64() for _ in range(4)]
         self._ck(self._L.wifi_b200_rx_counts(self._h, *[C.byref(x) for x in v]))
@@ -288,6 +300,14 @@ class Handle:
         if c["psdu_store_bytes"]:
             self._ck(self._L.wifi_b200_rx_psdus(self._h, _p(store), store.size))
         return RxResult(frames, store)
+
+    def frames(self):
+        """The frame table of the last rx call alone (96 bytes per trigger; the PSDU store stays on the device)."""
+        c = self.counts()
+        frames = np.zeros(c["n_frames"], FRAME_DTYPE)
+        if c["n_frames"]:
+            self._ck(self._L.wifi_b200_rx_frames(self._h, _p(frames), frames.size))
+        return frames
 
     def rows(self, carrier=False):
         c = self.counts()

@@ -155,6 +155,16 @@ int  wifi_b200_channel(wifi_b200_t *h, const float *in_host, int64_t in_len, flo
  * samples.  final != 0: the streams end here (flush).  Results stay in the handle until the next rx call. */
 int  wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int final);
 int  wifi_b200_rx_batch_dev(wifi_b200_t *h, const float *iq_dev, const uint64_t *link_off, int n_links, int final);
+/* The same for streams that are RESUMED in the middle (one long capture cut into segments that different GPUs decode,
+ * SURVEY 8e): per link the state sync_short / sync_long carry across the cut.  With the state of the sequential
+ * receiver at the cut, a segment's frames equal the sequential receiver's from there on. */
+typedef struct wifi_b200_link_state {
+    int64_t min_pos;   /* first sample index (relative to link_off[l]) sync_short may trigger on: previous trigger + 481; 0: none */
+    float   fo_carry;  /* sync_long's d_freq_offset entering the segment (freq_long of the last burst before it), 0 at a stream start */
+    int32_t hist;      /* valid samples stored in front of link_off[l] in the buffer (front-end history, up to 256) */
+} wifi_b200_link_state;
+int  wifi_b200_rx_batch_dev_state(wifi_b200_t *h, const float *iq_dev, const uint64_t *link_off, int n_links, int final,
+                                  const wifi_b200_link_state *state /* n_links entries */);
 /* Same from the radio's wire format: interleaved int16 I/Q (what uhd.usrp_source / the HackRF deliver before
  * the host driver converts to fc32; gnu_radio/IRS_AP.py:163-177 asks UHD for cpu_format "fc32").  The GPU forms
  * x = (float)i16 * scale, one rounding per component -- exactly UHD's sc16 -> fc32 host converter -- so the

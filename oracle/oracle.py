@@ -23,7 +23,8 @@ FRAME_DTYPE = np.dtype([
 
 class RxCfg(C.Structure):
     _fields_ = [("threshold", C.c_double), ("min_plateau", C.c_int32), ("algo", C.c_int32), ("freq", C.c_double),
-                ("bw", C.c_double), ("final", C.c_int32), ("want_carrier", C.c_int32), ("soft", C.c_int32), ("pad", C.c_int32)]
+                ("bw", C.c_double), ("final", C.c_int32), ("want_carrier", C.c_int32), ("soft", C.c_int32), ("hist", C.c_int32),
+                ("min_pos", C.c_int64), ("fo_carry", C.c_float), ("pad", C.c_int32)]
 
 
 class ChanCfg(C.Structure):
@@ -253,8 +254,9 @@ class RxResult:
         return [self.psdu(i)[:-4] for i in range(len(self.frames)) if self.frames[i]["crc_ok"]]
 
 
-def rx_cfg(threshold=0.56, min_plateau=2, algo=0, freq=5.89e9, bw=10e6, final=True, want_carrier=True, soft=False):
-    return RxCfg(threshold, min_plateau, algo, freq, bw, int(final), int(want_carrier), int(soft), 0)
+def rx_cfg(threshold=0.56, min_plateau=2, algo=0, freq=5.89e9, bw=10e6, final=True, want_carrier=True, soft=False,
+           hist=0, min_pos=0, fo_carry=0.0):
+    return RxCfg(threshold, min_plateau, algo, freq, bw, int(final), int(want_carrier), int(soft), int(hist), int(min_pos), float(fo_carry), 0)
 
 
 def _collect(h, want_carrier, soft=False):
@@ -275,9 +277,10 @@ def _collect(h, want_carrier, soft=False):
 
 
 def rx(x, link=0, **kw):
+    """hist > 0: the first `hist` samples of x are history in front of the stream's sample 0 (a resumed stream)."""
     cfg = rx_cfg(**kw)
     a = np.ascontiguousarray(x, np.complex64)
-    h = lib().orc_rx(_p(a), C.c_int64(a.size), C.c_int(link), C.byref(cfg))
+    h = lib().orc_rx(C.c_void_p(a.ctypes.data + 8 * cfg.hist), C.c_int64(a.size - cfg.hist), C.c_int(link), C.byref(cfg))
     return _collect(C.c_void_p(h), bool(cfg.want_carrier), bool(cfg.soft))
 
 

@@ -556,10 +556,11 @@ static void channel(const cf *in, cf *out, int64_t n, int64_t n0, const orc_chan
 struct FrontEnd {
     const cf *x;
     int64_t n;
+    int64_t hist = 0; /* valid samples stored before x[0] (a stream resumed in the middle); older ones read as 0 */
     cf sa = {0.f, 0.f};
     float sp = 0;
     /* samples before the start of the stream are zeros (GNU Radio history) */
-    inline cf at(int64_t j) const { return j < 0 ? cf{0.f, 0.f} : x[j]; }
+    inline cf at(int64_t j) const { return j < -hist ? cf{0.f, 0.f} : x[j]; }
     void seed(int64_t i0)
     {
         sa = {0.f, 0.f};
@@ -751,7 +752,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
     /* ---- sync_short (wifi_phy_hier.grc:716-734) [UP] sync_short.cc ---- */
     std::vector<Burst> bursts;
     {
-        FrontEnd fe{x, n};
+        FrontEnd fe{x, n, (int64_t)cfg.hist};
         enum { SEARCH, COPY } state = SEARCH;
         int plateau = 0, copied = 0;
         for (int64_t i = 0; i < n; ++i) {
@@ -762,6 +763,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
             if (state == SEARCH) {
                 if (over) {
                     if (plateau < cfg.min_plateau) { ++plateau; continue; }
+                    if (i < cfg.min_pos) continue; /* resumed stream: the previous trigger (before x[0]) is less than MIN_GAP back */
                     state = COPY;
                     copied = 0;
                     plateau = 0;
@@ -791,7 +793,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
     }
 
     /* ---- sync_long .. frame_equalizer, burst by burst ---- */
-    float fo_carry = 0.f; /* [UP] sync_long keeps d_freq_offset across frames */
+    float fo_carry = cfg.fo_carry; /* [UP] sync_long keeps d_freq_offset across frames (0 at the start of a stream) */
     size_t first_frame = R.frames.size();
     std::vector<cf> b;
     for (size_t bi = 0; bi < bursts.size(); ++bi) {
@@ -815,7 +817,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
         b.resize(SYNC_LENGTH + 63);
         for (int j = 0; j < SYNC_LENGTH + 63; ++j) {
             int64_t src = B.t + j - 16;
-            cf s = src >= 0 ? x[src] : cf{0.f, 0.f};
+            cf s = src >= -(int64_t)cfg.hist ? x[src] : cf{0.f, 0.f};
             b[j] = cmul(s, crot(-B.freq * (float)j));
         }
         /* sync_long SYNC: fir_filter_ccc(LONG) over 320 lags + search_frame_start() */
@@ -870,7 +872,7 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
                 int nn = k / 64, m = k % 64;
                 int j = F.frame_start + (nn < 2 ? 64 * nn + m : 128 + 80 * (nn - 2) + 16 + m);
                 int64_t src = B.t + j - 16;
-                cf xs = src >= 0 ? x[src] : cf{0.f, 0.f};
+                cf xs = src >= -(int64_t)cfg.hist ? x[src] : cf{0.f, 0.f};
                 cf rot;
                 if ((m & 1) == 0) { rot_even = crot(delta * (float)j); rot = rot_even; }
                 else rot = cmul(rot_even, w1);

@@ -53,6 +53,9 @@ typedef struct orc_rx_cfg {
     int32_t final;        /* 1: the stream ends with this buffer                */
     int32_t want_carrier; /* keep equalised points                              */
     int32_t soft;         /* 1: max-log LLR demapper + soft-decision Viterbi (no reference counterpart) */
+    int32_t hist;         /* resumed stream: valid samples stored before x[0] (front-end history), 0 at a stream start */
+    int64_t min_pos;      /* resumed stream: first index sync_short may trigger on (previous trigger + MIN_GAP + 1), else 0 */
+    float fo_carry;       /* resumed stream: sync_long's d_freq_offset entering the buffer, else 0 */
     int32_t pad;
 } orc_rx_cfg;
 

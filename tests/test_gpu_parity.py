@@ -7,7 +7,8 @@ import os
 import numpy as np
 import pytest
 
-from util import assert_frames_equal, capture_with_collection_over_many_bursts, make_capture, make_psdu
+from util import (adversarial_stream, assert_frames_equal, capture_with_collection_over_many_bursts, gpu_segment_decoder, make_capture,
+                  make_psdu)
 
 pytestmark = pytest.mark.gpu
 
@@ -486,6 +487,47 @@ def test_streaming_small_pushes_and_soft(O, W):
     st = h.stats()
     assert st["crc_ok"] == len(want) and st["pdu_bytes"] == sum(len(d) for _, d in want)
     h.close()
+
+
+@pytest.mark.parametrize("trunc", [500, 641])
+def test_time_sharding_reconciles_adversarial_traffic(O, W, trunc):
+    """Back-to-back traffic without one idle gap (trigger chains that never merge; a decode_mac tag pending across the
+    whole zone): the ranks' check fails, the lowest rank decodes again from a known state through
+    wifi_b200_rx_batch_dev_state, and the union of the owned frames equals the sequential oracle's table."""
+    S = W.sharding
+    y = adversarial_stream(O, trunc=trunc)
+    truth = S.records(O.rx(y, algo=0, want_carrier=False).frames, 0)
+    h = W.Handle(max_samples=1 << 18, max_frames=1024, chan_est=0)
+    try:
+        dec = gpu_segment_decoder(h, y)
+        for world in (2, 4):
+            owned, rounds = S.simulate_ranks(dec, S.shard_stream(y.size, world), y.size)
+            assert np.array_equal(np.concatenate(owned), truth) and rounds >= 1, (world, rounds)
+    finally:
+        h.close()
+
+
+def test_resumed_stream_state_entry_point_matches_oracle(O, W):
+    """wifi_b200_rx_batch_dev_state against the oracle given the same (min_pos, fo_carry, hist), every field and PSDU."""
+    S = W.sharding
+    rng = np.random.default_rng(41)
+    y, _ = make_capture(O, rng, [(int(e), 150 + 60 * int(e)) for e in (0, 3, 5, 7, 2, 6, 1, 4)], snr_db=27, seed=6, gap=300, cfo=0.01)
+    truth = S.records(O.rx(y, algo=3, want_carrier=False).frames, 0)
+    h = W.Handle(max_samples=1 << 18, max_frames=256, chan_est=3)
+    try:
+        dec = gpu_segment_decoder(h, y)
+        for k in (2, 5):
+            lo, st, _ = S.resume_point(truth, 0, int(truth[k, S.TRIG]) + 1)
+            ref = O.rx(y[lo - st["hist"]:], algo=3, hist=st["hist"], min_pos=st["min_pos"], fo_carry=st["fo_carry"])
+            dec(lo, y.size, st, True)
+            assert_frames_equal(h.results(), ref)
+            assert np.array_equal(S.records(ref.frames, lo), truth[k:])
+        with pytest.raises(W.WifiB200Error):       # history that is not there
+            bad = np.zeros(1, W.wifi_b200.LINK_STATE_DTYPE)
+            bad["hist"] = 64
+            h.rx_batch_dev_state(dec.keepalive.data_ptr(), np.array([0, 1000], np.uint64), bad)
+    finally:
+        h.close()
 
 
 def test_overlapping_segment_shards_dedup_to_whole_stream(O, W):

@@ -30,16 +30,24 @@ def _worker(rank, world, port, kind, out_dir):
         total = np.concatenate([O.rx(c, link=l, algo=0, want_carrier=False).frames for l, c in enumerate(caps)])
         ref = S.stats_vector(total, sum(c.size for c in caps))
     else:
-        y, _ = make_capture(O, rng, [(2, 400)] * 40, snr_db=30, seed=9, gap=900)
+        from util import adversarial_stream, oracle_segment_decoder
+        if kind == "stream":
+            y, _ = make_capture(O, rng, [(2, 400)] * 40, snr_db=30, seed=9, gap=900)
+        else:
+            y = adversarial_stream(O, trunc=int(kind[3:]))
         seg = S.shard_stream(y.size, world, overlap=S.OVERLAP)[rank]
-        r = O.rx(y[seg["start"]:seg["end"]], algo=0, want_carrier=False, final=(seg["end"] == y.size))
-        keep = S.owned(r.frames, seg)
-        frames = r.frames[keep]
-        n_samp = seg["core_end"] - seg["core_start"]
         full = O.rx(y, algo=0, want_carrier=False).frames
+        # every rank decodes its segment, the frame records are all-gathered (gloo here, NCCL on the GPUs), every rank
+        # checks that it joined the sequential receiver's state and decodes again from a known state if it did not
+        own, owned_all, rounds = S.reconcile(oracle_segment_decoder(O, y, algo=0), S.shard_stream(y.size, world), rank, y.size)
+        assert np.array_equal(np.concatenate(owned_all), S.records(full, 0)), (kind, rank)
+        assert (rounds >= 1) == (kind != "stream"), (kind, rounds)      # idle gaps: joined at once; adversarial: one more pass
+        frames = np.zeros(len(own), full.dtype)
+        for k, col in (("sig_ok", S.SIG), ("decoded", S.DEC), ("crc_ok", S.CRC), ("length", S.LEN), ("encoding", S.ENC)):
+            frames[k] = own[:, col]
+        n_samp = seg["core_end"] - seg["core_start"]
         ref = S.stats_vector(full, y.size)
-        trig = np.sort(frames["trigger"].astype(np.int64) + seg["start"])
-        np.save(os.path.join(out_dir, "trig%d.npy" % rank), trig)
+        np.save(os.path.join(out_dir, "trig%d.npy" % rank), own[:, S.TRIG])
         if rank == 0:
             np.save(os.path.join(out_dir, "trig_full.npy"), full["trigger"])
     got = S.allreduce_stats(S.stats_vector(frames, n_samp))
@@ -60,6 +68,53 @@ def test_overlapping_segments_dedup_to_the_sequential_frame_set(tmp_path):
     _run("stream", tmp_path)
     t = np.sort(np.concatenate([np.load(tmp_path / "trig0.npy"), np.load(tmp_path / "trig1.npy")]))
     assert np.array_equal(t, np.load(tmp_path / "trig_full.npy"))
+
+
+def test_back_to_back_traffic_without_idle_gaps_still_reconciles(tmp_path):
+    """Trigger chains that never merge (adv500) and a decode_mac tag pending across more than the overlap (adv641)."""
+    for kind in ("adv500", "adv641"):
+        _run(kind, tmp_path)
+        t = np.sort(np.concatenate([np.load(tmp_path / "trig0.npy"), np.load(tmp_path / "trig1.npy")]))
+        assert np.array_equal(t, np.load(tmp_path / "trig_full.npy"))
+
+
+def test_reconcile_cascades_over_many_ranks():
+    """Ranks 1..4 each start inside the adversarial zone: the lowest rank that has not joined decodes again, the next
+    one is checked against the corrected table, and so on (all ranks in one process, a barrier where the all-gather is)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+    from oracle import oracle as O
+    from util import adversarial_stream, make_capture, oracle_segment_decoder
+    S = importlib.import_module("gnuradio-wifi-imagetransfer_b200.sharding")
+    for trunc in (500, 641):
+        y = adversarial_stream(O, trunc=trunc)
+        truth = S.records(O.rx(y, algo=1, want_carrier=False).frames, 0)
+        for world in (3, 5):
+            owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=1), S.shard_stream(y.size, world), y.size)
+            assert np.array_equal(np.concatenate(owned), truth) and rounds >= 1, (trunc, world, rounds)
+    y, _ = make_capture(O, np.random.default_rng(8), [(4, 600)] * 30, snr_db=28, seed=3, gap=1100, cfo=0.004)
+    owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=0), S.shard_stream(y.size, 4), y.size)
+    assert np.array_equal(np.concatenate(owned), S.records(O.rx(y, algo=0, want_carrier=False).frames, 0)) and rounds == 0
+
+
+def test_resumed_stream_state_reproduces_the_sequential_receiver():
+    """(min_pos, fo_carry, hist) -- wifi_b200_link_state -- is all a decode needs to continue behind two regular frames."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+    from oracle import oracle as O
+    from util import make_capture
+    S = importlib.import_module("gnuradio-wifi-imagetransfer_b200.sharding")
+    y, _ = make_capture(O, np.random.default_rng(4), [(int(e), 200 + 50 * int(e)) for e in (0, 3, 5, 7, 2, 6, 1, 4)], snr_db=30, seed=6, gap=300, cfo=0.01)
+    full = O.rx(y, algo=3, want_carrier=False)
+    truth = S.records(full.frames, 0)
+    for k in (2, 4, 6):
+        lo, st, front = S.resume_point(truth, 0, int(truth[k, S.TRIG]) + 1)
+        assert len(front) == 1 and np.array_equal(front[0], truth[k - 1]) and lo + st["min_pos"] == truth[k, S.TRIG]
+        r = O.rx(y[lo - st["hist"]:], algo=3, want_carrier=False, hist=st["hist"], min_pos=st["min_pos"], fo_carry=st["fo_carry"])
+        assert np.array_equal(S.records(r.frames, lo), truth[k:])
+        assert r.pdus() == full.pdus()[k:]
 
 
 def test_shard_geometry():

@@ -75,3 +75,49 @@ def capture_with_collection_over_many_bursts(O, rng, n_interferers=6, spacing=11
         x[pos:pos + b.size] += b
         pos += spacing
     return O.channel(x, gain=0.6, cfo=0.002, noise_sigma=0.003, seed=12)
+
+
+def adversarial_stream(O, trunc=500, n_zone=230):
+    """Three ordinary frames, then `n_zone` back-to-back preambles cut to `trunc` samples with not one idle sample
+    between them, then four ordinary frames.  trunc = 500: the plateaus follow each other more closely than MIN_GAP
+    plus a plateau, so two sync_short trigger chains that start at different points of the zone never merge.
+    trunc = 641 (whole two-symbol frames): every SIGNAL decodes but no burst is long enough for a data symbol, so
+    decode_mac carries a pending tag across the whole zone."""
+    rng = np.random.default_rng(3)
+    head, _ = make_capture(O, rng, [(2, 300)] * 3, snr_db=30, seed=1, gap=900)
+    tail, _ = make_capture(O, rng, [(2, 300)] * 4, snr_db=30, seed=2, gap=900, lead=600)
+    f = O.tx_frame(make_psdu(O, rng, 2), 0, seed=3)
+    zone = O.channel(np.concatenate([f[:trunc]] * n_zone), gain=0.6, noise_sigma=0.6 * 10 ** (-30 / 20), seed=7)
+    return np.concatenate([head, zone, tail]).astype(np.complex64)
+
+
+def oracle_segment_decoder(O, y, **kw):
+    """decode(lo, end, state, final) callback of sharding.reconcile on top of the oracle."""
+    def decode(lo, end, st, final):
+        if st is None:
+            return O.rx(y[lo:end], want_carrier=False, final=final, **kw).frames
+        h = st["hist"]
+        return O.rx(y[lo - h:end], want_carrier=False, final=final, hist=h, min_pos=st["min_pos"], fo_carry=st["fo_carry"], **kw).frames
+    return decode
+
+
+def gpu_segment_decoder(h, y):
+    """decode(lo, end, state, final) callback of sharding.reconcile on top of the library: the capture lives in device
+    memory once, a segment is a pair of offsets into it (wifi_b200_rx_batch_dev / _rx_batch_dev_state)."""
+    import threading
+    import torch
+    from importlib import import_module
+    w = import_module("gnuradio-wifi-imagetransfer_b200.wifi_b200")
+    dev = torch.from_numpy(np.ascontiguousarray(y).view(np.float32)).cuda()
+    lock = threading.Lock()        # one handle: a call and the fetch of its results belong together
+
+    def decode(lo, end, st, final):
+        off = np.array([lo, end], np.uint64)
+        with lock:
+            if st is None:
+                return h.rx_batch_dev(dev.data_ptr(), off, final=final, fetch=True).frames
+            state = np.zeros(1, w.LINK_STATE_DTYPE)
+            state["min_pos"], state["fo_carry"], state["hist"] = st["min_pos"], st["fo_carry"], st["hist"]
+            return h.rx_batch_dev_state(dev.data_ptr(), off, state, final=final, fetch=True).frames
+    decode.keepalive = dev
+    return decode
