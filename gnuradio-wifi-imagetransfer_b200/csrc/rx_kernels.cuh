@@ -26,53 +26,33 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
     return lo;
 }
 
-// One block per tile of DET_TILE samples of one link, one thread per FE_CHUNK samples.  The tile
-// (plus two chunks of history) is staged in shared memory with coalesced loads; rows are padded
-// by one sample so that the per-thread sequential walk (stride FE_CHUNK) is bank-conflict free.
-// Each thread re-seeds the two running sums exactly as the oracle does at every multiple of
-// FE_CHUNK, runs them over its chunk and emits bit n = (c[n] > thr).  Samples before the start
-// of the stream are zeros, which makes every "index < 0" special case of the oracle an exact
-// no-op (x + 0 == x), so the inner loop is branch free.
+// One block per tile of DET_TILE samples of one link, one thread per FE_CHUNK samples.
+//
+// Data movement: the tile plus two chunks of history (130 rows of 64 samples) is fetched by 1-D bulk copies
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, one 512-byte row per copy, issued by one warp, one
+// mbarrier per block) -- the copy engine does the work that used to cost 15 instructions per sample.  Rows are 66
+// samples (528 bytes) apart in shared memory: 16-byte aligned, as bulk copies require, and 33 16-byte units apart, so
+// the threads' 16-byte loads (two samples each) of a warp are bank-conflict free.  A tile that touches the start or the
+// end of its stream, or whose samples are not 16-byte aligned in global memory, is staged element-wise (zeros outside
+// the stream: that makes every "index < 0" case of the oracle an exact no-op, x + 0 == x).
+//
+// Arithmetic: each thread re-seeds the two running sums exactly as the oracle does at every multiple of FE_CHUNK
+// and walks its 64 samples.  The walk is fully unrolled over a register ring of the last 64 samples: sample n is
+// loaded once (32 loads of the previous row for the history, 32 of its own row) and the three delayed taps
+// x[n-16], x[n-47], x[n-63] are register reads.  Flag n = |a[n]|^2 > thr^2 p[n]^2 (oracle rx_link).
 #define DET_ROWS (DET_THREADS + 2)
-struct DetState { cf sa; float sp; };
+#define DET_STRIDE 66                                        // samples between rows in shared memory
+#define DET_SMEM_BYTES (DET_ROWS * DET_STRIDE * (int)sizeof(cf) + 16)   // + the mbarrier
 
-// the oracle's expression c = |a| / p > thr; out of line: it runs for a handful of samples per tile and its
-// square root / division slow paths would otherwise be replicated in every unrolled copy of the walk
-__device__ __noinline__ bool det_exact(float m2, float p, float thr_f) { return (sqrtf(m2) / p) > thr_f; }
+__device__ __forceinline__ uint32_t det_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// samples [I0, I1) of the chunk; OD / OO / OOD = offsets of the n-16, n-47, n-63 streams in the padded tile
-// A segment lies inside one 32-bit half of the chunk's flag word; `w` is that half, a running one-hot mask marks the bit.
-template <int I0, int I1, int OD, int OO, int OOD>
-__device__ __forceinline__ void det_segment(const cf *base, DetState &st, float thr_f, float thr2, uint32_t &w)
-{
-    static_assert((I0 >> 5) == ((I1 - 1) >> 5), "segment straddles the two flag words");
-    uint32_t bit = 1u << (I0 & 31);
-#pragma unroll 4
-    for (int i = I0; i < I1; ++i) {
-        const cf xn = base[i], xd = base[i + OD], xo = base[i + OO], xod = base[i + OOD];
-        st.sa = wdm_cmacc(st.sa, xn, xd);          // fused multiply-add chains, as the oracle's FrontEnd::step
-        const float m2 = wdm_norm(st.sa);
-        st.sa = wdm_cmsubc(st.sa, xo, xod);
-        st.sp = wdm_norm_add(st.sp, xn);
-        const float p = st.sp;
-        st.sp = wdm_norm_sub(st.sp, xod);
-        // c = sqrt(m2)/p > thr.  Decide from the squares when the margin (1e-4) dwarfs the rounding of
-        // the exact expression (< 3e-7); evaluate the oracle's expression only inside the margin or when
-        // p is outside the range where the squares are safe.
-        const float t2 = thr2 * (p * p);
-        bool over = m2 > t2;
-        const bool sure = (p > 1e-12f) & (p < 1e12f) & ((m2 > t2 * 1.0001f) | (m2 < t2 * 0.9999f));
-        if (!sure) over = det_exact(m2, p, thr_f);
-        if (over) w |= bit;
-        bit += bit;
-    }
-}
-#define DET_IDX(q) ((q) + ((q) >> 6))     // row * 65 + col
 __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
                                                          int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
                                                          uint32_t *__restrict__ summary)
 {
-    extern __shared__ cf sx[];   // DET_ROWS * 65
+    extern __shared__ __align__(128) unsigned char det_raw[];
+    cf *sx = reinterpret_cast<cf *>(det_raw);                                         // DET_ROWS x DET_STRIDE
+    uint64_t *bar = reinterpret_cast<uint64_t *>(det_raw + DET_ROWS * DET_STRIDE * sizeof(cf));
     const int64_t tile = blockIdx.x;
     if (tile >= total_tiles) return;
     const int tid = threadIdx.x;
@@ -81,39 +61,75 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
     const cf *x = iq + L.x_off;
     const int64_t T0 = (tile * DET_THREADS - L.chunk_base) * FE_CHUNK;   // first sample of the tile in the link
     const int64_t lo = -(int64_t)L.hist, hi = L.len;
-    // global -> shared with cp.async (LDGSTS): all 65 copies of a thread are in flight at once,
-    // no register staging; samples outside the stream are zero-filled
-#pragma unroll 5
-    for (int q = tid; q < DET_ROWS * FE_CHUNK; q += DET_THREADS) {
-        int64_t g = T0 - 2 * FE_CHUNK + q;
-        cf *dst = &sx[DET_IDX(q)];
-        if (g >= lo && g < hi) __pipeline_memcpy_async(dst, &x[g], sizeof(cf));
-        else *dst = cf{0.f, 0.f};
+    const int64_t g0 = T0 - 2 * FE_CHUNK;                                // first staged sample
+    const bool bulk = g0 >= lo && g0 + DET_ROWS * FE_CHUNK <= hi && ((reinterpret_cast<uintptr_t>(x + g0) & 15) == 0);
+    if (bulk) {
+        const uint32_t bar_a = det_smem_u32(bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid < 32) {
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(DET_ROWS * FE_CHUNK * (int)sizeof(cf)) : "memory");
+            __syncwarp();
+            for (int r = tid; r < DET_ROWS; r += 32)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(det_smem_u32(sx + r * DET_STRIDE)),
+                             "l"(x + g0 + (int64_t)r * FE_CHUNK), "r"(FE_CHUNK * (int)sizeof(cf)), "r"(bar_a)
+                             : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar_a) : "memory");
+    } else {
+        for (int q = tid; q < DET_ROWS * FE_CHUNK; q += DET_THREADS) {
+            const int64_t g = g0 + q;
+            sx[(q >> 6) * DET_STRIDE + (q & 63)] = (g >= lo && g < hi) ? x[g] : cf{0.f, 0.f};
+        }
+        __syncthreads();
     }
-    __pipeline_commit();
-    __pipeline_wait_prior(0);
-    __syncthreads();
-    // this thread's chunk is row tid+2 of the padded tile: element c of the chunk (c may be negative,
-    // reaching into the previous rows) sits at base + c + floor(c / 64).  The walk is cut where one of
-    // the four sample streams (n, n-16, n-47, n-63) crosses a row, so inside a segment every address is
-    // base + i + constant.
-    const cf *base = sx + (tid + 2) * (FE_CHUNK + 1);
     uint32_t w0 = 0u, w1 = 0u;
     if (T0 + (int64_t)tid * FE_CHUNK < hi) {
-        DetState st;
-        st.sa = cf{0.f, 0.f};
-        st.sp = 0.f;
-        // the 47 (63) samples before the chunk live in the previous padded row: element -k sits at base - k - 1
-#pragma unroll 4
-        for (int k = 47; k >= 1; --k) st.sa = wdm_cmacc(st.sa, base[-k - 1], base[-k - 17]);
-#pragma unroll 4
-        for (int k = 63; k >= 1; --k) st.sp = wdm_norm_add(st.sp, base[-k - 1]);
+        // ring[i & 63] = sample i of the chunk for i in [-63, 63]: history sample -k sits in ring[64 - k]
+        const float4 *prev = reinterpret_cast<const float4 *>(sx + (tid + 1) * DET_STRIDE);
+        const float4 *own = reinterpret_cast<const float4 *>(sx + (tid + 2) * DET_STRIDE);
+        cf ring[64];
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            const float4 v = prev[m];
+            ring[2 * m] = cf{v.x, v.y};              // ring[0] (sample -64) is not used; overwritten by sample 0
+            ring[2 * m + 1] = cf{v.z, v.w};
+        }
+        cf sa = {0.f, 0.f};
+        float sp = 0.f;
+#pragma unroll
+        for (int j = -47; j <= -1; ++j) sa = wdm_cmacc(sa, ring[64 + j], ring[48 + j]);
+#pragma unroll
+        for (int j = -63; j <= -1; ++j) sp = wdm_norm_add(sp, ring[64 + j]);
         const float thr2 = thr_f * thr_f;
-        det_segment<0, 16, -17, -48, -64>(base, st, thr_f, thr2, w0);
-        det_segment<16, 32, -16, -48, -64>(base, st, thr_f, thr2, w0);
-        det_segment<32, 47, -16, -48, -64>(base, st, thr_f, thr2, w1);
-        det_segment<47, 63, -16, -47, -64>(base, st, thr_f, thr2, w1);
-        det_segment<63, 64, -16, -47, -63>(base, st, thr_f, thr2, w1);
+        cf nxt = {0.f, 0.f};
+#pragma unroll
+        for (int n = 0; n < 64; ++n) {
+            cf xn;
+            if ((n & 1) == 0) {
+                const float4 v = own[n >> 1];
+                xn = cf{v.x, v.y};
+                nxt = cf{v.z, v.w};
+            } else {
+                xn = nxt;
+            }
+            const cf xd = ring[(n + 48) & 63], xo = ring[(n + 17) & 63], xod = ring[(n + 1) & 63];   // n-16, n-47, n-63
+            sa = wdm_cmacc(sa, xn, xd);              // fused multiply-add chains, as the oracle's FrontEnd::step
+            const float m2 = wdm_norm(sa);
+            sa = wdm_cmsubc(sa, xo, xod);
+            sp = wdm_norm_add(sp, xn);
+            const float p = sp;
+            sp = wdm_norm_sub(sp, xod);
+            if (m2 > thr2 * (p * p)) {
+                if (n < 32) w0 |= 1u << n; else w1 |= 1u << (n - 32);
+            }
+            ring[n] = xn;                            // replaces sample n - 64
+        }
     }
     const int64_t chunk = tile * DET_THREADS + tid;
     reinterpret_cast<uint2 *>(flags)[chunk] = make_uint2(w0, w1);

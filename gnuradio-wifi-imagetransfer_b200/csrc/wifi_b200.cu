@@ -147,7 +147,7 @@ const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "de
 #ifndef VW_SWITCH
 #define VW_SWITCH 2368          // frames per call up to which the warp-per-frame Viterbi is used (148 SMs x 16 warps; measured crossover ~2700)
 #endif
-#define DET_SMEM (DET_ROWS * 65 * (int)sizeof(cf))
+#define DET_SMEM DET_SMEM_BYTES
 
 } // namespace
 

@@ -239,6 +239,14 @@ def frontend(x):
     return ao, po, co
 
 
+def flags(x, threshold=0.56):
+    """sync_short's per-sample plateau test as the numerical contract states it (squares, see wifi_oracle.cpp rx_link)."""
+    a = np.ascontiguousarray(x, np.complex64)
+    o = np.zeros(a.size, np.uint8)
+    lib().orc_flags(_p(a), C.c_int64(a.size), C.c_double(threshold), _p(o))
+    return o.astype(bool)
+
+
 class RxResult:
     def __init__(self, frames, rows, carrier, psdu):
         self.frames, self.rows, self.carrier, self.psdu_blob = frames, rows, carrier, psdu

@@ -570,6 +570,7 @@ struct FrontEnd {
     }
     /* running sums as fused multiply-add chains: a[i] = sum of x[j] conj(x[j-16]) over the last 48 lags, p[i] = sum of
      * |x[j]|^2 over the last 64 samples; the term leaving the window is subtracted after the output is taken */
+    float m2 = 0; /* |a[i]|^2 of the last step */
     inline void step(int64_t i, cf &a, float &p, float &c)
     {
         if ((i & 63) == 0) seed(i);
@@ -579,7 +580,8 @@ struct FrontEnd {
         sp = wdm_norm_add(sp, at(i));
         p = sp;
         sp = wdm_norm_sub(sp, at(i - 63));
-        c = sqrtf(wdm_norm(a)) / p;
+        m2 = wdm_norm(a);
+        c = sqrtf(m2) / p;
     }
 };
 
@@ -755,11 +757,18 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
         FrontEnd fe{x, n, (int64_t)cfg.hist};
         enum { SEARCH, COPY } state = SEARCH;
         int plateau = 0, copied = 0;
+        /* sync_short compares c = |a| / p with the threshold; the contract compares the squares,
+         * |a|^2 > thr^2 p^2 with thr the largest float not above the threshold: the same test up to one rounding of c
+         * (threshold jitter of a few 1e-8 relative), no square root and no division per sample (choice 7).
+         * p = 0 (silence) and NaN give "not over", as c = 0/0 does upstream. */
+        float thr_f = (float)cfg.threshold;
+        if ((double)thr_f > cfg.threshold) thr_f = nextafterf(thr_f, -INFINITY);
+        const float thr2 = thr_f * thr_f;
         for (int64_t i = 0; i < n; ++i) {
             cf a;
             float p, c;
             fe.step(i, a, p, c);
-            bool over = (double)c > cfg.threshold;
+            bool over = fe.m2 > thr2 * (p * p);
             if (state == SEARCH) {
                 if (over) {
                     if (plateau < cfg.min_plateau) { ++plateau; continue; }
@@ -1091,6 +1100,21 @@ void orc_frontend(const float *x, int64_t n, float *a_out, float *p_out, float *
         a_out[2 * i] = a.re; a_out[2 * i + 1] = a.im;
         p_out[i] = p;
         c_out[i] = c;
+    }
+}
+
+/* the plateau test of sync_short as the contract states it (see rx_link): out[i] = |a[i]|^2 > thr^2 p[i]^2 */
+void orc_flags(const float *x, int64_t n, double threshold, uint8_t *out)
+{
+    FrontEnd fe{(const cf *)x, n};
+    float thr_f = (float)threshold;
+    if ((double)thr_f > threshold) thr_f = nextafterf(thr_f, -INFINITY);
+    const float thr2 = thr_f * thr_f;
+    for (int64_t i = 0; i < n; ++i) {
+        cf a;
+        float p, c;
+        fe.step(i, a, p, c);
+        out[i] = fe.m2 > thr2 * (p * p);
     }
 }
 

@@ -98,6 +98,7 @@ void orc_channel(const float *in, float *out, int64_t n, int64_t n0, const orc_c
 
 /* ---- RX ---- */
 void orc_frontend(const float *x, int64_t n, float *a_out, float *p_out, float *c_out);
+void orc_flags(const float *x, int64_t n, double threshold, uint8_t *out);   /* sync_short's plateau test per sample */
 typedef struct orc_rx_result orc_rx_result;
 orc_rx_result *orc_rx(const float *x, int64_t n, int link, const orc_rx_cfg *cfg);
 /* many links, one std::thread per worker; link l is x + 2*off[l], length len[l] */

@@ -41,7 +41,7 @@ def test_config0_kodim01_in_1500_byte_psdus_bpsk_20db(O, W):
     x = np.concatenate(parts)
     y = O.channel(x, gain=0.6, noise_sigma=0.6 * 10 ** (-20 / 20), seed=0)
     got, res = phy.rx(y)
-    ref = O.rx(y, algo=0, want_carrier=False)
+    ref = O.rx(y, algo=0, want_carrier=False, bw=20e6, freq=5.89e9)
     assert_frames_equal(res, ref)
     assert len(got) == 352 and all(g[0]["encoding"] == 0 for g in got)
     assert b"".join(g[1][24:] for g in got) == data

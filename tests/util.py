@@ -34,7 +34,8 @@ def assert_frames_equal(gpu, ref, float_exact=True):
         for k in ("freq_short", "freq_long"):
             assert np.array_equal(gpu.frames[k], ref.frames[k], equal_nan=True), (k, gpu.frames[k], ref.frames[k])
     ok = ref.frames["sig_ok"] == 1
-    assert np.allclose(gpu.frames["snr"][ok], ref.frames["snr"][ok], rtol=1e-9, atol=1e-9, equal_nan=True)   # double log10: libm vs device
+    bad = ~np.isclose(gpu.frames["snr"][ok], ref.frames["snr"][ok], rtol=1e-9, atol=1e-9, equal_nan=True)   # double log10: libm vs device
+    assert not bad.any(), ("snr", np.nonzero(ok)[0][bad][:5], gpu.frames["snr"][ok][bad][:5], ref.frames["snr"][ok][bad][:5])
     for i in range(len(ref.frames)):
         if ref.frames[i]["decoded"]:
             assert gpu.psdu(i) == ref.psdu(i), ("psdu", i)
