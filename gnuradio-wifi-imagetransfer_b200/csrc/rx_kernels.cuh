@@ -29,8 +29,8 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
 // One block per tile of DET_TILE samples of one link, one thread per FE_CHUNK samples.
 //
 // Data movement: the tile plus two chunks of history (130 rows of 64 samples) is fetched by 1-D bulk copies
-// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, one 512-byte row per copy, issued by one warp, one
-// mbarrier per block) -- the copy engine does the work that used to cost 15 instructions per sample.  Rows are 66
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, one 512-byte row per copy, issued by one warp, four
+// mbarriers per block: a warp starts as soon as its quarter of the rows has arrived) -- the copy engine does the work that used to cost 15 instructions per sample.  Rows are 66
 // samples (528 bytes) apart in shared memory: 16-byte aligned, as bulk copies require, and 33 16-byte units apart, so
 // the threads' 16-byte loads (two samples each) of a warp are bank-conflict free.  A tile that touches the start or the
 // end of its stream, or whose samples are not 16-byte aligned in global memory, is staged element-wise (zeros outside
@@ -42,18 +42,18 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
 // x[n-16], x[n-47], x[n-63] are register reads.  Flag n = |a[n]|^2 > thr^2 p[n]^2 (oracle rx_link).
 #define DET_ROWS (DET_THREADS + 2)
 #define DET_STRIDE 66                                        // samples between rows in shared memory
-#define DET_SMEM_BYTES (DET_ROWS * DET_STRIDE * (int)sizeof(cf) + 16)   // + the mbarrier
+#define DET_SMEM_BYTES (DET_ROWS * DET_STRIDE * (int)sizeof(cf) + 32)   // + four mbarriers
 
 __device__ __forceinline__ uint32_t det_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
-                                                         int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
+                                                         int64_t tile_base, int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
                                                          uint32_t *__restrict__ summary)
 {
     extern __shared__ __align__(128) unsigned char det_raw[];
     cf *sx = reinterpret_cast<cf *>(det_raw);                                         // DET_ROWS x DET_STRIDE
     uint64_t *bar = reinterpret_cast<uint64_t *>(det_raw + DET_ROWS * DET_STRIDE * sizeof(cf));
-    const int64_t tile = blockIdx.x;
+    const int64_t tile = tile_base + blockIdx.x;          // links / n_links: the link group of this launch; tiles are numbered over the whole call
     if (tile >= total_tiles) return;
     const int tid = threadIdx.x;
     int l = find_link(links, n_links, tile * DET_THREADS);
@@ -64,23 +64,31 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
     const int64_t g0 = T0 - 2 * FE_CHUNK;                                // first staged sample
     const bool bulk = g0 >= lo && g0 + DET_ROWS * FE_CHUNK <= hi && ((reinterpret_cast<uintptr_t>(x + g0) & 15) == 0);
     if (bulk) {
+        // four mbarriers, one per warp of consumers: rows [0, 34) complete the first, then 32 rows each.  Warp w walks the
+        // rows 32 w + 1 .. 32 w + 33, i.e. it waits for its own barrier and the one before: the first warp starts its
+        // walk when a quarter of the tile has arrived, not the whole tile.
         const uint32_t bar_a = det_smem_u32(bar);
         if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+#pragma unroll
+            for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a + 8 * b));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         if (tid < 32) {
-            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(DET_ROWS * FE_CHUNK * (int)sizeof(cf)) : "memory");
+            if (tid < 4)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + 8 * tid), "r"((tid == 0 ? 34 : 32) * FE_CHUNK * (int)sizeof(cf)) : "memory");
             __syncwarp();
             for (int r = tid; r < DET_ROWS; r += 32)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(det_smem_u32(sx + r * DET_STRIDE)),
-                             "l"(x + g0 + (int64_t)r * FE_CHUNK), "r"(FE_CHUNK * (int)sizeof(cf)), "r"(bar_a)
+                             "l"(x + g0 + (int64_t)r * FE_CHUNK), "r"(FE_CHUNK * (int)sizeof(cf)), "r"(bar_a + 8 * (r < 34 ? 0 : (r - 2) >> 5))
                              : "memory");
         }
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar_a) : "memory");
+        const int wq = tid >> 5;
+        for (int b = (wq > 0 ? wq - 1 : 0); b <= wq; ++b) {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar_a + 8 * b) : "memory");
+        }
     } else {
         for (int q = tid; q < DET_ROWS * FE_CHUNK; q += DET_THREADS) {
             const int64_t g = g0 + q;
@@ -182,10 +190,10 @@ __device__ __forceinline__ int64_t next_candidate(const uint32_t *__restrict__ f
 #define SEG_CHUNKS DET_THREADS          // chunks per segment
 #define SEG_CAP 20                      // >= 8192 / 481 + 1 triggers per segment
 __global__ void __launch_bounds__(128) k_select_spec(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary,
-                                                      const LinkDesc *__restrict__ links, int n_links, int64_t total_segs, int min_plateau,
+                                                      const LinkDesc *__restrict__ links, int n_links, int64_t seg_base, int64_t total_segs, int min_plateau,
                                                       int *__restrict__ spec_trig, int4 *__restrict__ spec_meta)
 {
-    int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t seg = seg_base + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (seg >= total_segs) return;
     const int l = find_link(links, n_links, seg * SEG_CHUNKS);
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
 // do not overlap, so frame i may start at row floor(t_i / 80) + i of the link's range (its burst_len/80 + 1
 // rows end before the next frame's first row); the range is floor(len / 80) + k + 1 rows.
 __global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, int *counters, unsigned long long *row_counter,
-                                                   int64_t max_frames, int *err)
+                                                   int64_t max_frames, int *err, long long frame_base, long long row_base)
 {
     __shared__ long long s_f[1024], s_r[1024];
     const int tid = threadIdx.x;
@@ -375,8 +383,8 @@ __global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, 
         s_r[tid] += ar;
         __syncthreads();
     }
-    long long bf = s_f[tid] - f, br = s_r[tid] - r;
-    const long long total_f = s_f[1023];
+    long long bf = frame_base + s_f[tid] - f, br = row_base + s_r[tid] - r;      // bases: the link groups before this one
+    const long long total_f = frame_base + s_f[1023];
     const bool ovf = total_f > max_frames;
     for (int l = l0; l < l1; ++l) {
         const int k = links[l].frame_count;
@@ -388,14 +396,15 @@ __global__ void __launch_bounds__(1024) k_reserve(LinkDesc *links, int n_links, 
     }
     if (tid == 0) {
         counters[0] = total_f > 0x7fffffffll ? 0x7fffffff : (int)total_f;
-        *row_counter = (unsigned long long)s_r[1023];
+        *row_counter = (unsigned long long)(row_base + s_r[1023]);
         if (ovf) atomicExch(err, WIFI_E_OVERFLOW);
 
     }
 }
 
 // frame records of all links, one thread per frame (grid.y = link)
-__global__ void __launch_bounds__(128) k_frames_init(const LinkDesc *__restrict__ links, const int *__restrict__ trig_tmp, wifi_b200_frame *frames)
+__global__ void __launch_bounds__(128) k_frames_init(const LinkDesc *__restrict__ links, const int *__restrict__ trig_tmp, wifi_b200_frame *frames,
+                                                      int link_base)
 {
     const int l = blockIdx.y;
     const LinkDesc L = links[l];
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(128) k_frames_init(const LinkDesc *__restrict_
         const int64_t t = tmp[i];
         const int64_t endp = (i + 1 < k) ? (int64_t)tmp[i + 1] : L.len;
         wifi_b200_frame f;
-        f.trigger = t; f.link = l;
+        f.trigger = t; f.link = link_base + l;
         f.burst_len = (int)((endp - t) < SS_MAX_SAMPLES ? (endp - t) : SS_MAX_SAMPLES);
         // Streaming: the newest burst of a link is complete once MAX_SAMPLES of the stream lie behind its trigger
         // (sync_short's COPY state has ended whatever follows); until then a later trigger may still cut it short,
@@ -422,7 +431,8 @@ __global__ void __launch_bounds__(128) k_frames_init(const LinkDesc *__restrict_
 
 // ------------------------------------------------------------------ R2/R3 sync_long search
 // One block (128 threads) per frame.
-__global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames)
+// (f0, n_frames) here and below: the frame range of the link group a launch works on; `links` is the whole call's table
+__global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int f0, int n_frames)
 {
     __shared__ cf sb[SYNC_LENGTH + 64];
     __shared__ cf scorr[SYNC_LENGTH];
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
     __shared__ float rmax[4];
     __shared__ int ridx[4];
     __shared__ int top[4];
-    int f = blockIdx.x;
+    int f = f0 + blockIdx.x;
     if (f >= n_frames) return;
     wifi_b200_frame F = frames[f];
     const LinkDesc L = links[F.link];
@@ -544,7 +554,7 @@ __device__ __forceinline__ int emitted_symbols(int avail, int fs, bool last)
 // ALGO: the equalizer (WIFI_EQ_*) as a template parameter: the symbol loop carries only its own update rule
 // PHASE: 0 = LTS1, LTS2, SIGNAL -> EqState ; 1 = data symbols -> rows (and trellis words)
 template <bool SOFT, int ALGO, int PHASE>
-__global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int n_frames,
+__global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int f0, int n_frames,
                                                 EqState *states, uint8_t *rows, cf *carrier, DemodParams prm,
                                                 const uint16_t *__restrict__ depunct_lut, uint32_t *__restrict__ vit_in,
                                                 int8_t *__restrict__ soft_rows, uint32_t *__restrict__ vit_soft_in)
@@ -560,7 +570,7 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
     __shared__ __align__(8) uint8_t s_bits[4][49 * 8];
     constexpr int phase = PHASE;
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.x * 4 + wib;
+    const int f = f0 + blockIdx.x * 4 + wib;
     if (f >= n_frames) return;
     const wifi_b200_frame F = frames[f];
     if (F.burst_len < SYNC_LENGTH + 63) return;
@@ -899,11 +909,11 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
 
 // ------------------------------------------------------------------ R5f SIGNAL field
 // One thread per frame: deinterleave 48 hard bits, 62-step Viterbi (ntb 5), parse_signal.
-__global__ void __launch_bounds__(VIT_BLOCK) k_signal(wifi_b200_frame *frames, int n_frames, const EqState *states)
+__global__ void __launch_bounds__(VIT_BLOCK) k_signal(wifi_b200_frame *frames, int f0, int n_frames, const EqState *states)
 {
     __shared__ uint32_t ring[5 * 16 * VIT_BLOCK];
     const int tid = threadIdx.x;
-    int f = blockIdx.x * VIT_BLOCK + tid;
+    int f = f0 + blockIdx.x * VIT_BLOCK + tid;
     if (f >= n_frames) return;
     if (frames[f].n_syms < 3) return;
     const EqState *st = states + f;
@@ -1013,10 +1023,10 @@ __device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *f
 // none, whatever surrounds them -- unless some frame of the link is irregular (SIGNAL ok but no rows,
 // too few rows, or an oversize tag), in which case the link is flagged and k_plan replays the exact
 // sequential state machine over it.
-__global__ void __launch_bounds__(128) k_plan_fast(wifi_b200_frame *frames, int n_frames, JobDesc *jobs, int *pack_list, int *n_pack,
+__global__ void __launch_bounds__(128) k_plan_fast(wifi_b200_frame *frames, int f0, int n_frames, JobDesc *jobs, int *pack_list, int *n_pack,
                                                     int *link_dirty, int soft)
 {
-    int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    int fi = f0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (fi >= n_frames) return;
     const wifi_b200_frame *F = frames + fi;
     const int sig = F->sig_ok, nrows = F->n_rows, fsym = F->frame_symbols, len = F->length, enc = F->encoding;
@@ -1145,7 +1155,7 @@ __global__ void __launch_bounds__(256) k_pack(const JobDesc *__restrict__ jobs, 
 // ------------------------------------------------------------------ R6a-c Viterbi + descramble + CRC
 // One thread per frame slot; jobs[frame].n_sym == 0 means nothing to decode.  Trellis words of the
 // frame are contiguous (vit_in[frame][w]); words past the coded data read as 0 (oracle note 2).
-__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict__ jobs, int n_frames, const uint32_t *__restrict__ vit_in,
+__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict__ jobs, int f0, int n_frames, const uint32_t *__restrict__ vit_in,
                                                         uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
 {
     extern __shared__ uint32_t vsm[];
@@ -1158,7 +1168,7 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
     if (tid < 16) { uint32_t T, E; VitCore::branch((uint32_t)tid, T, E); s_bm[tid] = make_uint2(T, E); }
     __syncthreads();
-    const int job = blockIdx.x * VIT_BLOCK + tid;
+    const int job = f0 + blockIdx.x * VIT_BLOCK + tid;
     if (job >= n_frames) return;
     const JobDesc J = jobs[job];
     if (J.n_sym == 0) return;
@@ -1217,7 +1227,7 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
 // with the last 32 + ntb snapshots and the per-lane best-state keys parked in shared memory, 32 chains run in lock step.
 #define VW_WARPS 4
 #define VW_RING 48            // snapshots kept per frame: >= 32 + VIT_NTB_MAX - 1
-__global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *__restrict__ jobs, int n_frames, const uint32_t *__restrict__ vit_in,
+__global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *__restrict__ jobs, int f0, int n_frames, const uint32_t *__restrict__ vit_in,
                                                                uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
 {
     __shared__ uint8_t s_ring[VW_WARPS][VW_RING][64];
@@ -1228,7 +1238,7 @@ __global__ void __launch_bounds__(32 * VW_WARPS) k_viterbi_warp(const JobDesc *_
     for (int i = threadIdx.x; i < 128; i += blockDim.x) s_scr[i] = c_tab.scr_tab[i];
     __syncthreads();
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int job = blockIdx.x * VW_WARPS + wib;
+    const int job = f0 + blockIdx.x * VW_WARPS + wib;
     if (job >= n_frames) return;
     const JobDesc J = jobs[job];
     if (J.n_sym == 0) return;
@@ -1340,7 +1350,7 @@ __global__ void __launch_bounds__(256) k_pack_soft(const JobDesc *__restrict__ j
     }
 }
 
-__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi_soft(const JobDesc *__restrict__ jobs, int n_frames, const uint32_t *__restrict__ vit_soft_in,
+__global__ void __launch_bounds__(VIT_BLOCK) k_viterbi_soft(const JobDesc *__restrict__ jobs, int f0, int n_frames, const uint32_t *__restrict__ vit_soft_in,
                                                              uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
 {
     extern __shared__ uint32_t vsm[];
@@ -1351,7 +1361,7 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi_soft(const JobDesc *__res
     for (int i = tid; i < 256; i += VIT_BLOCK) s_crc[i] = c_tab.crc_tab[i];
     for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
     __syncthreads();
-    const int job = blockIdx.x * VIT_BLOCK + tid;
+    const int job = f0 + blockIdx.x * VIT_BLOCK + tid;
     if (job >= n_frames) return;
     const JobDesc J = jobs[job];
     if (J.n_sym == 0) return;

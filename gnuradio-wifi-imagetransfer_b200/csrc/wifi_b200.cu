@@ -155,6 +155,8 @@ struct wifi_b200 {
     wifi_b200_cfg cfg;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // host input / results of one link group while another is decoded
+    std::vector<cudaEvent_t> ev_h2d, ev_done;
     std::mutex mu;
     std::string err;
     // device workspace
@@ -236,7 +238,6 @@ namespace {
     } while (0)
 
 std::mutex g_tab_mu;
-std::mutex g_h2d_mu[64];
 bool g_tab_done[64];
 
 int upload_tables(wifi_b200 *h)
@@ -265,6 +266,10 @@ void free_all(wifi_b200 *h)
     if (h->h_psdu) cudaFreeHost(h->h_psdu);
     if (h->h_iq) cudaFreeHost(h->h_iq);
     for (int i = 0; i <= ST_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -364,8 +369,19 @@ void mark(wifi_b200 *h, int i)
     h->ev_used[i] = true;
 }
 
-// the receive pipeline over device-resident samples; links already in h->h_links
-int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
+// One host -> device copy of a link group, queued on the copy stream before run_rx is called
+struct H2dPlan {
+    const void *src = nullptr;     // host buffer (fc32 or sc16) of the first sample of link 0 of the call
+    size_t bytes_per_sample = 0;   // 8 (fc32) or 4 (sc16)
+    float sc16_scale = 0.f;        // != 0: the group is converted from d_sc16 to d_iq on the compute stream once it has arrived
+};
+
+// The receive pipeline over the links in h->h_links.  `iq` is device memory.  The links are processed in GROUPS of
+// whole links (one group for device-resident input): with host input (`plan`) the copy of group g + 1 runs on the copy
+// stream while group g is decoded, and the results of group g travel back on a third stream while group g + 1 is
+// decoded -- one cudaMemcpyAsync per group and direction.  Frame records, rows and PSDU slots of the groups follow each
+// other in link order, so the result is the same table as from one pass over all links.
+int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullptr)
 {
     const int n_links = (int)h->h_links.size();
     int64_t total_tiles = 0, total = 0;
@@ -379,92 +395,142 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
     h->n_frames = h->n_jobs = h->n_rows = 0;
     h->n_samples = total;
     h->host_mirror = h->psdu_mirror = false;
-    bool h2d_marked = h->ev_used[ST_H2D];
     for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
-    h->ev_used[ST_H2D] = h2d_marked;
     memset(h->stage_ms, 0, sizeof h->stage_ms);
     const double thr = h->cfg.sensitivity;
     float thr_f = (float)thr;   // (double)c > thr  <=>  c > largest float <= thr
     if ((double)thr_f > thr) thr_f = nextafterf(thr_f, -INFINITY);
     cudaStream_t s = h->stream;
-    CK(cudaMemcpyAsync(h->d_links, h->h_links.data(), n_links * sizeof(LinkDesc), cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(h->d_counters, 0, 64, s));
-    mark(h, ST_DETECT);
-    if (total_tiles > 0)
-        k_detect<<<(unsigned)total_tiles, DET_THREADS, DET_SMEM, s>>>(iq, h->d_links, n_links, total_tiles, thr_f, h->d_flags, h->d_summary);
-    mark(h, ST_SELECT);
-    if (total_tiles > 0)
-        k_select_spec<<<(unsigned)((total_tiles * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, total_tiles,
-                                                                              h->cfg.min_plateau, h->d_spec_trig, h->d_spec_cnt);
-    k_select<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, h->d_links, n_links, h->cfg.min_plateau, h->d_trig_tmp,
-                                                        h->d_spec_trig, h->d_spec_cnt);
-    k_reserve<<<1, 1024, 0, s>>>(h->d_links, n_links, h->d_counters, (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames,
-                                 h->d_counters + 2);
-    k_frames_init<<<dim3(8, n_links), 128, 0, s>>>(h->d_links, h->d_trig_tmp, h->d_frames);
-    mark(h, ST_SYNC_LONG);
-    CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (h->h_counters[2] != 0 || h->h_counters[0] > h->cfg.max_frames) {
-        h->err = "more sync_short triggers than max_frames";
-        return WIFI_E_OVERFLOW;
-    }
-    int64_t nf = h->h_counters[0];
-    int64_t rows_needed = *(int64_t *)(h->h_counters + 8);
-    if (rows_needed > h->row_cap) {
-        h->err = "row capacity exceeded";
-        return WIFI_E_OVERFLOW;
-    }
-    h->n_triggers = nf;
-    h->n_frames = nf;
-    h->n_jobs = nf;       // decode jobs live at the index of their owner frame
-    h->n_rows = rows_needed;
-    if (nf > 0) {
-        const int soft = h->cfg.soft_decision ? 1 : 0;
-        if (soft) { int rc_ = ensure_soft(h); if (rc_) return rc_; }
-        DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier, soft};
-        k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf);
-        mark(h, ST_DEMOD_HEAD);
-        typedef void (*demod_fn)(const cf *, const LinkDesc *, wifi_b200_frame *, int, EqState *, uint8_t *, cf *, DemodParams,
-                                 const uint16_t *, uint32_t *, int8_t *, uint32_t *);
-#define DEMOD_ROW(S, P) {k_demod<S, WIFI_EQ_LS, P>, k_demod<S, WIFI_EQ_LMS, P>, k_demod<S, WIFI_EQ_COMB, P>, k_demod<S, WIFI_EQ_STA, P>}
-        static const demod_fn demod_tab[2][2][4] = {{DEMOD_ROW(false, 0), DEMOD_ROW(false, 1)}, {DEMOD_ROW(true, 0), DEMOD_ROW(true, 1)}};
-#undef DEMOD_ROW
-        const demod_fn demod_head = demod_tab[soft ? 1 : 0][0][prm.algo & 3], demod_data = demod_tab[soft ? 1 : 0][1][prm.algo & 3];
-        demod_head<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm,
-                                                        h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
-        mark(h, ST_SIGNAL);
-        k_signal<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, 0, s>>>(h->d_frames, (int)nf, h->d_states);
-        mark(h, ST_DEMOD_DATA);
-        demod_data<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, (int)nf, h->d_states, h->d_rows, h->d_carrier, prm,
-                                                        h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
-        mark(h, ST_PLAN);
-        CK(cudaMemsetAsync(h->d_link_dirty, 0, (size_t)n_links * sizeof(int), s));
-        CK(cudaMemsetAsync(h->d_link_dirty + MAX_LINKS, 0xff, (size_t)n_links * sizeof(int), s));
-        k_plan_fast<<<(unsigned)((nf + 127) / 128), 128, 0, s>>>(h->d_frames, (int)nf, h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_link_dirty, soft);
-        k_plan<<<(n_links * 32 + 127) / 128, 128, 0, s>>>(h->d_links, n_links, h->d_frames, h->d_jobs, h->d_pack_list, h->d_counters + 1,
-                                                          h->d_counters + 2, soft, h->d_link_dirty, h->d_link_dirty + MAX_LINKS);
-        mark(h, ST_PACK);
-        size_t smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256 + 128;   // ring, CRC table, descrambler table, branch words
-        if (!soft) {
-            k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in, h->d_frames);
-            mark(h, ST_VITERBI);
-            // a handful of frames (streaming runs): one trellis per warp, a third of the latency; else one per thread
-            if (nf <= VW_SWITCH) k_viterbi_warp<<<(unsigned)((nf + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
-            else k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_in, h->d_psdu, h->d_frames);
-        } else {
-            k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in, h->d_frames);
-            mark(h, ST_VITERBI);
-            k_viterbi_soft<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, smem, s>>>(h->d_jobs, (int)nf, h->d_vit_soft_in, h->d_psdu, h->d_frames);
+    // link groups: about 16 M samples each when the input comes from the host (copy / decode overlap), else one
+    std::vector<int> gstart{0};
+    if (plan && n_links > 1) {
+        const int64_t target = std::max<int64_t>(total / 16, (int64_t)1 << 22);
+        int64_t acc = 0;
+        for (int l = 0; l < n_links; ++l) {
+            acc += h->h_links[l].len;
+            if (acc >= target && l + 1 < n_links) { gstart.push_back(l + 1); acc = 0; }
         }
     }
-    mark(h, ST_D2H);
-    if (mirror && h->n_triggers > 0) {
-        CK(cudaMemcpyAsync(h->h_frames, h->d_frames, h->n_triggers * sizeof(wifi_b200_frame), cudaMemcpyDeviceToHost, s));
-        if (h->n_jobs > 0) CK(cudaMemcpyAsync(h->h_psdu, h->d_psdu, (size_t)h->n_jobs * PSDU_STRIDE, cudaMemcpyDeviceToHost, s));
+    gstart.push_back(n_links);
+    const int n_groups = (int)gstart.size() - 1;
+    while ((int)h->ev_h2d.size() < n_groups) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_h2d.push_back(a);
+        h->ev_done.push_back(b);
     }
+    if (plan) {
+        mark(h, ST_H2D);
+        for (int g = 0; g < n_groups; ++g) {
+            const int64_t o0 = h->h_links[gstart[g]].x_off, o1 = h->h_links[gstart[g + 1] - 1].x_off + h->h_links[gstart[g + 1] - 1].len;
+            void *dst = plan->bytes_per_sample == 8 ? (void *)(h->d_iq + o0) : (void *)(h->d_sc16 + 2 * o0);
+            CK(cudaMemcpyAsync(dst, (const char *)plan->src + (size_t)o0 * plan->bytes_per_sample, (size_t)(o1 - o0) * plan->bytes_per_sample,
+                               cudaMemcpyHostToDevice, h->copy_stream));
+            CK(cudaEventRecord(h->ev_h2d[g], h->copy_stream));
+        }
+    }
+    CK(cudaMemcpyAsync(h->d_links, h->h_links.data(), n_links * sizeof(LinkDesc), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->d_counters, 0, 64, s));
+    const int soft = h->cfg.soft_decision ? 1 : 0;
+    if (soft) { int rc_ = ensure_soft(h); if (rc_) return rc_; }
+    const DemodParams prm{h->cfg.bandwidth, h->cfg.frequency, h->cfg.chan_est, h->cfg.want_carrier, soft};
+    typedef void (*demod_fn)(const cf *, const LinkDesc *, wifi_b200_frame *, int, int, EqState *, uint8_t *, cf *, DemodParams,
+                             const uint16_t *, uint32_t *, int8_t *, uint32_t *);
+#define DEMOD_ROW(S, P) {k_demod<S, WIFI_EQ_LS, P>, k_demod<S, WIFI_EQ_LMS, P>, k_demod<S, WIFI_EQ_COMB, P>, k_demod<S, WIFI_EQ_STA, P>}
+    static const demod_fn demod_tab[2][2][4] = {{DEMOD_ROW(false, 0), DEMOD_ROW(false, 1)}, {DEMOD_ROW(true, 0), DEMOD_ROW(true, 1)}};
+#undef DEMOD_ROW
+    const demod_fn demod_head = demod_tab[soft][0][prm.algo & 3], demod_data = demod_tab[soft][1][prm.algo & 3];
+    const size_t vit_smem = (size_t)(VIT_NTB_MAX * 16 * VIT_BLOCK + 256) * 4 + 256 + 128;   // ring, CRC table, descrambler table, branch words
+    const bool timed = n_groups == 1;              // per-stage events only make sense for a single pass
+    int64_t frame_base = 0, row_base = 0, tile_base = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int lb = gstart[g], ng = gstart[g + 1] - gstart[g];
+        int64_t tiles_g = 0, samples_g = 0;
+        for (int l = lb; l < lb + ng; ++l) { tiles_g += (h->h_links[l].len + DET_TILE - 1) / DET_TILE; samples_g += h->h_links[l].len; }
+        LinkDesc *gl = h->d_links + lb;
+        if (plan) {
+            CK(cudaStreamWaitEvent(s, h->ev_h2d[g], 0));
+            if (plan->sc16_scale != 0.f && samples_g > 0) {
+                const int64_t o0 = h->h_links[lb].x_off;
+                int64_t blocks = std::min<int64_t>((samples_g / 4 + 255) / 256 + 1, 148 * 16);
+                k_sc16_to_fc32<<<(unsigned)blocks, 256, 0, s>>>(h->d_sc16 + 2 * o0, h->d_iq + o0, samples_g, plan->sc16_scale);
+            }
+        }
+        if (timed) mark(h, ST_DETECT);
+        if (tiles_g > 0)
+            k_detect<<<(unsigned)tiles_g, DET_THREADS, DET_SMEM, s>>>(iq, gl, ng, tile_base, tile_base + tiles_g, thr_f, h->d_flags, h->d_summary);
+        if (timed) mark(h, ST_SELECT);
+        if (tiles_g > 0)
+            k_select_spec<<<(unsigned)((tiles_g * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, tile_base, tile_base + tiles_g,
+                                                                                h->cfg.min_plateau, h->d_spec_trig, h->d_spec_cnt);
+        k_select<<<(ng * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, h->cfg.min_plateau, h->d_trig_tmp, h->d_spec_trig, h->d_spec_cnt);
+        k_reserve<<<1, 1024, 0, s>>>(gl, ng, h->d_counters, (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames, h->d_counters + 2,
+                                     (long long)frame_base, (long long)row_base);
+        k_frames_init<<<dim3(8, ng), 128, 0, s>>>(gl, h->d_trig_tmp, h->d_frames, lb);
+        if (timed) mark(h, ST_SYNC_LONG);
+        CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h->h_counters[2] != 0 || h->h_counters[0] > h->cfg.max_frames) {
+            h->err = "more sync_short triggers than max_frames";
+            return WIFI_E_OVERFLOW;
+        }
+        const int64_t f_end = h->h_counters[0], nf = f_end - frame_base;
+        const int64_t rows_needed = *(int64_t *)(h->h_counters + 8);
+        if (rows_needed > h->row_cap) {
+            h->err = "row capacity exceeded";
+            return WIFI_E_OVERFLOW;
+        }
+        const int f0 = (int)frame_base, fe = (int)f_end;
+        if (nf > 0) {
+            k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, f0, fe);
+            if (timed) mark(h, ST_DEMOD_HEAD);
+            demod_head<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, f0, fe, h->d_states, h->d_rows, h->d_carrier, prm,
+                                                            h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
+            if (timed) mark(h, ST_SIGNAL);
+            k_signal<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, 0, s>>>(h->d_frames, f0, fe, h->d_states);
+            if (timed) mark(h, ST_DEMOD_DATA);
+            demod_data<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, f0, fe, h->d_states, h->d_rows, h->d_carrier, prm,
+                                                            h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
+            if (timed) mark(h, ST_PLAN);
+            CK(cudaMemsetAsync(h->d_link_dirty + lb, 0, (size_t)ng * sizeof(int), s));
+            CK(cudaMemsetAsync(h->d_link_dirty + MAX_LINKS + lb, 0xff, (size_t)ng * sizeof(int), s));
+            CK(cudaMemsetAsync(h->d_counters + 1, 0, sizeof(int), s));          // the pack list starts over with every group
+            k_plan_fast<<<(unsigned)((nf + 127) / 128), 128, 0, s>>>(h->d_frames, f0, fe, h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_link_dirty, soft);
+            k_plan<<<(ng * 32 + 127) / 128, 128, 0, s>>>(gl, ng, h->d_frames, h->d_jobs, h->d_pack_list, h->d_counters + 1,
+                                                         h->d_counters + 2, soft, h->d_link_dirty + lb, h->d_link_dirty + MAX_LINKS + lb);
+            if (timed) mark(h, ST_PACK);
+            if (!soft) {
+                k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in, h->d_frames);
+                if (timed) mark(h, ST_VITERBI);
+                // a handful of frames (streaming runs, small link groups): one trellis per warp, a third of the latency; else one per thread
+                if (nf <= VW_SWITCH) k_viterbi_warp<<<(unsigned)((nf + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
+                else k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, vit_smem, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
+            } else {
+                k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in, h->d_frames);
+                if (timed) mark(h, ST_VITERBI);
+                k_viterbi_soft<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, vit_smem, s>>>(h->d_jobs, f0, fe, h->d_vit_soft_in, h->d_psdu, h->d_frames);
+            }
+            if (mirror) {
+                // results of this group go home on their own stream while the next group is decoded
+                CK(cudaEventRecord(h->ev_done[g], s));
+                CK(cudaStreamWaitEvent(h->d2h_stream, h->ev_done[g], 0));
+                CK(cudaMemcpyAsync(h->h_frames + f0, h->d_frames + f0, (size_t)nf * sizeof(wifi_b200_frame), cudaMemcpyDeviceToHost, h->d2h_stream));
+                CK(cudaMemcpyAsync(h->h_psdu + (size_t)f0 * PSDU_STRIDE, (const uint8_t *)h->d_psdu + (size_t)f0 * PSDU_STRIDE, (size_t)nf * PSDU_STRIDE,
+                                   cudaMemcpyDeviceToHost, h->d2h_stream));
+            }
+        }
+        frame_base = f_end;
+        row_base = rows_needed;
+        tile_base += tiles_g;
+    }
+    h->n_triggers = h->n_frames = h->n_jobs = frame_base;       // decode jobs live at the index of their owner frame
+    h->n_rows = row_base;
+    if (timed) mark(h, ST_D2H);
     mark(h, ST_COUNT);
     CK(cudaMemcpyAsync(h->h_counters, h->d_counters, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (mirror) CK(cudaStreamSynchronize(h->d2h_stream));
     CK(cudaGetLastError());
     if (h->h_counters[2] != 0) {
         h->err = "receive pipeline reported an internal overflow";
@@ -479,6 +545,18 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror)
         prev = i;
     }
     return WIFI_OK;
+}
+
+// run_rx with host input: whatever happens, the caller's buffer is no longer being read when the call returns
+int run_rx_host(wifi_b200 *h, const H2dPlan &plan)
+{
+    int rc = run_rx(h, h->d_iq, true, &plan);
+    if (rc != WIFI_OK) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->d2h_stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    return rc;
 }
 
 int fetch_frames(wifi_b200 *h)
@@ -591,6 +669,8 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     auto fail = [&](int code) { free_all(h); delete h; return code; };
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(WIFI_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
     for (int i = 0; i <= ST_COUNT; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) return fail(WIFI_E_CUDA);
     if (upload_tables(h) != WIFI_OK) return fail(WIFI_E_CUDA);
     if (cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM) != cudaSuccess) return fail(WIFI_E_CUDA);
@@ -903,18 +983,11 @@ int wifi_b200_rx_batch(wifi_b200_t *h, const float *iq_host, const uint64_t *lin
     if (rc) return rc;
     // rebase the links onto the staging buffer
     uint64_t base = link_off[0];
-    int64_t total = (int64_t)(link_off[n_links] - base);
     for (auto &L : h->h_links) L.x_off -= (int64_t)base;
-    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
-    mark(h, ST_H2D);
-    {
-        // One host->device capture copy at a time per GPU: with two handles driven from two threads the
-        // copy of one batch then overlaps the kernels of the other instead of halving its PCIe share.
-        std::lock_guard<std::mutex> lk(g_h2d_mu[h->device & 63]);
-        CK(cudaMemcpyAsync(h->d_iq, iq_host + 2 * base, (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    }
-    rc = run_rx(h, h->d_iq, true);
+    H2dPlan plan;
+    plan.src = iq_host + 2 * base;
+    plan.bytes_per_sample = sizeof(cf);
+    rc = run_rx_host(h, plan);
     if (rc) return rc;
     update_stats(h);
     return WIFI_OK;
@@ -932,21 +1005,13 @@ int wifi_b200_rx_batch_sc16(wifi_b200_t *h, const int16_t *iq_host, float scale,
     rc = ensure_sc16_staging(h);
     if (rc) return rc;
     uint64_t base = link_off[0];
-    int64_t total = (int64_t)(link_off[n_links] - base);
     for (auto &L : h->h_links) L.x_off -= (int64_t)base;
-    for (int i = 0; i <= ST_COUNT; ++i) h->ev_used[i] = false;
-    mark(h, ST_H2D);
-    {
-        std::lock_guard<std::mutex> lk(g_h2d_mu[h->device & 63]);     // one capture copy at a time per GPU (see rx_batch)
-        CK(cudaMemcpyAsync(h->d_sc16, iq_host + 2 * base, (size_t)total * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    }
-    if (total > 0) {
-        int64_t blocks = (total / 4 + 255) / 256 + 1;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        k_sc16_to_fc32<<<(unsigned)blocks, 256, 0, h->stream>>>(h->d_sc16, h->d_iq, total, scale);
-    }
-    rc = run_rx(h, h->d_iq, true);
+    H2dPlan plan;
+    plan.src = iq_host + 2 * base;
+    plan.bytes_per_sample = 2 * sizeof(int16_t);
+    if (scale == 0.f) { h->err = "sc16 scale must not be 0"; return WIFI_E_ARG; }
+    plan.sc16_scale = scale;
+    rc = run_rx_host(h, plan);
     if (rc) return rc;
     update_stats(h);
     return WIFI_OK;
