@@ -401,10 +401,12 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
     float thr_f = (float)thr;   // (double)c > thr  <=>  c > largest float <= thr
     if ((double)thr_f > thr) thr_f = nextafterf(thr_f, -INFINITY);
     cudaStream_t s = h->stream;
-    // link groups: about 16 M samples each when the input comes from the host (copy / decode overlap), else one
+    // link groups when the input comes from the host (copy / decode overlap), else one
     std::vector<int> gstart{0};
     if (plan && n_links > 1) {
-        const int64_t target = std::max<int64_t>(total / 16, (int64_t)1 << 22);
+        // about 128 MB of host bytes per group: its copy then takes longer than its decode (a group costs 1.5 - 3 ms of
+        // kernels whatever its size: the Viterbi launch is latency bound), so the decode hides behind the next copy
+        const int64_t target = std::max<int64_t>(((int64_t)128 << 20) / (int64_t)plan->bytes_per_sample, (int64_t)1 << 22);
         int64_t acc = 0;
         for (int l = 0; l < n_links; ++l) {
             acc += h->h_links[l].len;

@@ -186,6 +186,88 @@ def test_annex_g_message_fcs_geometry_and_loopback(O):
     assert (int(f["encoding"]), int(f["length"]), int(f["frame_symbols"])) == (5, 100, 6)
 
 
+# Intermediate tables of the same example (36 Mb/s, 16-QAM 3/4, scrambler state 1011101), restated from the standard:
+# scrambled DATA bits (Table L-15 / G.16, first 144, eight bits per hex pair in transmit order), the coded and punctured
+# stream (L-17 / G.18, first 144), the interleaved bits of the first DATA symbol (L-20 / G.21, all 192), its first mapped
+# carriers (L-21 / G.22) and the first time samples of the SIGNAL and first DATA symbols (L-12 / L-24; the standard scales
+# its IFFT by 1/64 where the flowgraph scales to unit power: x sqrt(52)/64).  tests/ref_model.py reproduces every one.
+ANNEX_G_SCRAMBLED_144 = "6c19898f6821f4a5614fd7ae240cf33ae4bc"
+ANNEX_G_CODED_144 = ("0010 1011 0000 1000 1010 0001 1111 0000 1001 1101 1011 0101 1001 1010 0001 1101 0100 1010 1111 1011 1110 1000 1100 0010 "
+                     "1000 1111 1100 0000 1100 1000 0111 0011 1100 0000 0100 0011").replace(" ", "")
+ANNEX_G_INTERLEAVED_SYM1 = ("0111 0111 1111 0000 1110 1111 1100 0100 0111 0011 0000 0000 1011 1111 0001 0001 0001 0000 1001 1010 0001 1101 0001 0010 "
+                            "0110 1110 0011 1000 1111 0101 0110 1001 0001 1011 0110 1011 1001 1000 0100 0011 0000 0000 0000 1101 1011 0011 0110 1101").replace(" ", "")
+ANNEX_G_FREQ_SYM1 = [-1 + 1j, -1 + 1j, 1 + 1j, -3 - 3j, 1 + 3j, 1 + 1j, 1 - 3j, -1 - 3j]        # x 1/sqrt(10): carriers -26..-22, -20..-18
+ANNEX_G_TIME_SIGNAL_1_7 = [0.033 - 0.044j, -0.002 - 0.038j, -0.081 + 0.084j, 0.007 - 0.100j, -0.001 - 0.113j, -0.021 - 0.005j, 0.136 - 0.105j]
+ANNEX_G_TIME_DATA1_0_15 = [-0.139 + 0.050j, 0.004 + 0.014j, 0.011 - 0.100j, -0.097 - 0.020j, 0.062 + 0.081j, 0.124 + 0.139j, 0.104 - 0.015j,
+                           0.173 - 0.140j, -0.040 + 0.006j, -0.133 + 0.009j, -0.002 - 0.043j, -0.047 + 0.092j, -0.109 + 0.082j, -0.024 + 0.010j,
+                           0.096 + 0.019j, 0.019 - 0.023j]
+
+
+def test_annex_g_intermediate_tables(O):
+    psdu = ANNEX_G_HDR + ANNEX_G_TEXT + ANNEX_G_FCS
+    n_data = 6 * 144
+    bits = np.zeros(n_data, np.uint8)
+    bits[16:16 + 800] = np.unpackbits(np.frombuffer(psdu, np.uint8), bitorder="little")
+    scr = O.scramble(bits, 0b1011101)
+    assert np.packbits(scr[:144]).tobytes().hex() == ANNEX_G_SCRAMBLED_144
+    scr[816:822] = 0                                                   # the six tail bits are zeroed after scrambling
+    coded = O.puncture(O.conv_encode(scr), 5)
+    assert coded.size == 6 * 192 and "".join(map(str, coded[:144])) == ANNEX_G_CODED_144
+    inter = O.interleave(coded, 5)
+    assert "".join(map(str, inter[:192])) == ANNEX_G_INTERLEAVED_SYM1
+    # the mapper's whole pipeline (generate_bits .. split_symbols): bit k of a carrier index is coded bit b_k
+    idx = O.tx_symbols(psdu, 5, 0b1011101)
+    assert idx.shape == (6, 48)
+    assert "".join(str((int(v) >> k) & 1) for v in idx[0] for k in range(4)) == ANNEX_G_INTERLEAVED_SYM1
+    cons = O.constellation(5)
+    assert np.allclose(cons[idx[0, :8]] * np.sqrt(10), ANNEX_G_FREQ_SYM1, atol=1e-6)
+    iq = O.tx_frame(psdu, 5, 0b1011101) * (np.sqrt(52) / 64)
+    for got, want in ((iq[321:328], ANNEX_G_TIME_SIGNAL_1_7), (iq[400:416], ANNEX_G_TIME_DATA1_0_15)):
+        d = got - np.array(want)
+        assert max(np.abs(d.real).max(), np.abs(d.imag).max()) < 5.5e-4            # three printed decimals per component
+    # and the independent model agrees with every table as well
+    import ref_model as M
+    mscr, _ = M.data_bits(psdu, 5, 0b1011101)
+    assert np.array_equal(mscr, scr) and np.array_equal(M.puncture(M.conv_encode(mscr), 5), coded)
+
+
+def test_truncated_traceback_against_full_traceback_on_short_pads(O):
+    """DESIGN.md choice 2 as a tested property.  upstream's decoder (and the oracle) keeps tracing back `ntraceback` bytes
+    behind the coded frame and reads zeros there; a maximum-likelihood decoder with full traceback
+    (tests/ref_model.viterbi_full) has no such tail.  On a CLEAN channel, over all 8 MCS and PSDU lengths 30..329:
+    the oracle returns every PSDU byte correctly unless the code rate is 3/4 and only 6 or 10 pad bits follow the tail
+    bits; then the LAST PSDU byte (the end of the FCS) is wrong in about 17 % (pad 6: BPSK 3/4 only) / 4 % (pad 10) of
+    the frames, and nothing else ever is.  The full-traceback decoder gets those same frames right."""
+    import ref_model as M
+    rng = np.random.default_rng(12)
+    ntb = {0: 5, 1: 10, 2: 5, 3: 10, 4: 5, 5: 10, 6: 9, 7: 10}
+    fails, total, replay = {}, {}, []
+    for enc in range(8):
+        nd = M.N_DBPS[enc]
+        for L in range(30, 330):
+            pad = -(-(22 + 8 * L) // nd) * nd - (22 + 8 * L)
+            for _ in range(2):
+                psdu = bytes(rng.integers(0, 256, L, dtype=np.uint8))
+                scr, _n = M.data_bits(psdu, enc, int(rng.integers(1, 128)))
+                pat = np.resize(np.array(M.PUNCT[enc], bool), 2 * scr.size)
+                dep = np.full(pat.size, 2, np.uint8)
+                dep[pat] = M.puncture(M.conv_encode(scr), enc)
+                got = O.viterbi(dep, scr.size, ntb[enc])
+                diff = np.nonzero(got[16:16 + 8 * L] != scr[16:16 + 8 * L])[0]
+                key = (M.PUNCT[enc] == (1, 1, 1, 0, 0, 1), pad)
+                total[key] = total.get(key, 0) + 1
+                if len(diff):
+                    fails[key] = fails.get(key, 0) + 1
+                    assert diff.min() // 8 == L - 1, (enc, L, pad)              # only ever the last PSDU byte
+                    if len(replay) < 1 and L < 60:
+                        replay.append((dep, scr, L))
+    assert set(fails) == {(True, 6), (True, 10)}, fails                           # rate 3/4 with a 6- or 10-bit pad, nothing else
+    r6, r10 = fails[(True, 6)] / total[(True, 6)], fails[(True, 10)] / total[(True, 10)]
+    assert 0.08 < r6 < 0.30 and 0.01 < r10 < 0.10, (r6, r10)
+    for dep, scr, L in replay:                                                    # ML with full traceback decodes the same input correctly
+        assert np.array_equal(M.viterbi_full(dep)[:16 + 8 * L], scr[:16 + 8 * L])
+
+
 def test_oracle_matches_its_committed_digests(O):
     """The oracle defines parity for the CUDA library: its outputs for fixed seeds are pinned by digests
     (tests/golden/oracle_regression.json, regenerated only by tests/golden/make_oracle_regression.py), so a change of
