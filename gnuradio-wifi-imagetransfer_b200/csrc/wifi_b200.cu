@@ -224,6 +224,13 @@ struct wifi_b200 {
     int64_t s_unprocessed = 0;     // samples appended to the fullest link since the last pipeline run
     std::vector<wifi_b200_frame> s_meta;
     std::vector<uint8_t> s_bytes;
+    // asynchronous pushes (wifi_b200_rx_push_links_async): up to two in flight, each with its device staging buffer
+    struct AsyncPush { int slot = 0; int flush = 0; std::vector<uint64_t> off; };
+    std::vector<AsyncPush> a_pending;
+    cf *d_stage[2] = {nullptr, nullptr};
+    size_t a_cap[2] = {0, 0};
+    cudaEvent_t a_ev[2] = {nullptr, nullptr};
+    int a_next = 0;
 };
 
 namespace {
@@ -258,7 +265,8 @@ int upload_tables(wifi_b200 *h)
 void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
+    for (int k = 0; k < 2; ++k) if (h->a_ev[k]) cudaEventDestroy(h->a_ev[k]);
+    void *ptrs[] = {h->d_stage[0], h->d_stage[1], h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
                     h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -1101,6 +1109,9 @@ int wifi_b200_rx_reset(wifi_b200_t *h)
 {
     if (!h) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->copy_stream);
+    h->a_pending.clear();
     h->s_links.clear();
     h->s_cap = 0;
     h->s_unprocessed = 0;
@@ -1112,7 +1123,9 @@ int wifi_b200_rx_reset(wifi_b200_t *h)
 // Samples are copied once, from the caller's buffer into the link's region of a device arena (pinned caller memory
 // makes that a plain DMA), and stay on the device: a run decodes the regions in place, then every link's retained
 // tail (history + held / deferred bursts) slides to the front of its region.
-static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, int n_links, int flush)
+// dev_src != nullptr: the new samples already sit in device memory (the staging buffer of an asynchronous push, link l at
+// dev_src[link_off[l]]) and are appended by a copy kernel; else they are copied from the host buffer `iq`.
+static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, int n_links, int flush, const cf *dev_src = nullptr)
 {
     if (n_links <= 0 || n_links > MAX_LINKS) return WIFI_E_ARG;
     cudaSetDevice(h->device);
@@ -1131,19 +1144,26 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
         pushed += n;
     }
     int64_t have_all = 0, fullest = 0;
+    std::vector<wifi_b200::MoveSeg> app;
     for (int l = 0; l < n_links; ++l) {
         auto &S = h->s_links[l];
         const int64_t n = (int64_t)(link_off[l + 1] - link_off[l]);
-        if (n) CK(cudaMemcpyAsync(h->d_stream + (int64_t)l * h->s_cap + S.fill, iq + 2 * link_off[l], (size_t)n * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
+        if (n && !dev_src) CK(cudaMemcpyAsync(h->d_stream + (int64_t)l * h->s_cap + S.fill, iq + 2 * link_off[l], (size_t)n * sizeof(cf), cudaMemcpyHostToDevice, h->stream));
+        if (n && dev_src) app.push_back({(int64_t)link_off[l], (int64_t)l * h->s_cap + S.fill, n});
         S.fill += n;
         have_all += S.fill - S.hist;
         if (S.fill > fullest) fullest = S.fill;
+    }
+    if (!app.empty()) {
+        CK(cudaMemcpyAsync(h->d_moves, app.data(), app.size() * sizeof(wifi_b200::MoveSeg), cudaMemcpyHostToDevice, h->stream));
+        unsigned bx = (unsigned)std::min<int64_t>((newest + 2047) / 2048, 64);
+        k_move_segments<<<dim3(bx ? bx : 1, (unsigned)app.size()), 256, 0, h->stream>>>(dev_src, h->d_stream, h->d_moves);
     }
     h->s_unprocessed += newest;
     // small pushes only buffer: a pipeline run has a fixed cost of about a millisecond (the decoder's latency for the
     // longest frame), so it runs when enough new samples wait, when a region is half full, on an empty push, or on flush
     if (have_all <= 0 || (!flush && pushed != 0 && h->s_unprocessed < h->s_batch && 2 * fullest < h->s_cap)) {
-        if (pushed) {
+        if (pushed && !dev_src) {
             // The caller's buffer must be free again when the call returns.  A copy from pageable memory has left the
             // source when cudaMemcpyAsync returns (it is staged); only page-locked sources are read asynchronously.
             cudaPointerAttributes at;
@@ -1277,6 +1297,55 @@ int wifi_b200_rx_push_links(wifi_b200_t *h, const float *iq, const uint64_t *lin
     if (!iq && link_off[n_links] != link_off[0]) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
     return stream_push(h, iq, link_off, n_links, flush);
+}
+
+int wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq, const uint64_t *link_off, int n_links, int flush)
+{
+    if (!h || !link_off || n_links <= 0 || n_links > MAX_LINKS) return WIFI_E_ARG;
+    for (int l = 0; l < n_links; ++l)
+        if (link_off[l + 1] < link_off[l]) return WIFI_E_ARG;
+    const int64_t total = (int64_t)(link_off[n_links] - link_off[0]);
+    if (!iq && total) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (h->a_pending.size() >= 2) { h->err = "two asynchronous pushes are already pending: call wifi_b200_rx_push_wait first"; return WIFI_E_OVERFLOW; }
+    if (total > h->cfg.max_samples) { h->err = "push larger than max_samples"; return WIFI_E_OVERFLOW; }
+    const int slot = h->a_next & 1;
+    if ((int64_t)h->a_cap[slot] < total) {
+        if (h->d_stage[slot]) cudaFree(h->d_stage[slot]);
+        h->d_stage[slot] = nullptr;
+        h->a_cap[slot] = 0;
+        CK(cudaMalloc(&h->d_stage[slot], (size_t)(total + 64) * sizeof(cf)));
+        h->a_cap[slot] = (size_t)total + 64;
+    }
+    if (!h->a_ev[slot]) CK(cudaEventCreateWithFlags(&h->a_ev[slot], cudaEventDisableTiming));
+    wifi_b200::AsyncPush job;
+    job.slot = slot;
+    job.flush = flush;
+    job.off.resize(n_links + 1);
+    for (int l = 0; l <= n_links; ++l) job.off[l] = link_off[l] - link_off[0];
+    // one copy for the whole push (the links lie back to back in the caller's buffer), on the copy stream: it runs while
+    // the pipeline of the push before it is still decoding
+    if (total) CK(cudaMemcpyAsync(h->d_stage[slot], iq + 2 * link_off[0], (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->a_ev[slot], h->copy_stream));
+    h->a_pending.push_back(std::move(job));
+    h->a_next++;
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_push_wait(wifi_b200_t *h)
+{
+    if (!h) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    if (h->a_pending.empty()) return 0;
+    wifi_b200::AsyncPush job = std::move(h->a_pending.front());
+    h->a_pending.erase(h->a_pending.begin());
+    CK(cudaStreamWaitEvent(h->stream, h->a_ev[job.slot], 0));
+    int rc = stream_push(h, nullptr, job.off.data(), (int)job.off.size() - 1, job.flush, h->d_stage[job.slot]);
+    // the staging buffer may be written by the next asynchronous push only after the append kernel has read it
+    cudaStreamSynchronize(h->stream);
+    return rc < 0 ? rc : 1;
 }
 
 int wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *psdu_buf, size_t psdu_cap, int *n_out)

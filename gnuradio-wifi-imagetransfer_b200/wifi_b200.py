@@ -62,7 +62,7 @@ EXPORTS = [
     "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_dev_state", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_rx_push_links", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
-    "wifi_b200_selftest_detmath", "wifi_b200_alu_peak",
+    "wifi_b200_selftest_detmath", "wifi_b200_alu_peak", "wifi_b200_rx_push_links_async", "wifi_b200_rx_push_wait",
 ]
 
 _LIB = None
@@ -107,6 +107,8 @@ def lib():
         L.wifi_b200_rx_flags.argtypes = [vp, C.c_int, vp, i64]
         L.wifi_b200_rx_push.argtypes = [vp, vp, C.c_size_t, C.c_int]
         L.wifi_b200_rx_push_links.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.wifi_b200_rx_push_links_async.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.wifi_b200_rx_push_wait.argtypes = [vp]
         L.wifi_b200_rx_pop.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_int)]
         L.wifi_b200_rx_reset.argtypes = [vp]
         L.wifi_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -345,6 +347,17 @@ class Handle:
         a = blob if (isinstance(blob, np.ndarray) and blob.dtype == np.complex64 and blob.flags.c_contiguous) else np.ascontiguousarray(blob, np.complex64)
         off = np.ascontiguousarray(link_off, np.uint64)
         self._ck(self._L.wifi_b200_rx_push_links(self._h, _p(a) if a.size else None, _p(off), off.size - 1, int(flush)))
+
+    def rx_push_links_async(self, blob, link_off, flush=False):
+        """Queues the copy of this push and returns; `blob` (page-locked complex64) must stay untouched until the
+        rx_push_wait() that completes it.  At most two pushes may be pending."""
+        assert isinstance(blob, np.ndarray) and blob.dtype == np.complex64 and blob.flags.c_contiguous
+        off = np.ascontiguousarray(link_off, np.uint64)
+        self._ck(self._L.wifi_b200_rx_push_links_async(self._h, _p(blob) if blob.size else None, _p(off), off.size - 1, int(flush)))
+
+    def rx_push_wait(self):
+        """Completes the oldest pending asynchronous push (copy done, pipeline run); True if there was one."""
+        return self._ck(self._L.wifi_b200_rx_push_wait(self._h)) == 1
 
     def rx_pop(self, cap=256):
         meta = np.zeros(cap, FRAME_DTYPE)

@@ -356,6 +356,59 @@ def test_udp_runner_speaks_the_apps_contract(O, W):
     t.close()
 
 
+def test_asynchronous_pushes_equal_synchronous_ones(O, W):
+    """wifi_b200_rx_push_links_async / _rx_push_wait with two page-locked buffers used in turn: the copy of push k + 1 is in
+    flight while push k is decoded; the frames that come out are those of the synchronous calls, in the same order."""
+    import torch
+    rng = np.random.default_rng(61)
+    n_links, chunk = 5, 6000
+    caps = [make_capture(O, rng, [(int(rng.integers(0, 8)), int(rng.integers(60, 500))) for _ in range(9)], snr_db=28,
+                         cfo=float(rng.uniform(-0.01, 0.01)), seed=l, lead=int(rng.integers(50, 400)))[0] for l in range(n_links)]
+    n_push = max(-(-c.size // chunk) for c in caps)
+    off = (np.arange(n_links + 1) * chunk).astype(np.uint64)
+
+    def fill(buf, k):
+        for l, c in enumerate(caps):
+            seg = c[k * chunk:(k + 1) * chunk]
+            buf[l * chunk:l * chunk + seg.size] = seg
+            buf[l * chunk + seg.size:(l + 1) * chunk] = 0
+
+    def run(asynchronous):
+        h = W.Handle(max_samples=n_links * (1 << 17), max_frames=512)
+        pins = [torch.empty(2 * n_links * chunk, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        bufs = [p.numpy().view(np.complex64) for p in pins]
+        out = []
+        if not asynchronous:
+            for k in range(n_push):
+                fill(bufs[0], k)
+                h.rx_push_links_blob(bufs[0], off, flush=(k == n_push - 1))
+                out += h.rx_pop(cap=512)
+        else:
+            fill(bufs[0], 0)
+            h.rx_push_links_async(bufs[0], off, flush=(n_push == 1))
+            for k in range(1, n_push + 1):
+                if k < n_push:
+                    fill(bufs[k & 1], k)                         # the other buffer: push k - 1 may still be copying from its own
+                    h.rx_push_links_async(bufs[k & 1], off, flush=(k == n_push - 1))
+                assert h.rx_push_wait()                          # completes push k - 1
+                out += h.rx_pop(cap=512)
+            assert not h.rx_push_wait()                          # nothing pending
+            with pytest.raises(W.WifiB200Error):                 # a third pending push is refused
+                for _ in range(3):
+                    h.rx_push_links_async(bufs[0], off)
+        h.close()
+        return [(int(f["link"]), int(f["trigger"]), d) for f, d in out]
+
+    sync, asyn = run(False), run(True)
+    assert sync == asyn and len(sync) >= 30
+    want = []
+    for l, c in enumerate(caps):
+        pad = np.concatenate([c, np.zeros(n_push * chunk - c.size, np.complex64)])
+        r = O.rx(pad, algo=0, want_carrier=False)
+        want += [(l, int(f["trigger"]), r.psdu(i)[:-4]) for i, f in enumerate(r.frames) if f["crc_ok"]]
+    assert sorted(sync) == sorted(want)
+
+
 def test_loopback_epsilon_is_the_channel_models_frequency_offset(O, W):
     """channel_model(frequency_offset = epsilon * freq / 10e6) is cycles per sample (IRS_tranceiver.py:284,434): with the
     slider at its end stop (20e-6) the receiver must report 2 pi * 0.01178 = 0.074 rad/sample, not a 2e7 times smaller one."""
