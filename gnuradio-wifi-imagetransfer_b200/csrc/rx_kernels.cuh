@@ -26,56 +26,61 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
     return lo;
 }
 
-// One block per tile of DET_TILE samples of one link, one thread per FE_CHUNK samples.
+// Two blocks per tile of DET_TILE samples of one link (64 chunks each), one thread per FE_CHUNK samples.
 //
-// Data movement: the tile plus two chunks of history (130 rows of 64 samples) is fetched by 1-D bulk copies
-// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, one 512-byte row per copy, issued by one warp, four
-// mbarriers per block: a warp starts as soon as its quarter of the rows has arrived) -- the copy engine does the work that used to cost 15 instructions per sample.  Rows are 66
-// samples (528 bytes) apart in shared memory: 16-byte aligned, as bulk copies require, and 33 16-byte units apart, so
-// the threads' 16-byte loads (two samples each) of a warp are bank-conflict free.  A tile that touches the start or the
-// end of its stream, or whose samples are not 16-byte aligned in global memory, is staged element-wise (zeros outside
-// the stream: that makes every "index < 0" case of the oracle an exact no-op, x + 0 == x).
+// Data movement: a block's 64 chunks plus two chunks of history (66 rows of 64 samples) are fetched by 1-D bulk copies
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, one 512-byte row per copy, issued by one warp, one
+// mbarrier per consumer warp: a warp starts as soon as its rows have arrived) -- the copy engine does the work that used
+// to cost 15 instructions per sample.  Rows are 66 samples (528 bytes) apart in shared memory: 16-byte aligned, as bulk
+// copies require, and 33 16-byte units apart, so the threads' 16-byte loads (two samples each) of a warp are
+// bank-conflict free.  A block that touches the start or the end of its stream, or whose samples are not 16-byte
+// aligned in global memory, is staged element-wise (zeros outside the stream: that makes every "index < 0" case of
+// the oracle an exact no-op, x + 0 == x).
 //
 // Arithmetic: each thread re-seeds the two running sums exactly as the oracle does at every multiple of FE_CHUNK
 // and walks its 64 samples.  The walk is fully unrolled over a register ring of the last 64 samples: sample n is
 // loaded once (32 loads of the previous row for the history, 32 of its own row) and the three delayed taps
 // x[n-16], x[n-47], x[n-63] are register reads.  Flag n = |a[n]|^2 > thr^2 p[n]^2 (oracle rx_link).
-#define DET_ROWS (DET_THREADS + 2)
+// A block is DET_BLOCK threads and works on half a tile (its 64 chunks plus two chunks of history): six blocks fit an
+// SM, so six loads are in different phases instead of three.
+#define DET_BLOCK 64
+#define DET_ROWS (DET_BLOCK + 2)
 #define DET_STRIDE 66                                        // samples between rows in shared memory
-#define DET_SMEM_BYTES (DET_ROWS * DET_STRIDE * (int)sizeof(cf) + 32)   // + four mbarriers
+#define DET_SMEM_BYTES (DET_ROWS * DET_STRIDE * (int)sizeof(cf) + 16)   // + two mbarriers
 
 __device__ __forceinline__ uint32_t det_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
+__global__ void __launch_bounds__(DET_BLOCK, 6) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
                                                          int64_t tile_base, int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
                                                          uint32_t *__restrict__ summary)
 {
     extern __shared__ __align__(128) unsigned char det_raw[];
     cf *sx = reinterpret_cast<cf *>(det_raw);                                         // DET_ROWS x DET_STRIDE
     uint64_t *bar = reinterpret_cast<uint64_t *>(det_raw + DET_ROWS * DET_STRIDE * sizeof(cf));
-    const int64_t tile = tile_base + blockIdx.x;          // links / n_links: the link group of this launch; tiles are numbered over the whole call
+    const int64_t tile = tile_base + (blockIdx.x >> 1);   // links / n_links: the link group of this launch; tiles are numbered over the whole call
+    const int half = blockIdx.x & 1;                      // which 64 chunks of the tile
     if (tile >= total_tiles) return;
     const int tid = threadIdx.x;
     int l = find_link(links, n_links, tile * DET_THREADS);
     const LinkDesc L = links[l];
     const cf *x = iq + L.x_off;
-    const int64_t T0 = (tile * DET_THREADS - L.chunk_base) * FE_CHUNK;   // first sample of the tile in the link
+    const int64_t T0 = (tile * DET_THREADS - L.chunk_base + half * DET_BLOCK) * FE_CHUNK;   // first sample of this block's chunks in the link
     const int64_t lo = -(int64_t)L.hist, hi = L.len;
     const int64_t g0 = T0 - 2 * FE_CHUNK;                                // first staged sample
     const bool bulk = g0 >= lo && g0 + DET_ROWS * FE_CHUNK <= hi && ((reinterpret_cast<uintptr_t>(x + g0) & 15) == 0);
     if (bulk) {
-        // four mbarriers, one per warp of consumers: rows [0, 34) complete the first, then 32 rows each.  Warp w walks the
-        // rows 32 w + 1 .. 32 w + 33, i.e. it waits for its own barrier and the one before: the first warp starts its
-        // walk when a quarter of the tile has arrived, not the whole tile.
+        // one mbarrier per warp of consumers: rows [0, 34) complete the first, the next 32 rows the second.  Warp w walks
+        // the rows 32 w + 1 .. 32 w + 33, i.e. it waits for its own barrier and the one before: the first warp starts
+        // its walk when half of the rows have arrived.
         const uint32_t bar_a = det_smem_u32(bar);
         if (tid == 0) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a + 8 * b));
+            for (int b = 0; b < DET_BLOCK / 32; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a + 8 * b));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         if (tid < 32) {
-            if (tid < 4)
+            if (tid < DET_BLOCK / 32)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a + 8 * tid), "r"((tid == 0 ? 34 : 32) * FE_CHUNK * (int)sizeof(cf)) : "memory");
             __syncwarp();
             for (int r = tid; r < DET_ROWS; r += 32)
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar_a + 8 * b) : "memory");
         }
     } else {
-        for (int q = tid; q < DET_ROWS * FE_CHUNK; q += DET_THREADS) {
+        for (int q = tid; q < DET_ROWS * FE_CHUNK; q += DET_BLOCK) {
             const int64_t g = g0 + q;
             sx[(q >> 6) * DET_STRIDE + (q & 63)] = (g >= lo && g < hi) ? x[g] : cf{0.f, 0.f};
         }
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(DET_THREADS, 3) k_detect(const cf *__restrict_
             ring[n] = xn;                            // replaces sample n - 64
         }
     }
-    const int64_t chunk = tile * DET_THREADS + tid;
+    const int64_t chunk = tile * DET_THREADS + half * DET_BLOCK + tid;
     reinterpret_cast<uint2 *>(flags)[chunk] = make_uint2(w0, w1);
     uint32_t any = __ballot_sync(0xffffffffu, (w0 | w1) != 0u);
     if ((tid & 31) == 0) summary[chunk >> 5] = any;
@@ -430,16 +435,22 @@ __global__ void __launch_bounds__(128) k_frames_init(const LinkDesc *__restrict_
 }
 
 // ------------------------------------------------------------------ R2/R3 sync_long search
-// One block (128 threads) per frame.
+// One block of SL_THREADS threads per frame.  The 320 x 64 matched filter is register blocked: a thread owns five
+// consecutive lags, keeps the five samples under the current tap in registers and loads ONE new sample per tap
+// (20 fused multiply-adds per load instead of 4); the taps are compile-time offsets into constant memory, i.e.
+// operands of the multiply-adds, not loads.  Each lag still accumulates its 64 taps in ascending order (the contract).
+#define SL_THREADS 64
+#define SL_LAGS 5                       // SYNC_LENGTH / SL_THREADS
 // (f0, n_frames) here and below: the frame range of the link group a launch works on; `links` is the whole call's table
-__global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int f0, int n_frames)
+__global__ void __launch_bounds__(SL_THREADS) k_sync_long(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, wifi_b200_frame *frames, int f0, int n_frames)
 {
+    static_assert(SL_THREADS * SL_LAGS == SYNC_LENGTH, "lags per thread");
     __shared__ cf sb[SYNC_LENGTH + 64];
     __shared__ cf scorr[SYNC_LENGTH];
     __shared__ float smag[SYNC_LENGTH];
     __shared__ float s_freq;
-    __shared__ float rmax[4];
-    __shared__ int ridx[4];
+    __shared__ float rmax[SL_THREADS / 32];
+    __shared__ int ridx[SL_THREADS / 32];
     __shared__ int top[4];
     int f = f0 + blockIdx.x;
     if (f >= n_frames) return;
@@ -456,7 +467,7 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
         const int64_t i0 = t & ~(int64_t)(FE_CHUNK - 1);
         cf *sx = sb;         // scratch, reused later: samples i0 - 63 .. t
         const int cnt = (int)(t - i0) + 64;
-        for (int q = tid; q < cnt; q += blockDim.x) sx[q] = fe_at(x, i0 - 63 + q, hist);
+        for (int q = tid; q < cnt; q += SL_THREADS) sx[q] = fe_at(x, i0 - 63 + q, hist);
         __syncthreads();
         if (tid == 0) {
             cf sa = {0.f, 0.f};
@@ -472,25 +483,36 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
     const float freq = s_freq;
     if (tid == 0) frames[f].freq_short = freq;
     if (F.burst_len < SYNC_LENGTH + 63) return;   // SYNC never completes (end of stream)
-    for (int j = tid; j < SYNC_LENGTH + 63; j += blockDim.x) {
+    for (int j = tid; j < SYNC_LENGTH + 63; j += SL_THREADS) {
         int64_t src = t + j - 16;
         cf s = src >= -(int64_t)hist ? x[src] : cf{0.f, 0.f};
         sb[j] = cmul(s, crot(-freq * (float)j));
     }
     __syncthreads();
-    for (int i = tid; i < SYNC_LENGTH; i += blockDim.x) {
-        cf acc = {0.f, 0.f};
-#pragma unroll 8
-        for (int m = 0; m < 64; ++m) acc = wdm_cmac(acc, c_tab.long_taps[63 - m], sb[i + m]);
-        scorr[i] = acc;
-        smag[i] = wdm_norm(acc);
+    {
+        const int i0 = SL_LAGS * tid;
+        cf acc[SL_LAGS], win[SL_LAGS];
+#pragma unroll
+        for (int q = 0; q < SL_LAGS; ++q) { acc[q] = cf{0.f, 0.f}; win[q] = q < SL_LAGS - 1 ? sb[i0 + q] : cf{0.f, 0.f}; }
+#pragma unroll
+        for (int m = 0; m < 64; ++m) {
+            win[(m + SL_LAGS - 1) % SL_LAGS] = sb[i0 + m + SL_LAGS - 1];      // the window is a ring: sample i0 + m + q sits in win[(m + q) % 5]
+            const cf tap = c_tab.long_taps[63 - m];
+#pragma unroll
+            for (int q = 0; q < SL_LAGS; ++q) acc[q] = wdm_cmac(acc[q], tap, win[(m + q) % SL_LAGS]);
+        }
+#pragma unroll
+        for (int q = 0; q < SL_LAGS; ++q) {
+            scorr[i0 + q] = acc[q];
+            smag[i0 + q] = wdm_norm(acc[q]);
+        }
     }
     __syncthreads();
     // four largest |corr|^2, earlier index first on ties (stable descending sort)
     for (int r = 0; r < 4; ++r) {
         float bm = -1.f;
         int bi = 0x7fffffff;
-        for (int i = tid; i < SYNC_LENGTH; i += blockDim.x) {
+        for (int i = tid; i < SYNC_LENGTH; i += SL_THREADS) {
             float v = smag[i];
             if (v > bm) { bm = v; bi = i; }   // ascending i per thread: first max kept
         }
@@ -502,7 +524,7 @@ __global__ void __launch_bounds__(128) k_sync_long(const cf *__restrict__ iq, co
         if ((tid & 31) == 0) { rmax[tid >> 5] = bm; ridx[tid >> 5] = bi; }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < 4; ++w)
+            for (int w = 1; w < SL_THREADS / 32; ++w)
                 if (rmax[w] > bm || (rmax[w] == bm && ridx[w] < bi)) { bm = rmax[w]; bi = ridx[w]; }
             top[r] = bi;
             smag[bi] = -2.f;

@@ -151,6 +151,7 @@ const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "de
 
 } // namespace
 
+#define A_SLOTS 3                // asynchronous pushes that may be pending at once (device staging buffers)
 struct wifi_b200 {
     wifi_b200_cfg cfg;
     int device = 0;
@@ -224,12 +225,12 @@ struct wifi_b200 {
     int64_t s_unprocessed = 0;     // samples appended to the fullest link since the last pipeline run
     std::vector<wifi_b200_frame> s_meta;
     std::vector<uint8_t> s_bytes;
-    // asynchronous pushes (wifi_b200_rx_push_links_async): up to two in flight, each with its device staging buffer
+    // asynchronous pushes (wifi_b200_rx_push_links_async): up to A_SLOTS in flight, each with its device staging buffer
     struct AsyncPush { int slot = 0; int flush = 0; std::vector<uint64_t> off; };
     std::vector<AsyncPush> a_pending;
-    cf *d_stage[2] = {nullptr, nullptr};
-    size_t a_cap[2] = {0, 0};
-    cudaEvent_t a_ev[2] = {nullptr, nullptr};
+    cf *d_stage[A_SLOTS] = {};
+    size_t a_cap[A_SLOTS] = {};
+    cudaEvent_t a_ev[A_SLOTS] = {};
     int a_next = 0;
 };
 
@@ -265,8 +266,8 @@ int upload_tables(wifi_b200 *h)
 void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
-    for (int k = 0; k < 2; ++k) if (h->a_ev[k]) cudaEventDestroy(h->a_ev[k]);
-    void *ptrs[] = {h->d_stage[0], h->d_stage[1], h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
+    for (int k = 0; k < A_SLOTS; ++k) if (h->a_ev[k]) cudaEventDestroy(h->a_ev[k]);
+    void *ptrs[] = {h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
                     h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -469,7 +470,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
         }
         if (timed) mark(h, ST_DETECT);
         if (tiles_g > 0)
-            k_detect<<<(unsigned)tiles_g, DET_THREADS, DET_SMEM, s>>>(iq, gl, ng, tile_base, tile_base + tiles_g, thr_f, h->d_flags, h->d_summary);
+            k_detect<<<(unsigned)(2 * tiles_g), DET_BLOCK, DET_SMEM, s>>>(iq, gl, ng, tile_base, tile_base + tiles_g, thr_f, h->d_flags, h->d_summary);
         if (timed) mark(h, ST_SELECT);
         if (tiles_g > 0)
             k_select_spec<<<(unsigned)((tiles_g * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, tile_base, tile_base + tiles_g,
@@ -493,7 +494,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
         }
         const int f0 = (int)frame_base, fe = (int)f_end;
         if (nf > 0) {
-            k_sync_long<<<(unsigned)nf, 128, 0, s>>>(iq, h->d_links, h->d_frames, f0, fe);
+            k_sync_long<<<(unsigned)nf, SL_THREADS, 0, s>>>(iq, h->d_links, h->d_frames, f0, fe);
             if (timed) mark(h, ST_DEMOD_HEAD);
             demod_head<<<(unsigned)((nf + 3) / 4), 128, 0, s>>>(iq, h->d_links, h->d_frames, f0, fe, h->d_states, h->d_rows, h->d_carrier, prm,
                                                             h->d_depunct, h->d_vit_in, h->d_soft, h->d_vit_soft_in);
@@ -1308,9 +1309,9 @@ int wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq, const uint64_
     if (!iq && total) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
     cudaSetDevice(h->device);
-    if (h->a_pending.size() >= 2) { h->err = "two asynchronous pushes are already pending: call wifi_b200_rx_push_wait first"; return WIFI_E_OVERFLOW; }
+    if (h->a_pending.size() >= A_SLOTS) { h->err = "three asynchronous pushes are already pending: call wifi_b200_rx_push_wait first"; return WIFI_E_OVERFLOW; }
     if (total > h->cfg.max_samples) { h->err = "push larger than max_samples"; return WIFI_E_OVERFLOW; }
-    const int slot = h->a_next & 1;
+    const int slot = h->a_next % A_SLOTS;
     if ((int64_t)h->a_cap[slot] < total) {
         if (h->d_stage[slot]) cudaFree(h->d_stage[slot]);
         h->d_stage[slot] = nullptr;

@@ -350,7 +350,7 @@ class Handle:
 
     def rx_push_links_async(self, blob, link_off, flush=False):
         """Queues the copy of this push and returns; `blob` (page-locked complex64) must stay untouched until the
-        rx_push_wait() that completes it.  At most two pushes may be pending."""
+        rx_push_wait() that completes it.  At most three pushes may be pending."""
         assert isinstance(blob, np.ndarray) and blob.dtype == np.complex64 and blob.flags.c_contiguous
         off = np.ascontiguousarray(link_off, np.uint64)
         self._ck(self._L.wifi_b200_rx_push_links_async(self._h, _p(blob) if blob.size else None, _p(off), off.size - 1, int(flush)))

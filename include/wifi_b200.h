@@ -197,7 +197,7 @@ int  wifi_b200_rx_push_links(wifi_b200_t *h, const float *iq_host, const uint64_
  * host -> device copy of this push on the handle's copy stream and returns at once; the buffer must stay untouched until
  * the wifi_b200_rx_push_wait that completes this push.  _wait takes the OLDEST pending push, waits for its copy, appends
  * it to the streams and runs the pipeline as wifi_b200_rx_push_links would (results through wifi_b200_rx_pop); it returns
- * 1 if it completed a push, 0 if none was pending.  At most two pushes may be pending: with
+ * 1 if it completed a push, 0 if none was pending.  At most three pushes may be pending: with
  *     async(k + 1); wait()  (completes k);  pop ...
  * the copy of push k + 1 overlaps the decoding of push k.  Results are identical to the synchronous calls. */
 int  wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int flush);

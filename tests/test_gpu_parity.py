@@ -393,8 +393,8 @@ def test_asynchronous_pushes_equal_synchronous_ones(O, W):
                 assert h.rx_push_wait()                          # completes push k - 1
                 out += h.rx_pop(cap=512)
             assert not h.rx_push_wait()                          # nothing pending
-            with pytest.raises(W.WifiB200Error):                 # a third pending push is refused
-                for _ in range(3):
+            with pytest.raises(W.WifiB200Error):                 # a fourth pending push is refused
+                for _ in range(4):
                     h.rx_push_links_async(bufs[0], off)
         h.close()
         return [(int(f["link"]), int(f["trigger"]), d) for f, d in out]
