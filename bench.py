@@ -369,6 +369,12 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # every rank keeps to its own share of the host cores: the page-locked capture of the e2e section is first touched
+        # (and, where the box shows NUMA nodes, placed) from the cores that will feed this rank's GPU
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // world
+        if per >= 1:
+            os.sched_setaffinity(0, cpus[local * per:(local + 1) * per])
     n_links, fpl = args.links, args.frames_per_link
     n = n_links * fpl
     flen = frame_samples()
@@ -553,7 +559,7 @@ def main():
                     hl.rx_push_wait()
                     drain()
                 hl.rx_reset()
-                n_pdu, push_ms = 0, []
+                n_pdu, push_ms, wait_ms, stage_last = 0, [], [], {}
                 barrier()
                 t_start = time.perf_counter()
                 hl.rx_push_links_async(blobs[0], off, flush=False)
@@ -562,11 +568,16 @@ def main():
                     t0 = time.perf_counter()
                     if k + 1 < pushes:
                         hl.rx_push_links_async(blobs[k + 1], off, flush=(k + 1 == pushes - 1))
+                    tw = time.perf_counter()
                     hl.rx_push_wait()
+                    wait_ms.append(round(1e3 * (time.perf_counter() - tw), 2))
+                    if k == pushes - 1:
+                        stage_last = {kk: round(v, 3) for kk, v in hl.stage_times().items() if v}
                     n_pdu += drain()
                     push_ms.append(round(1e3 * (time.perf_counter() - t0), 2))
                 t_lib = time.perf_counter() - t_start
-                e2e["streaming"] = {"value": s_links * chunk * pushes / t_lib / 1e6, "push_ms": push_ms, "unit": "Msamples/s", "links": s_links,
+                e2e["streaming"] = {"value": s_links * chunk * pushes / t_lib / 1e6, "push_ms": push_ms, "wait_ms": wait_ms, "stage_ms_of_one_push": stage_last,
+                                    "unit": "Msamples/s", "links": s_links,
                                     "samples_per_push_per_link": chunk, "pushes": pushes, "pdus": n_pdu,
                                     "realtime_factor_per_20Msps_link": chunk * pushes / t_lib / 20e6,
                                     "how": "wifi_b200_rx_push_links_async(k+2), rx_push_wait(k), rx_pop per chunk; pre-filled pinned host buffers, one handle; wall time of the whole loop, per-rank figure"}
