@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--soft", action="store_true", help="soft-decision mode (extension, DESIGN.md 9)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-time-shard", action="store_true", help="skip the time-sharded section (one capture cut into overlapping segments across the ranks)")
-    ap.add_argument("--ts-frames", type=int, default=32768, help="frames of the single-link capture the time-sharded section cuts across the ranks")
+    ap.add_argument("--ts-frames", type=int, default=131072, help="frames of the single-link capture the time-sharded section cuts across the ranks (the same at every N: strong scaling)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8192, help="frames of the cpu_baseline sample")
     return ap.parse_args()
@@ -431,10 +431,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         import threading
-        host = torch.empty(cap.numel(), dtype=torch.float32, pin_memory=True)
-        host.copy_(cap)
-        torch.cuda.synchronize()
-        hn = host.numpy().view(np.complex64)
+        # page-locked host capture from the library's own allocator: first touched on the cores next to this rank's GPU
+        hn = h.host_alloc(cap.numel() // 2, np.complex64)
+        hn.view(np.float32)[:] = cap.cpu().numpy()
+        host = hn
         parts = 4 if n_links >= 4 else 1
         bounds = [n_links * i // parts for i in range(parts + 1)]
         part_samples = max(int(link_off[bounds[i + 1]] - link_off[bounds[i]]) for i in range(parts))
@@ -548,7 +548,7 @@ def main():
                 def drain():
                     n_ = 0
                     while True:
-                        meta, _pd = hl.rx_pop_arrays(cap=8192)
+                        meta, _pd = hl.rx_pop_arrays(cap=8192, copy=False)
                         if not len(meta):
                             return n_
                         n_ += len(meta)
@@ -585,7 +585,8 @@ def main():
                 del pins
         except Exception as ex:
             e2e["streaming"] = {"error": repr(ex)}
-        del host
+        h.host_free(hn)
+        del host, hn
 
     tsh = None
     if not args.no_time_shard and args.workload == "c3":

@@ -1,6 +1,8 @@
 // wifi_b200.cu -- host side of libwifi_b200.so: handle, workspace, C ABI (include/wifi_b200.h).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -shared -Xcompiler -fPIC
 // No CPU fallback anywhere in this file: every entry point that computes launches CUDA kernels.
+#include <sched.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -42,7 +44,8 @@ uint32_t h_crc32(const uint8_t *p, int n)
 }
 
 // Tables are generated from the formulas of the standard / upstream sources, never copied:
-// see the matching generator in oracle/wifi_oracle.cpp and tests/test_tables.py.
+// see the matching generator in oracle/wifi_oracle.cpp; tests/test_oracle_kat.py checks both against the standard's
+// Annex G/L tables and against the constants written in the reference's wifi_phy_hier.grc.
 void build_tables(DevTables &t, std::vector<uint16_t> &depunct)
 {
     memset(&t, 0, sizeof t);
@@ -1419,6 +1422,71 @@ int wifi_b200_alu_peak(wifi_b200_t *h, int iters, double *warp_inst_per_s, doubl
     if (rc) { h->err = "alu_peak: CUDA error"; return rc; }
     *warp_inst_per_s = (double)blocks * (threads / 32) * (double)iters * ALU_PROBE_OPS / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
+    return WIFI_OK;
+}
+
+// ---- page-locked host memory near the handle's GPU ----
+// Reads /sys/bus/pci/devices/<gpu>/local_cpulist: the host cores on the GPU's side of the machine.  The buffer is allocated
+// and first touched from those cores, so on a multi-socket box its pages land on the NUMA node whose PCIe root the GPU hangs
+// off (Linux places pages on the node of the core that first writes them); the caller's affinity is restored afterwards.
+static bool gpu_local_cpus(int device, cpu_set_t *set)
+{
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, device) != cudaSuccess) return false;
+    for (char *c = bdf; *c; ++c) *c = (char)tolower(*c);
+    std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    char buf[4096] = {0};
+    const bool ok = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char *p = buf; *p && *p != '\n';) {                        // "0-15,32-47"
+        char *e;
+        long a = strtol(p, &e, 10), b = a;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++n; }
+        p = (*e == ',') ? e + 1 : e;
+    }
+    return n > 0;
+}
+
+int wifi_b200_host_alloc(wifi_b200_t *h, size_t bytes, void **out)
+{
+    if (!h || !out || bytes == 0) return WIFI_E_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    cpu_set_t old_set, local;
+    const bool have_old = sched_getaffinity(0, sizeof old_set, &old_set) == 0;
+    bool moved = false;
+    if (have_old && gpu_local_cpus(h->device, &local)) {
+        cpu_set_t both;
+        CPU_AND(&both, &local, &old_set);                             // never leave the cores the caller is allowed on
+        if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
+    void *p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+        volatile char *c = (volatile char *)p;                        // first touch from the GPU's side of the machine
+        for (size_t i = 0; i < bytes; i += 4096) c[i] = 0;
+    }
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (e != cudaSuccess) { cudaGetLastError(); h->err = "cudaHostAlloc failed"; return WIFI_E_NOMEM; }
+    *out = p;
+    return WIFI_OK;
+}
+
+int wifi_b200_host_free(wifi_b200_t *h, void *p)
+{
+    if (!h) return WIFI_E_ARG;
+    if (!p) return WIFI_OK;
+    std::lock_guard<std::mutex> g(h->mu);
+    cudaSetDevice(h->device);
+    CK(cudaFreeHost(p));
     return WIFI_OK;
 }
 

@@ -76,17 +76,19 @@ SS_MIN_GAP = 480
 HIST = 128          # front-end history a resumed segment is given (two FE_CHUNKs: the running sums re-seed inside it)
 
 
+# int32 word of each record column inside a 96-byte frame record (wifi_b200_frame / orc_frame, include/wifi_b200.h):
+# burst_len, found, freq_long (bit pattern), sig_ok, encoding, length, frame_symbols, n_rows, accepted, decoded, crc_ok
+_FRAME_WORDS = [3, 6, 5, 9, 10, 11, 12, 13, 14, 15, 16]
+
+
 def records(frames, offset):
     """Frame table -> int64 [n, 12] records ordered by absolute trigger position (freq_long travels as its bit pattern)."""
+    frames = np.ascontiguousarray(frames)
+    assert frames.dtype.itemsize == 96
     r = np.empty((len(frames), REC_FIELDS), np.int64)
-    for k, name in enumerate(REC_NAMES):
-        if name == "trigger":
-            r[:, k] = frames["trigger"]
-            r[:, k] += offset
-        elif name == "freq_bits":
-            r[:, k] = np.ascontiguousarray(frames["freq_long"], np.float32).view(np.int32)
-        else:
-            r[:, k] = frames[name]
+    r[:, TRIG] = frames["trigger"]
+    r[:, TRIG] += offset
+    r[:, 1:] = frames.view(np.int32).reshape(len(frames), 24)[:, _FRAME_WORDS]      # one gather for the eleven 32-bit columns
     if len(r) > 1 and np.any(np.diff(r[:, TRIG]) < 0):
         r = r[np.argsort(r[:, TRIG], kind="stable")]
     return r

@@ -63,6 +63,7 @@ EXPORTS = [
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_rx_push_links", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
     "wifi_b200_selftest_detmath", "wifi_b200_alu_peak", "wifi_b200_rx_push_links_async", "wifi_b200_rx_push_wait",
+    "wifi_b200_host_alloc", "wifi_b200_host_free",
 ]
 
 _LIB = None
@@ -116,6 +117,8 @@ def lib():
         L.wifi_b200_stage_name.restype = C.c_char_p
         L.wifi_b200_selftest_detmath.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, i64]
         L.wifi_b200_alu_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.wifi_b200_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        L.wifi_b200_host_free.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -370,9 +373,10 @@ class Handle:
             out.append((f.copy(), buf[f["psdu_off"]:f["psdu_off"] + f["length"] - 4].tobytes()))
         return out
 
-    def rx_pop_arrays(self, cap=4096):
+    def rx_pop_arrays(self, cap=4096, copy=True):
         """Bulk form of rx_pop for many live links: (frame records, PSDU bytes back to back); record i's PSDU is
-        blob[rec["psdu_off"] : rec["psdu_off"] + rec["length"] - 4].  No per-frame Python objects."""
+        blob[rec["psdu_off"] : rec["psdu_off"] + rec["length"] - 4].  No per-frame Python objects.  copy=False returns
+        views of the wrapper's receive buffers, valid until the next rx_pop_arrays call."""
         if getattr(self, "_pop_meta", None) is None or self._pop_meta.size < cap:
             self._pop_meta = np.zeros(cap, FRAME_DTYPE)
             self._pop_buf = np.zeros(cap * 1528, np.uint8)
@@ -380,6 +384,8 @@ class Handle:
         self._ck(self._L.wifi_b200_rx_pop(self._h, _p(self._pop_meta), cap, _p(self._pop_buf), self._pop_buf.size, C.byref(n)))
         k = n.value
         used = int(self._pop_meta["psdu_off"][k - 1] + self._pop_meta["length"][k - 1] - 4) if k else 0
+        if not copy:
+            return self._pop_meta[:k], self._pop_buf[:used]
         return self._pop_meta[:k].copy(), self._pop_buf[:used].copy()
 
     def rx_reset(self):
@@ -401,6 +407,23 @@ class Handle:
         o1 = np.zeros_like(a) if o1 is None else np.array(o1, np.float32)
         self._ck(self._L.wifi_b200_selftest_detmath(self._h, int(fn), _p(a), _p(b), _p(c), _p(d), _p(o0), _p(o1), a.size))
         return o0, o1
+
+    def host_alloc(self, n, dtype=np.complex64):
+        """Page-locked host array of n elements, allocated and first touched on the GPU's side of the machine
+        (wifi_b200_host_alloc).  Free it with host_free(array) before closing the handle."""
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        self._ck(self._L.wifi_b200_host_alloc(self._h, int(n) * dt.itemsize, C.byref(p)))
+        buf = (C.c_char * (int(n) * dt.itemsize)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dt)
+        self._host_ptrs = getattr(self, "_host_ptrs", {})
+        self._host_ptrs[a.ctypes.data] = p
+        return a
+
+    def host_free(self, a):
+        p = getattr(self, "_host_ptrs", {}).pop(a.ctypes.data, None)
+        if p is not None:
+            self._ck(self._L.wifi_b200_host_free(self._h, p))
 
     def alu_peak(self, iters=4096):
         """Measured issue rate of the integer ALU pipe: (warp-instructions per second, milliseconds of the probe)."""

@@ -208,6 +208,12 @@ int  wifi_b200_get_stats(wifi_b200_t *h, wifi_b200_stats *out);
 int  wifi_b200_stage_times(wifi_b200_t *h, float *ms, int cap);
 const char *wifi_b200_stage_name(int i);
 
+/* ---- page-locked host memory for the host-buffer entry points (rx_batch, rx_push*, tx) ----
+ * cudaHostAlloc'd, so copies are plain DMA, and first touched from the host cores on the GPU's side of the machine
+ * (/sys/bus/pci/devices/<gpu>/local_cpulist): on a multi-socket box the pages land on the NUMA node of the GPU's PCIe root. */
+int  wifi_b200_host_alloc(wifi_b200_t *h, size_t bytes, void **out);
+int  wifi_b200_host_free(wifi_b200_t *h, void *p);
+
 /* ---- diagnostics (no reference counterpart) ----
  * Element-wise evaluation of the numerical contract (include/wifi_detmath.h, wdm_selftest(fn, ...)) on the GPU with host
  * buffers: tests/test_detmath.py asks for bit equality with the same call on the host.  o0 / o1 are in-out. */

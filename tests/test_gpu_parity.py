@@ -356,6 +356,23 @@ def test_udp_runner_speaks_the_apps_contract(O, W):
     t.close()
 
 
+def test_host_alloc_gives_page_locked_memory_the_entry_points_accept(O, W):
+    rng = np.random.default_rng(71)
+    y, psdus = make_capture(O, rng, [(6, 300), (2, 150)], snr_db=30, seed=4)
+    h = W.Handle(max_samples=1 << 17)
+    try:
+        a = h.host_alloc(y.size, np.complex64)
+        assert a.size == y.size and not a.any()                 # zero filled by the first touch
+        a[:] = y
+        res = h.rx_batch(a)
+        assert res.pdus() == [p[:-4] for p in psdus]
+        h.host_free(a)
+        with pytest.raises(W.WifiB200Error):
+            h.host_alloc(0)
+    finally:
+        h.close()
+
+
 def test_asynchronous_pushes_equal_synchronous_ones(O, W):
     """wifi_b200_rx_push_links_async / _rx_push_wait with two page-locked buffers used in turn: the copy of push k + 1 is in
     flight while push k is decoded; the frames that come out are those of the synchronous calls, in the same order."""
