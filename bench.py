@@ -195,7 +195,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
     t_one = (time.perf_counter() - t0) / reps
     equal = None
     if rank == 0:
-        equal = bool(np.array_equal(np.concatenate(owned_all), S.records(whole, 0)))
+        equal = S.same(np.concatenate(owned_all), S.records(whole, 0))
     tv = torch.tensor([t_sh, dec_sh, t_one], dtype=torch.float64, device="cuda")
     cnt = S.allreduce_stats(np.array([len(own), int(own[:, S.CRC].sum())], np.int64), device=dev if world > 1 else None)
     if world > 1:
@@ -209,7 +209,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
             "single_gpu_ms": 1e3 * t_one, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
             "value_msamples_per_s": n_total / t_sh / 1e6, "frames_owned_total": int(cnt[0]), "crc_ok_total": int(cnt[1]),
             "re_decode_rounds": rounds, "union_equals_single_gpu_table": equal, "scaling": "strong",
-            "collective": "NCCL all_gather of the frame records (12 x int64 per frame) + counter all_reduce" if world > 1 else "none (one rank)",
+            "collective": "NCCL all_gather of the frame tables (96 bytes per frame) + counter all_reduce" if world > 1 else "none (one rank)",
             "timing": "wall clock around sharding.reconcile (decode, record all-gather, join check), barrier + synchronize on both sides, max over ranks, mean of %d" % reps}
 
 

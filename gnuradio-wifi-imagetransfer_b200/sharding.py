@@ -68,30 +68,31 @@ def allreduce_stats(vec, device=None):
 # within a frame or two; back-to-back traffic without a single idle gap can keep two trigger chains apart for ever.
 # `boundary_check` decides from the frame records alone whether the segment joined; `resume_point` gives the place
 # and the state from which to decode again when it did not.
-# A frame record is one row of 12 int64 (what the all-gather moves); column names:
-REC_NAMES = ("trigger", "burst_len", "found", "freq_bits", "sig_ok", "encoding", "length", "frame_symbols", "n_rows", "accepted", "decoded", "crc_ok")
-TRIG, BURST, FOUND, FREQ, SIG, ENC, LEN, FSYM, NROWS, ACC, DEC, CRC = range(12)
-REC_FIELDS = len(REC_NAMES)
+# A frame record is the library's own 96-byte frame record (wifi_b200_frame / orc_frame, include/wifi_b200.h) seen as 24
+# int32 words -- no conversion, the all-gather moves the table as it is -- with the trigger made absolute in place (a
+# capture is one link: fewer than 2^31 samples, so the low word holds it).  Word of each field the checks look at:
+TRIG, BURST, FREQ, FOUND, SIG, ENC, LEN, FSYM, NROWS, ACC, DEC, CRC = 0, 3, 5, 6, 9, 10, 11, 12, 13, 14, 15, 16
+_CMP = [TRIG, BURST, FREQ, FOUND, SIG, ENC, LEN, FSYM, NROWS, ACC, DEC, CRC]      # what must agree between two decodes of the same frame
+REC_FIELDS = 24                                                                    # (row / PSDU offsets, words 20-23, are per decode)
 SS_MIN_GAP = 480
 HIST = 128          # front-end history a resumed segment is given (two FE_CHUNKs: the running sums re-seed inside it)
 
 
-# int32 word of each record column inside a 96-byte frame record (wifi_b200_frame / orc_frame, include/wifi_b200.h):
-# burst_len, found, freq_long (bit pattern), sig_ok, encoding, length, frame_symbols, n_rows, accepted, decoded, crc_ok
-_FRAME_WORDS = [3, 6, 5, 9, 10, 11, 12, 13, 14, 15, 16]
-
-
 def records(frames, offset):
-    """Frame table -> int64 [n, 12] records ordered by absolute trigger position (freq_long travels as its bit pattern)."""
+    """Frame table -> int32 [n, 24] view of its records, ordered by absolute trigger position (changes `frames` in place)."""
     frames = np.ascontiguousarray(frames)
     assert frames.dtype.itemsize == 96
-    r = np.empty((len(frames), REC_FIELDS), np.int64)
-    r[:, TRIG] = frames["trigger"]
-    r[:, TRIG] += offset
-    r[:, 1:] = frames.view(np.int32).reshape(len(frames), 24)[:, _FRAME_WORDS]      # one gather for the eleven 32-bit columns
+    r = frames.view(np.int32).reshape(len(frames), REC_FIELDS)
+    if offset:
+        r[:, TRIG] += offset
     if len(r) > 1 and np.any(np.diff(r[:, TRIG]) < 0):
         r = r[np.argsort(r[:, TRIG], kind="stable")]
     return r
+
+
+def same(a, b):
+    """Two record tables describe the same frames (every field that does not depend on where a decode started)."""
+    return len(a) == len(b) and bool(np.array_equal(a[:, _CMP], b[:, _CMP]))
 
 
 def _regular(r):
@@ -133,7 +134,7 @@ def _f32_bits(x):
 
 
 def _bits_f32(b):
-    return float(np.array([b], np.int64).astype(np.int32).view(np.float32)[0])
+    return float(np.array([b], np.int32).view(np.float32)[0])
 
 
 def boundary_check(truth, local, carry_bits, seg_start, core_start):
@@ -155,7 +156,7 @@ def boundary_check(truth, local, carry_bits, seg_start, core_start):
     m = min(len(t), len(l))
     if m < 2:
         return False
-    same = np.all(t[len(t) - m:] == l[len(l) - m:], axis=1)[::-1]       # common tail, newest frame first
+    same = np.all(t[len(t) - m:][:, _CMP] == l[len(l) - m:][:, _CMP], axis=1)[::-1]       # common tail, newest frame first
     n = m if same.all() else int(np.argmin(same))
     if n < 2:
         return False
@@ -185,18 +186,19 @@ def resume_point(truth, seg_start, core_start):
 
 
 def gather_records(rec, device=None):
-    """All ranks' record arrays (NCCL all_gather of padded int64 tensors on GPUs, gloo on CPU); list indexed by rank."""
+    """All ranks' record arrays (NCCL all_gather of the padded int32 tables on GPUs, gloo on CPU); list indexed by rank."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [rec]
     world = dist.get_world_size()
+    rec = np.ascontiguousarray(rec, np.int32)
     n = torch.tensor([len(rec)], dtype=torch.int64, device=device)
     counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(counts, n)
     counts = [int(c.item()) for c in counts]
     cap = max(max(counts), 1)
-    buf = torch.zeros((cap, REC_FIELDS), dtype=torch.int64, device=device)
+    buf = torch.zeros((cap, REC_FIELDS), dtype=torch.int32, device=device)
     if len(rec):
         buf[:len(rec)] = torch.from_numpy(np.ascontiguousarray(rec)).to(buf.device)
     bufs = [torch.zeros_like(buf) for _ in range(world)]
@@ -206,7 +208,7 @@ def gather_records(rec, device=None):
 
 def _with_header(rec, lo, carry_bits):
     """First row of what a rank sends: where its decode started and the frequency offset it started with."""
-    h = np.zeros((1, REC_FIELDS), np.int64)
+    h = np.zeros((1, REC_FIELDS), np.int32)
     h[0, TRIG], h[0, BURST], h[0, FREQ] = -1, lo, carry_bits
     return np.concatenate([h, rec])
 
@@ -237,7 +239,7 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
     rounds = 0
     while True:
         allrec = (gather or gather_records)(_with_header(local, lo, carry), device)
-        truth = np.zeros((0, REC_FIELDS), np.int64)
+        truth = np.zeros((0, REC_FIELDS), np.int32)
         bad = None
         owned_all = []
         for r, sr in enumerate(segs):

@@ -575,7 +575,7 @@ def test_time_sharding_reconciles_adversarial_traffic(O, W, trunc):
         dec = gpu_segment_decoder(h, y)
         for world in (2, 4):
             owned, rounds = S.simulate_ranks(dec, S.shard_stream(y.size, world), y.size)
-            assert np.array_equal(np.concatenate(owned), truth) and rounds >= 1, (world, rounds)
+            assert S.same(np.concatenate(owned), truth) and rounds >= 1, (world, rounds)
     finally:
         h.close()
 
@@ -594,7 +594,7 @@ def test_resumed_stream_state_entry_point_matches_oracle(O, W):
             ref = O.rx(y[lo - st["hist"]:], algo=3, hist=st["hist"], min_pos=st["min_pos"], fo_carry=st["fo_carry"])
             dec(lo, y.size, st, True)
             assert_frames_equal(h.results(), ref)
-            assert np.array_equal(S.records(ref.frames, lo), truth[k:])
+            assert S.same(S.records(ref.frames, lo), truth[k:])
         with pytest.raises(W.WifiB200Error):       # history that is not there
             bad = np.zeros(1, W.wifi_b200.LINK_STATE_DTYPE)
             bad["hist"] = 64

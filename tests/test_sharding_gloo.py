@@ -40,7 +40,7 @@ def _worker(rank, world, port, kind, out_dir):
         # every rank decodes its segment, the frame records are all-gathered (gloo here, NCCL on the GPUs), every rank
         # checks that it joined the sequential receiver's state and decodes again from a known state if it did not
         own, owned_all, rounds = S.reconcile(oracle_segment_decoder(O, y, algo=0), S.shard_stream(y.size, world), rank, y.size)
-        assert np.array_equal(np.concatenate(owned_all), S.records(full, 0)), (kind, rank)
+        assert S.same(np.concatenate(owned_all), S.records(full.copy(), 0)), (kind, rank)
         assert (rounds >= 1) == (kind != "stream"), (kind, rounds)      # idle gaps: joined at once; adversarial: one more pass
         frames = np.zeros(len(own), full.dtype)
         for k, col in (("sig_ok", S.SIG), ("decoded", S.DEC), ("crc_ok", S.CRC), ("length", S.LEN), ("encoding", S.ENC)):
@@ -92,10 +92,10 @@ def test_reconcile_cascades_over_many_ranks():
         truth = S.records(O.rx(y, algo=1, want_carrier=False).frames, 0)
         for world in (3, 5):
             owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=1), S.shard_stream(y.size, world), y.size)
-            assert np.array_equal(np.concatenate(owned), truth) and rounds >= 1, (trunc, world, rounds)
+            assert S.same(np.concatenate(owned), truth) and rounds >= 1, (trunc, world, rounds)
     y, _ = make_capture(O, np.random.default_rng(8), [(4, 600)] * 30, snr_db=28, seed=3, gap=1100, cfo=0.004)
     owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=0), S.shard_stream(y.size, 4), y.size)
-    assert np.array_equal(np.concatenate(owned), S.records(O.rx(y, algo=0, want_carrier=False).frames, 0)) and rounds == 0
+    assert S.same(np.concatenate(owned), S.records(O.rx(y, algo=0, want_carrier=False).frames, 0)) and rounds == 0
 
 
 def test_resumed_stream_state_reproduces_the_sequential_receiver():
@@ -111,9 +111,9 @@ def test_resumed_stream_state_reproduces_the_sequential_receiver():
     truth = S.records(full.frames, 0)
     for k in (2, 4, 6):
         lo, st, front = S.resume_point(truth, 0, int(truth[k, S.TRIG]) + 1)
-        assert len(front) == 1 and np.array_equal(front[0], truth[k - 1]) and lo + st["min_pos"] == truth[k, S.TRIG]
+        assert len(front) == 1 and S.same(front, truth[k - 1:k]) and lo + st["min_pos"] == truth[k, S.TRIG]
         r = O.rx(y[lo - st["hist"]:], algo=3, want_carrier=False, hist=st["hist"], min_pos=st["min_pos"], fo_carry=st["fo_carry"])
-        assert np.array_equal(S.records(r.frames, lo), truth[k:])
+        assert S.same(S.records(r.frames, lo), truth[k:])
         assert r.pdus() == full.pdus()[k:]
 
 
