@@ -185,32 +185,43 @@ def resume_point(truth, seg_start, core_start):
     return start, {"min_pos": int(f2[TRIG]) - start, "fo_carry": _bits_f32(f1[FREQ]), "hist": min(HIST, start)}, t[idx[-1]:idx[-1] + 1]
 
 
-def gather_records(rec, device=None):
-    """All ranks' record arrays (NCCL all_gather of the padded int32 tables on GPUs, gloo on CPU); list indexed by rank."""
+def gather_records(hdr, rec, device=None):
+    """All ranks' (header, record table) pairs (NCCL all_gather of the padded int32 tables on GPUs, gloo on CPU); list
+    indexed by rank.  The header row says where a rank's decode started and the frequency offset it started with."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return [rec]
+        return [(hdr, rec)]
     world = dist.get_world_size()
     rec = np.ascontiguousarray(rec, np.int32)
     n = torch.tensor([len(rec)], dtype=torch.int64, device=device)
     counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(counts, n)
     counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
+    cap = max(counts) + 1
     buf = torch.zeros((cap, REC_FIELDS), dtype=torch.int32, device=device)
+    buf[0] = torch.from_numpy(hdr).to(buf.device)
     if len(rec):
-        buf[:len(rec)] = torch.from_numpy(np.ascontiguousarray(rec)).to(buf.device)
+        buf[1:1 + len(rec)] = torch.from_numpy(rec).to(buf.device)
     bufs = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(bufs, buf)
-    return [b[:c].cpu().numpy() for b, c in zip(bufs, counts)]
+    out = []
+    for b, c in zip(bufs, counts):
+        a = b[:1 + c].cpu().numpy()
+        out.append((a[0], a[1:]))
+    return out
 
 
-def _with_header(rec, lo, carry_bits):
-    """First row of what a rank sends: where its decode started and the frequency offset it started with."""
-    h = np.zeros((1, REC_FIELDS), np.int32)
-    h[0, TRIG], h[0, BURST], h[0, FREQ] = -1, lo, carry_bits
-    return np.concatenate([h, rec])
+def _header(lo, carry_bits):
+    h = np.zeros(REC_FIELDS, np.int32)
+    h[TRIG], h[BURST], h[FREQ] = -1, lo, carry_bits
+    return h
+
+
+def _owned(rec, seg):
+    """The rows of a trigger-ordered table that lie in the segment's core region (a view)."""
+    a, b = np.searchsorted(rec[:, TRIG], [seg["core_start"], seg["core_end"]])
+    return rec[a:b]
 
 
 def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gather=None):
@@ -238,25 +249,35 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
     local = decode_closed(lo, None)
     rounds = 0
     while True:
-        allrec = (gather or gather_records)(_with_header(local, lo, carry), device)
-        truth = np.zeros((0, REC_FIELDS), np.int32)
-        bad = None
-        owned_all = []
+        allrec = (gather or gather_records)(_header(lo, carry), local, device)
+        owned_all, bad = [], None
+
+        def truth_before(core_start, rows):
+            """The lower ranks' owned records in front of core_start: the last `rows` of them (None: all)."""
+            parts, have = [], 0
+            for own in reversed(owned_all):
+                parts.append(own)
+                have += len(own)
+                if rows is not None and have >= rows:
+                    break
+            t = np.concatenate(parts[::-1]) if parts else np.zeros((0, REC_FIELDS), np.int32)
+            return t[t[:, TRIG] < core_start]
+
         for r, sr in enumerate(segs):
-            hdr, rec = allrec[r][0], allrec[r][1:]
-            if r > 0 and not boundary_check(truth, rec, int(hdr[FREQ]), int(hdr[BURST]), sr["core_start"]):
-                bad = r
-                break
-            own = rec[(rec[:, TRIG] >= sr["core_start"]) & (rec[:, TRIG] < sr["core_end"])]
-            owned_all.append(own)
-            truth = np.concatenate([truth, own])
+            hdr, rec = allrec[r]
+            if r > 0:
+                n_front = int(np.searchsorted(rec[:, TRIG], sr["core_start"]))
+                if not boundary_check(truth_before(sr["core_start"], n_front + 64), rec, int(hdr[FREQ]), int(hdr[BURST]), sr["core_start"]):
+                    bad = r
+                    break
+            owned_all.append(_owned(rec, sr))
         if bad is None:
             return owned_all[rank], owned_all, rounds
         rounds += 1
         if max_rounds is not None and rounds > max_rounds:
             raise RuntimeError("time sharding did not reconcile in %d rounds" % max_rounds)
         if bad == rank:
-            rp = resume_point(truth, seg["start"], seg["core_start"])
+            rp = resume_point(truth_before(seg["core_start"], None), seg["start"], seg["core_start"])
             if rp is None:                                # nothing is known but the start of the capture
                 lo, carry = 0, _f32_bits(0.0)
                 local = decode_closed(0, None)
@@ -274,8 +295,8 @@ def simulate_ranks(decode, segs, n_samples):
     slots, out, bar, errs = [None] * world, [None] * world, threading.Barrier(world), []
 
     def run(rank):
-        def gather(rec, device=None):
-            slots[rank] = rec
+        def gather(hdr, rec, device=None):
+            slots[rank] = (hdr, rec)
             bar.wait()
             res = list(slots)
             bar.wait()
