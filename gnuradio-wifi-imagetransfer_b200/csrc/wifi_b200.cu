@@ -224,6 +224,7 @@ struct wifi_b200 {
     int64_t s_cap = 0;             //   straight to the device and stay there until their burst is decoded
     struct MoveSeg { int64_t src, dst, n; };
     MoveSeg *d_moves = nullptr;    // tail compaction descriptors
+    int64_t group_samples = 0;     // WIFI_P_HOST_GROUP_SAMPLES: samples per link group of the host-input batch calls (0: 128 MB of host bytes)
     int64_t s_batch = 0;           // WIFI_P_STREAM_BATCH: a push only buffers until this many new samples per link wait (0: every push)
     int64_t s_unprocessed = 0;     // samples appended to the fullest link since the last pipeline run
     std::vector<wifi_b200_frame> s_meta;
@@ -418,7 +419,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
     if (plan && n_links > 1) {
         // about 128 MB of host bytes per group: its copy then takes longer than its decode (a group costs 1.5 - 3 ms of
         // kernels whatever its size: the Viterbi launch is latency bound), so the decode hides behind the next copy
-        const int64_t target = std::max<int64_t>(((int64_t)128 << 20) / (int64_t)plan->bytes_per_sample, (int64_t)1 << 22);
+        const int64_t target = h->group_samples > 0 ? h->group_samples : std::max<int64_t>(((int64_t)128 << 20) / (int64_t)plan->bytes_per_sample, (int64_t)1 << 22);
         int64_t acc = 0;
         for (int l = 0; l < n_links; ++l) {
             acc += h->h_links[l].len;
@@ -751,6 +752,7 @@ int wifi_b200_set_param(wifi_b200_t *h, int id, double v)
     case WIFI_P_MIN_PLATEAU: if (v < 1 || v > 16) return WIFI_E_ARG; h->cfg.min_plateau = (int)v; break;
     case WIFI_P_SOFT_DECISION: h->cfg.soft_decision = v != 0; break;
     case WIFI_P_STREAM_BATCH: if (v < 0 || v > (double)h->cfg.max_samples / 2) return WIFI_E_ARG; h->s_batch = (int64_t)v; break;
+    case WIFI_P_HOST_GROUP_SAMPLES: if (v < 0) return WIFI_E_ARG; h->group_samples = (int64_t)v; break;
     case WIFI_P_WANT_CARRIER:
         if (v != 0 && !h->d_carrier) {
             cudaSetDevice(h->device);
@@ -777,6 +779,7 @@ double wifi_b200_get_param(wifi_b200_t *h, int id)
     case WIFI_P_WANT_CARRIER: return h->cfg.want_carrier;
     case WIFI_P_SOFT_DECISION: return h->cfg.soft_decision;
     case WIFI_P_STREAM_BATCH: return (double)h->s_batch;
+    case WIFI_P_HOST_GROUP_SAMPLES: return (double)h->group_samples;
     default: return NAN;
     }
 }

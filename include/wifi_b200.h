@@ -56,7 +56,11 @@ enum { WIFI_P_BANDWIDTH = 0, WIFI_P_FREQUENCY = 1, WIFI_P_SENSITIVITY = 2, WIFI_
        /* streaming only: wifi_b200_rx_push buffers until this many new samples wait (0 = run on every push).  A run
         * costs 1-3 ms whatever its size, so a live 20 Msps stream wants 65536 or more; results are unchanged.
         * An empty push (n = 0, flush = 0) runs the pipeline on whatever is buffered without ending the stream. */
-       WIFI_P_STREAM_BATCH = 8 };
+       WIFI_P_STREAM_BATCH = 8,
+       /* host-input batch calls (rx_batch, rx_batch_sc16) process the links in groups so that the copy of one group overlaps
+        * the decoding of the previous one; a group is closed when it holds this many samples (0 = about 128 MB of host
+        * bytes, the default).  Results do not depend on it. */
+       WIFI_P_HOST_GROUP_SAMPLES = 9 };
 
 typedef struct wifi_b200_cfg {
     double bandwidth;      /* Hz, hier default 10e6 (wifi_phy_hier.grc:92)                        */

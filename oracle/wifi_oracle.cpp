@@ -565,6 +565,11 @@ struct FrontEnd {
     {
         sa = {0.f, 0.f};
         sp = 0.f;
+        if (i0 >= 64) {
+            for (int64_t j = i0 - 47; j < i0; ++j) sa = wdm_cmacc(sa, x[j], x[j - 16]);
+            for (int64_t j = i0 - 63; j < i0; ++j) sp = wdm_norm_add(sp, x[j]);
+            return;
+        }
         for (int64_t j = i0 - 47; j < i0; ++j) sa = wdm_cmacc(sa, at(j), at(j - 16));
         for (int64_t j = i0 - 63; j < i0; ++j) sp = wdm_norm_add(sp, at(j));
     }
@@ -574,12 +579,21 @@ struct FrontEnd {
     inline void step(int64_t i, cf &a, float &p, float &c)
     {
         if ((i & 63) == 0) seed(i);
-        sa = wdm_cmacc(sa, at(i), at(i - 16));
-        a = sa;
-        sa = wdm_cmsubc(sa, at(i - 47), at(i - 63));
-        sp = wdm_norm_add(sp, at(i));
-        p = sp;
-        sp = wdm_norm_sub(sp, at(i - 63));
+        if (i >= 64) { /* every tap lies inside the stream: the same operations without the start-of-stream tests */
+            sa = wdm_cmacc(sa, x[i], x[i - 16]);
+            a = sa;
+            sa = wdm_cmsubc(sa, x[i - 47], x[i - 63]);
+            sp = wdm_norm_add(sp, x[i]);
+            p = sp;
+            sp = wdm_norm_sub(sp, x[i - 63]);
+        } else {
+            sa = wdm_cmacc(sa, at(i), at(i - 16));
+            a = sa;
+            sa = wdm_cmsubc(sa, at(i - 47), at(i - 63));
+            sp = wdm_norm_add(sp, at(i));
+            p = sp;
+            sp = wdm_norm_sub(sp, at(i - 63));
+        }
         m2 = wdm_norm(a);
         c = sqrtf(m2) / p;
     }

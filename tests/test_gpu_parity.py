@@ -356,6 +356,37 @@ def test_udp_runner_speaks_the_apps_contract(O, W):
     t.close()
 
 
+@pytest.mark.parametrize("soft", [False, True])
+def test_host_batch_link_groups_give_the_single_pass_table(O, W, soft):
+    """wifi_b200_rx_batch pipelines groups of links (copy / decode / results on three streams); frame records, rows, equalised
+    points and PSDU slots of the groups follow each other exactly as one pass over all links would lay them out."""
+    rng = np.random.default_rng(23)
+    links, offs = [], [0]
+    for l in range(7):
+        y, _ = make_capture(O, rng, [(int(rng.integers(0, 8)), int(rng.integers(40, 400))) for _ in range(int(rng.integers(1, 5)))],
+                            snr_db=float(rng.uniform(12, 30)), cfo=float(rng.uniform(-0.01, 0.01)), seed=l, lead=int(rng.integers(20, 300)), gap=int(rng.integers(200, 900)))
+        links.append(y if l != 3 else np.zeros(500, np.complex64))          # one silent link: a group without frames
+        offs.append(offs[-1] + links[-1].size)
+    x = np.concatenate(links)
+    ref = O.rx_links(x, offs[:-1], np.diff(offs), algo=1, soft=soft)
+    h = W.Handle(max_samples=1 << 19, max_frames=512, chan_est=1, want_carrier=True, soft_decision=soft)
+    try:
+        for group in (1, 9000, 0):                                          # a group per link, a few links per group, one group
+            h.set_param(W.wifi_b200.P_HOST_GROUP_SAMPLES, group)
+            res = h.rx_batch(x, np.array(offs, np.uint64))
+            assert_frames_equal(res, ref)
+            rows, car = h.rows(carrier=True)
+            used = np.concatenate([np.arange(int(r["row_off"]), int(r["row_off"]) + int(r["n_rows"])) for r in res.frames])
+            assert np.array_equal(rows[used], ref.rows) and np.array_equal(car[used], ref.carrier)
+            if soft:
+                assert np.array_equal(h.soft_rows()[used], ref.soft)
+            i16 = np.clip(np.rint(np.stack([x.real, x.imag], axis=1) * 2048), -32768, 32767).astype(np.int16)
+            xq = (i16.astype(np.float32) * np.float32(1 / 2048)).view(np.complex64).reshape(-1)
+            assert_frames_equal(h.rx_batch_sc16(i16, 1 / 2048, np.array(offs, np.uint64)), O.rx_links(xq, offs[:-1], np.diff(offs), algo=1, soft=soft))
+    finally:
+        h.close()
+
+
 def test_host_alloc_gives_page_locked_memory_the_entry_points_accept(O, W):
     rng = np.random.default_rng(71)
     y, psdus = make_capture(O, rng, [(6, 300), (2, 150)], snr_db=30, seed=4)
