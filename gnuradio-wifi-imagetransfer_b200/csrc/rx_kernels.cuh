@@ -43,22 +43,25 @@ __device__ __forceinline__ int find_link(const LinkDesc *links, int n_links, int
 // x[n-16], x[n-47], x[n-63] are register reads.  Flag n = |a[n]|^2 > thr^2 p[n]^2 (oracle rx_link).
 // A block is DET_BLOCK threads and works on half a tile (its 64 chunks plus two chunks of history): six blocks fit an
 // SM, so six loads are in different phases instead of three.
+#ifndef DET_BLOCK
 #define DET_BLOCK 64
+#endif
+#define DET_SPLIT (DET_THREADS / DET_BLOCK)               // blocks per tile
 #define DET_ROWS (DET_BLOCK + 2)
 #define DET_STRIDE 66                                        // samples between rows in shared memory
-#define DET_SMEM_BYTES (DET_ROWS * DET_STRIDE * (int)sizeof(cf) + 16)   // + two mbarriers
+#define DET_SMEM_BYTES (DET_ROWS * DET_STRIDE * (int)sizeof(cf) + 32)   // + one mbarrier per warp
 
 __device__ __forceinline__ uint32_t det_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(DET_BLOCK, 6) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
+__global__ void __launch_bounds__(DET_BLOCK, 384 / DET_BLOCK) k_detect(const cf *__restrict__ iq, const LinkDesc *__restrict__ links, int n_links,
                                                          int64_t tile_base, int64_t total_tiles, float thr_f, uint32_t *__restrict__ flags,
                                                          uint32_t *__restrict__ summary)
 {
     extern __shared__ __align__(128) unsigned char det_raw[];
     cf *sx = reinterpret_cast<cf *>(det_raw);                                         // DET_ROWS x DET_STRIDE
     uint64_t *bar = reinterpret_cast<uint64_t *>(det_raw + DET_ROWS * DET_STRIDE * sizeof(cf));
-    const int64_t tile = tile_base + (blockIdx.x >> 1);   // links / n_links: the link group of this launch; tiles are numbered over the whole call
-    const int half = blockIdx.x & 1;                      // which 64 chunks of the tile
+    const int64_t tile = tile_base + blockIdx.x / DET_SPLIT;   // links / n_links: the link group of this launch; tiles are numbered over the whole call
+    const int half = blockIdx.x % DET_SPLIT;                   // which DET_BLOCK chunks of the tile
     if (tile >= total_tiles) return;
     const int tid = threadIdx.x;
     int l = find_link(links, n_links, tile * DET_THREADS);

@@ -474,7 +474,7 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
         }
         if (timed) mark(h, ST_DETECT);
         if (tiles_g > 0)
-            k_detect<<<(unsigned)(2 * tiles_g), DET_BLOCK, DET_SMEM, s>>>(iq, gl, ng, tile_base, tile_base + tiles_g, thr_f, h->d_flags, h->d_summary);
+            k_detect<<<(unsigned)(DET_SPLIT * tiles_g), DET_BLOCK, DET_SMEM, s>>>(iq, gl, ng, tile_base, tile_base + tiles_g, thr_f, h->d_flags, h->d_summary);
         if (timed) mark(h, ST_SELECT);
         if (tiles_g > 0)
             k_select_spec<<<(unsigned)((tiles_g * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, tile_base, tile_base + tiles_g,
