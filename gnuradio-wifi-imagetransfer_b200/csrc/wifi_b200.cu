@@ -270,6 +270,10 @@ int upload_tables(wifi_b200 *h)
 void free_all(wifi_b200 *h)
 {
     cudaSetDevice(h->device);
+    // nothing of this handle may still be reading a caller's buffer or writing a pinned mirror when the memory goes away
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     for (int k = 0; k < A_SLOTS; ++k) if (h->a_ev[k]) cudaEventDestroy(h->a_ev[k]);
     void *ptrs[] = {h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
                     h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
