@@ -8,4 +8,4 @@ imported through the `wifi_b200` shim at the repository root or with importlib:
 from . import build, wifi_b200  # noqa: F401
 from .wifi_b200 import Handle, WifiB200Error, FRAME_DTYPE, ENCODINGS, EQUALIZERS  # noqa: F401
 from .wifi_phy_hier import wifi_phy_hier, mac  # noqa: F401
-from . import sharding, loopback_runner, ota_runners, pcap  # noqa: F401
+from . import sharding, loopback_runner, ota_runners, pcap, featuremap  # noqa: F401

@@ -73,23 +73,21 @@ def test_config1_full_10s_capture_16qam_multipath_cfo(O, W):
         bench.ENC, bench.PSDU_LEN, bench.GAP, bench.SNR_DB, bench.N_DBPS, bench.TAPS = saved
 
 
+def latent_of(img):
+    """img2msg's latent -- a (30, 30, 128) float32 map per image; the trained weights are absent from the reference, so a
+    seeded surrogate of the same shape and dtype stands in."""
+    return np.random.default_rng(1000 + img).standard_normal((30, 30, 128)).astype(np.float32)
+
+
 def feature_map_payloads(n_images=6):
-    """What upload_featuremap_udp.py puts on the wire (:32-48): img2msg's latent -- a (30, 30, 128) float32 map per image;
-    the trained weights are absent from the reference, so a seeded surrogate of the same shape and dtype stands in
-     -- cut by image_detach_rebuild.detach_image (:6-32) into (10, 10, 1) pieces with their (y, x, c)
-    positions, shuffled (sklearn.utils.shuffle, seeded here), each sent as `=L` length + pickle."""
-    from sklearn.utils import shuffle
+    """What upload_featuremap_udp.py puts on the wire (:32-48) for each image: the latent cut by detach_image
+    (image_detach_rebuild.py:6-32) into (10, 10, 1) pieces with their (y, x, c) positions, shuffled (seeded here), each sent
+    as `=L` length + pickle -- through the package's featuremap module."""
+    import wifi_b200
+    fm = wifi_b200.featuremap
     out = []
     for img in range(n_images):
-        latent = np.random.default_rng(1000 + img).standard_normal((30, 30, 128)).astype(np.float32)
-        pieces = []
-        for y in range(0, 30, 10):
-            for x in range(0, 30, 10):
-                for c in range(128):
-                    pieces.append(((y, x, c), latent[y:y + 10, x:x + 10, c:c + 1]))
-        for piece in shuffle(pieces, random_state=img):
-            d = pickle.dumps(piece)
-            out.append(struct.pack("=L", len(d)) + d)
+        out += [fm.to_datagram(p) for p in fm.detach(latent_of(img), random_state=img)]
     return out
 
 
@@ -166,4 +164,17 @@ def test_config4_per_ladder_all_mcs_feature_map_payloads(O, W):
     assert len(pdus) == int((res.frames["crc_ok"] == 1).sum()) and all(p[24:] in sent for p in pdus[::97])
     (pos, piece) = pickle.loads(pdus[-1][24:][4:])
     assert piece.shape == (10, 10, 1) and piece.dtype == np.float32 and len(pos) == 3
+    # the viewer's side (download_featuremap_udp.py:53-69): at the top of the ladder every piece of the links' images arrives
+    # and rebuild_image gives the latent back; lower down the map has holes where frames were lost
+    fm = W.featuremap
+    top = res.frames["link"] == 7 * len(snrs) + len(snrs) - 1                 # 64-QAM 3/4 at 30 dB: frames 7*16*200+15*200 .. of the sequence
+    got = [fm.from_datagram(res.psdu(i)[:-4][24:][4:]) for i in np.nonzero(top & (res.frames["crc_ok"] == 1))[0]]
+    first = (7 * len(snrs) + len(snrs) - 1) * fpp
+    sent_here = [fm.from_datagram(pay[(first + j) % len(pay)][4:]) for j in range(fpp)]
+    assert len(got) >= fpp - 4
+    img = (first % len(pay)) // 1152
+    rebuilt, want = fm.rebuild(got, (30, 30, 128)), fm.rebuild([p for p in sent_here], (30, 30, 128))
+    mask = rebuilt != 0
+    assert mask.sum() >= 0.97 * (want != 0).sum() and np.array_equal(rebuilt[mask], want[mask])
+    assert np.array_equal(want[want != 0], latent_of(img)[want != 0]) or (first % len(pay)) % 1152 + fpp > 1152
     h.close()
