@@ -193,6 +193,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
         h.rx_batch_dev(cap.data_ptr(), link_off, final=True, fetch=False)
         whole = h.frames()
     t_one = (time.perf_counter() - t0) / reps
+    one_stage = {k: round(v, 3) for k, v in h.stage_times().items() if v}
     equal = None
     if rank == 0:
         equal = S.same(np.concatenate(owned_all), S.records(whole, 0))
@@ -206,7 +207,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
     t_sh, dec_sh, t_one = [float(v) for v in tv.tolist()]
     return {"capture": "one link, %d frames, %d samples (%.2f GB), the same on every rank" % (fpl, n_total, n_total * 8 / 1e9),
             "ranks": world, "overlap_samples": S.OVERLAP, "sharded_ms": 1e3 * t_sh, "sharded_decode_device_ms": dec_sh,
-            "single_gpu_ms": 1e3 * t_one, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
+            "single_gpu_ms": 1e3 * t_one, "single_gpu_stage_ms": one_stage, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
             "value_msamples_per_s": n_total / t_sh / 1e6, "frames_owned_total": int(cnt[0]), "crc_ok_total": int(cnt[1]),
             "re_decode_rounds": rounds, "union_equals_single_gpu_table": equal, "scaling": "strong",
             "collective": "NCCL all_gather of the frame tables (96 bytes per frame) + counter all_reduce" if world > 1 else "none (one rank)",

@@ -98,6 +98,32 @@ def test_reconcile_cascades_over_many_ranks():
     assert S.same(np.concatenate(owned), S.records(O.rx(y, algo=0, want_carrier=False).frames, 0)) and rounds == 0
 
 
+def test_reconcile_fuzz_random_traffic():
+    """Random traffic -- gaps from none at all to a long silence, frames cut short by the next one, short captures against
+    many ranks (cores shorter than the overlap) -- cut across 2..6 ranks: always the sequential table."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+    from oracle import oracle as O
+    from util import make_psdu, oracle_segment_decoder
+    S = importlib.import_module("gnuradio-wifi-imagetransfer_b200.sharding")
+    for seed in range(5):
+        rng = np.random.default_rng(500 + seed)
+        parts = [np.zeros(int(rng.integers(0, 400)), np.complex64)]
+        for i in range(int(rng.integers(25, 60))):
+            f = O.tx_frame(make_psdu(O, rng, int(rng.integers(30, 500)), seq=i), int(rng.integers(0, 8)), seed=1 + i % 127)
+            if rng.random() < 0.2:
+                f = f[:int(rng.integers(350, f.size))]                  # cut short: the next preamble re-triggers inside it
+            parts += [f, np.zeros(int(rng.choice([0, 0, 40, 300, 900, 2500, 60000 if i % 17 == 5 else 700])), np.complex64)]
+        x = np.concatenate(parts).astype(np.complex64)
+        y = O.channel(x, gain=0.6, cfo=float(rng.uniform(-0.01, 0.01)), noise_sigma=0.6 * 10 ** (-float(rng.uniform(14, 30)) / 20), seed=seed)
+        algo = int(rng.integers(0, 4))
+        truth = S.records(O.rx(y, algo=algo, want_carrier=False).frames, 0)
+        for world in (2, 3, 6):
+            owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=algo), S.shard_stream(y.size, world), y.size)
+            assert S.same(np.concatenate(owned), truth), (seed, world, rounds)
+
+
 def test_resumed_stream_state_reproduces_the_sequential_receiver():
     """(min_pos, fo_carry, hist) -- wifi_b200_link_state -- is all a decode needs to continue behind two regular frames."""
     sys.path.insert(0, ROOT)
