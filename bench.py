@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--soft", action="store_true", help="soft-decision mode (extension, DESIGN.md 9)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-time-shard", action="store_true", help="skip the time-sharded section (one capture cut into overlapping segments across the ranks)")
-    ap.add_argument("--ts-frames", type=int, default=131072, help="frames of the single-link capture the time-sharded section cuts across the ranks (the same at every N: strong scaling)")
+    ap.add_argument("--ts-frames", type=int, default=151552, help="frames of the single-link capture the time-sharded section cuts across the ranks (the same at every N: strong scaling)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8192, help="frames of the cpu_baseline sample")
     return ap.parse_args()
@@ -434,7 +434,8 @@ def main():
         import threading
         # page-locked host capture from the library's own allocator: first touched on the cores next to this rank's GPU
         hn = h.host_alloc(cap.numel() // 2, np.complex64)
-        hn.view(np.float32)[:] = cap.cpu().numpy()
+        torch.from_numpy(hn.view(np.float32)).copy_(cap)       # device -> page-locked host, no temporary
+        torch.cuda.synchronize()
         host = hn
         parts = 4 if n_links >= 4 else 1
         bounds = [n_links * i // parts for i in range(parts + 1)]
