@@ -228,13 +228,62 @@ __global__ void __launch_bounds__(128) k_select_spec(const uint32_t *__restrict_
     if (lane == 0) spec_meta[seg] = make_int4(k < SEG_CAP ? k : SEG_CAP, first, last, 0);
 }
 
+// Second speculative pass, one warp per segment: a segment whose first speculative trigger lies inside the MIN_GAP of the
+// LAST speculative trigger of the segment before it (an STS plateau near or across the segment boundary: 7 % of the
+// segments of back-to-back traffic) walks its chain again from behind that trigger -- in parallel, into a second trigger
+// array.  Unless the segment before changes its own last trigger in this very pass (second order), the sequential pass then
+// finds every segment acceptable: without this pass one long stream spent 7 ms per 900 Msamples re-walking there.
+// meta2[seg] = (count, first, last, w): w = 0: the unconstrained chain of the first pass (in spec_trig), valid whenever its
+// first trigger is more than MIN_GAP behind the true previous trigger; w = p + 1: the chain walked from behind trigger p (in
+// spec_trig2), valid exactly when the true previous trigger IS p.
+__global__ void __launch_bounds__(128) k_select_fix(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary,
+                                                     const LinkDesc *__restrict__ links, int n_links, int64_t seg_base, int64_t total_segs, int min_plateau,
+                                                     const int *__restrict__ spec_trig, const int4 *__restrict__ spec_meta, int *__restrict__ spec_trig2,
+                                                     int4 *__restrict__ meta2)
+{
+    int64_t seg = seg_base + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (seg >= total_segs) return;
+    const int l = find_link(links, n_links, seg * SEG_CHUNKS);
+    const LinkDesc L = links[l];
+    const int4 me = spec_meta[seg];
+    const int64_t c0 = seg * SEG_CHUNKS - L.chunk_base;            // first chunk of the segment in the link
+    bool redo = false;
+    int64_t p = 0;
+    if (c0 > 0 && me.x > 0) {
+        const int4 pv = spec_meta[seg - 1];                        // same link: its segments are consecutive
+        if (pv.x > 0) { p = pv.z; redo = !((int64_t)me.y > p + SS_MIN_GAP); }
+    }
+    if (!redo) {
+        if (lane == 0) meta2[seg] = make_int4(me.x, me.y, me.z, 0);
+        return;
+    }
+    const uint32_t *fw = flags + L.chunk_base * 2;
+    const int64_t n_chunks = (L.len + FE_CHUNK - 1) / FE_CHUNK;
+    const int64_t c1 = (c0 + SEG_CHUNKS < n_chunks) ? c0 + SEG_CHUNKS : n_chunks;
+    const int64_t end = (c1 * FE_CHUNK < L.len) ? c1 * FE_CHUNK : L.len;
+    int64_t pos = p + SS_MIN_GAP + 1;
+    int k = 0, first = 0, last = 0;
+    while (pos < end) {
+        int64_t m = next_candidate(fw, summary, L.chunk_base, c1, pos, lane, min_plateau);
+        if (m < 0 || m >= end) break;
+        if (lane == 0 && k < SEG_CAP) spec_trig2[seg * SEG_CAP + k] = (int)m;
+        if (k == 0) first = (int)m;
+        last = (int)m;
+        ++k;
+        pos = m + SS_MIN_GAP + 1;
+    }
+    if (lane == 0) meta2[seg] = make_int4(k < SEG_CAP ? k : SEG_CAP, first, last, (int)p + 1);
+}
+
 // Sequential pass, one warp per link: accepts speculative segments 32 at a time while each first
 // trigger is more than MIN_GAP after the last trigger before it, re-walks the flags otherwise.
 // Leaves the triggers in trig_tmp and their count in links[].frame_count.
 __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ summary, LinkDesc *links,
                                                  int n_links, int min_plateau, int *trig_tmp,
-                                                 const int *__restrict__ spec_trig, const int4 *__restrict__ spec_meta)
+                                                 const int *__restrict__ spec_trig, const int4 *__restrict__ spec_meta, const int *__restrict__ spec_trig2)
 {
+    // spec_meta here is k_select_fix's output: .w says which of the two trigger arrays holds a segment's chain
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_links) return;
     LinkDesc L = links[warp];
@@ -268,8 +317,9 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
         nxt_s = s + 128;
         load_group(nxt_s, nxt);
         int cnt[4], first[4], last[4];
+        const int *src[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { cnt[q] = meta[q].x; first[q] = meta[q].y; last[q] = meta[q].z; }
+        for (int q = 0; q < 4; ++q) { cnt[q] = meta[q].x; first[q] = meta[q].y; last[q] = meta[q].z; src[q] = meta[q].w ? spec_trig2 : spec_trig; }
         // last trigger before each segment, assuming every earlier segment of the group is accepted
         const int64_t NONE = -(1ll << 40);
         int64_t lane_last = NONE;
@@ -286,10 +336,12 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
         int64_t b4 = before;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (cnt[q]) {
+            if (meta[q].w) {                                             // second-pass chain: right iff the trigger before it is the assumed one
+                if (my_bad == 4 && b4 != (int64_t)meta[q].w - 1) my_bad = q;
+            } else if (cnt[q]) {
                 if (my_bad == 4 && !((int64_t)first[q] > b4 + SS_MIN_GAP)) my_bad = q;
-                b4 = last[q];
             }
+            if (cnt[q]) b4 = last[q];
         }
         unsigned badm = __ballot_sync(0xffffffffu, my_bad < 4);
         int n_ok;                                                        // segments s .. s+n_ok-1 are accepted as speculated
@@ -317,7 +369,7 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
                 int64_t si = s + lane * 4 + q;
                 if (cnt[q] > 0) tmp[wpos] = first[q];
                 if (cnt[q] > 1) tmp[wpos + cnt[q] - 1] = last[q];
-                for (int j = 1; j < cnt[q] - 1; ++j) tmp[wpos + j] = spec_trig[(seg0 + si) * SEG_CAP + j];
+                for (int j = 1; j < cnt[q] - 1; ++j) tmp[wpos + j] = src[q][(seg0 + si) * SEG_CAP + j];
                 wpos += cnt[q];
             }
         }
@@ -340,6 +392,7 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
             const int64_t c1 = ((s + 1) * SEG_CHUNKS < n_chunks) ? (s + 1) * SEG_CHUNKS : n_chunks;
             const int64_t end = (c1 * FE_CHUNK < L.len) ? c1 * FE_CHUNK : L.len;
             const int scnt = spec_meta[seg0 + s].x;
+            const int *strig = (spec_meta[seg0 + s].w ? spec_trig2 : spec_trig) + (seg0 + s) * SEG_CAP;
             int64_t pos = t_prev + SS_MIN_GAP + 1;
             while (pos < end) {
                 int64_t m = next_candidate(fw, summary, L.chunk_base, c1, pos, lane, min_plateau);
@@ -347,11 +400,11 @@ __global__ void __launch_bounds__(128) k_select(const uint32_t *__restrict__ fla
                 // merged with the speculative chain?  then the rest of it is true as well
                 int at = -1;
                 for (int j = 0; j < scnt; ++j)
-                    if (spec_trig[(seg0 + s) * SEG_CAP + j] == (int)m) at = j;
+                    if (strig[j] == (int)m) at = j;
                 if (at >= 0) {
-                    for (int j = at + lane; j < scnt; j += 32) tmp[k + j - at] = spec_trig[(seg0 + s) * SEG_CAP + j];
+                    for (int j = at + lane; j < scnt; j += 32) tmp[k + j - at] = strig[j];
                     k += scnt - at;
-                    t_prev = spec_trig[(seg0 + s) * SEG_CAP + scnt - 1];
+                    t_prev = strig[scnt - 1];
                     break;
                 }
                 if (lane == 0) tmp[k] = (int)m;

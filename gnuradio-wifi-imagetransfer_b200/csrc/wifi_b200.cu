@@ -171,6 +171,8 @@ struct wifi_b200 {
     int *d_trig_tmp = nullptr;        // k_select scratch: trigger list per link
     int *d_spec_trig = nullptr;       // speculative triggers per 8192-sample segment
     int4 *d_spec_cnt = nullptr;       // per segment (count, first, last, -)
+    int *d_spec_trig2 = nullptr;      // second speculative pass (k_select_fix): chains walked again behind the previous segment's last trigger
+    int4 *d_spec_cnt2 = nullptr;      // per segment (count, first, last, which trigger array)
     int *d_pack_list = nullptr;       // frames whose trellis words k_pack must build
     int *d_link_dirty = nullptr;      // links that need the sequential decode_mac replay
     int64_t tile_cap = 0;
@@ -276,7 +278,7 @@ void free_all(wifi_b200 *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int k = 0; k < A_SLOTS; ++k) if (h->a_ev[k]) cudaEventDestroy(h->a_ev[k]);
     void *ptrs[] = {h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
-                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
+                    h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_spec_trig2, h->d_spec_cnt2, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_frames) cudaFreeHost(h->h_frames);
@@ -483,7 +485,11 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
         if (tiles_g > 0)
             k_select_spec<<<(unsigned)((tiles_g * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, tile_base, tile_base + tiles_g,
                                                                                 h->cfg.min_plateau, h->d_spec_trig, h->d_spec_cnt);
-        k_select<<<(ng * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, h->cfg.min_plateau, h->d_trig_tmp, h->d_spec_trig, h->d_spec_cnt);
+        if (tiles_g > 0)
+            k_select_fix<<<(unsigned)((tiles_g * 32 + 127) / 128), 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, tile_base, tile_base + tiles_g,
+                                                                               h->cfg.min_plateau, h->d_spec_trig, h->d_spec_cnt, h->d_spec_trig2, h->d_spec_cnt2);
+        k_select<<<(ng * 32 + 127) / 128, 128, 0, s>>>(h->d_flags, h->d_summary, gl, ng, h->cfg.min_plateau, h->d_trig_tmp, h->d_spec_trig, h->d_spec_cnt2,
+                                                       h->d_spec_trig2);
         k_reserve<<<1, 1024, 0, s>>>(gl, ng, h->d_counters, (unsigned long long *)(h->d_counters + 8), h->cfg.max_frames, h->d_counters + 2,
                                      (long long)frame_base, (long long)row_base);
         k_frames_init<<<dim3(8, ng), 128, 0, s>>>(gl, h->d_trig_tmp, h->d_frames, lb);
@@ -695,7 +701,7 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     if (cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM) != cudaSuccess) return fail(WIFI_E_CUDA);
     {
         // CUDA loads a kernel on its first launch (milliseconds): do it here, not inside the first live run
-        const void *kernels[] = {(const void *)k_detect, (const void *)k_select_spec, (const void *)k_select, (const void *)k_reserve,
+        const void *kernels[] = {(const void *)k_detect, (const void *)k_select_spec, (const void *)k_select_fix, (const void *)k_select, (const void *)k_reserve,
                                  (const void *)k_frames_init, (const void *)k_sync_long, (const void *)k_signal, (const void *)k_plan_fast,
                                  (const void *)k_plan, (const void *)k_pack, (const void *)k_viterbi, (const void *)k_viterbi_warp,
                                  (const void *)k_move_segments, (const void *)k_sc16_to_fc32, (const void *)k_tx, (const void *)k_channel,
@@ -717,6 +723,8 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     A((void **)&h->d_trig_tmp, (size_t)h->tile_cap * (DET_THREADS / 4) * sizeof(int));
     A((void **)&h->d_spec_trig, (size_t)h->tile_cap * SEG_CAP * sizeof(int));
     A((void **)&h->d_spec_cnt, (size_t)h->tile_cap * sizeof(int4));
+    A((void **)&h->d_spec_trig2, (size_t)h->tile_cap * SEG_CAP * sizeof(int));
+    A((void **)&h->d_spec_cnt2, (size_t)h->tile_cap * sizeof(int4));
     A((void **)&h->d_pack_list, (size_t)2 * Fm * sizeof(int));
     A((void **)&h->d_link_dirty, (size_t)2 * MAX_LINKS * sizeof(int));   // [0, MAX_LINKS): dirty flags, [MAX_LINKS, 2 MAX_LINKS): open decode_mac state
     A((void **)&h->d_links, (size_t)MAX_LINKS * sizeof(LinkDesc));
