@@ -188,7 +188,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
             barrier()
             decode_ms[0] = 0.0
             t0 = time.perf_counter()
-        own, owned_all, rounds = S.reconcile(decode, segs, rank, n_total, device=dev if world > 1 else None, max_rounds=world + 2)
+        own, _tails, rounds = S.reconcile(decode, segs, rank, n_total, device=dev if world > 1 else None, max_rounds=world + 2, tail_rows=512)
     barrier()
     t_sh = (time.perf_counter() - t0) / reps
     dec_sh = decode_ms[0] / reps
@@ -202,6 +202,8 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
         whole = h.frames()
     t_one = (time.perf_counter() - t0) / reps
     one_stage = {k: round(v, 3) for k, v in h.stage_times().items() if v}
+    # outside the timed region: every rank's owned records travel to rank 0, which compares their union with its own decode
+    owned_all = S.gather_owned(own, dev if world > 1 else None)
     equal = None
     if rank == 0:
         equal = S.same(np.concatenate(owned_all), S.records(whole, 0))
@@ -221,8 +223,8 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
             "single_gpu_ms": 1e3 * t_one, "single_gpu_stage_ms": one_stage, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
             "value_msamples_per_s": n_total / t_sh / 1e6, "frames_owned_total": int(cnt[0]), "crc_ok_total": int(cnt[1]),
             "re_decode_rounds": rounds, "union_equals_single_gpu_table": equal, "problems": problems or None, "scaling": "strong",
-            "collective": "NCCL all_gather of the frame tables (96 bytes per frame) + counter all_reduce" if world > 1 else "none (one rank)",
-            "timing": "wall clock around sharding.reconcile (decode, record all-gather, join check), barrier + synchronize on both sides, max over ranks, mean of %d" % reps}
+            "collective": "per round two NCCL all_gathers: the last 512 owned frame records of every rank (96 bytes each), then the ranks' verdicts; + one counter all_reduce" if world > 1 else "none (one rank)",
+            "timing": "wall clock around sharding.reconcile (decode, record all-gather, join check), barrier + synchronize on both sides, max over ranks, mean of %d; the union check against rank 0's whole-capture decode runs outside it" % reps}
 
 
 class ClockSampler:

@@ -224,15 +224,21 @@ def _owned(rec, seg):
     return rec[a:b]
 
 
-def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gather=None):
+def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gather=None, tail_rows=None):
     """Time-sharded receive with an exact result.  `decode(lo, end, state, final)` runs this rank's receiver over
     samples [lo, end) of the capture -- state None: a stream start at lo; else the wifi_b200_link_state fields, with
     state["hist"] samples of history in front of lo (the callee reads them from lo - hist) -- and returns its frame
     table (triggers relative to lo).
     Every rank decodes its segment; the records are all-gathered; every rank walks the same check from rank 0 upwards;
     the lowest rank that has not joined the sequential state decodes again from a known one; repeated until all have.
-    Returns (records this rank owns, every rank's owned records, number of re-decoding rounds)."""
+    Returns (records this rank owns, every rank's owned records, number of re-decoding rounds).
+
+    tail_rows = K: the ranks exchange only the last K records they own (a few tens of kB instead of the whole tables) and
+    every rank checks ITSELF against the tails of the ranks below it, then the verdicts are gathered; what comes back as
+    "every rank's owned records" are those tails.  Ordinary traffic joins within a frame or two, so K = 512 decides every
+    check; a look-back with more than K irregular frames falls back to decoding from the start of the capture."""
     seg = segs[rank]
+    do_gather = gather or gather_records
 
     def decode_closed(lo, st):
         """Decode [lo, end); while a frame this rank owns leaves decode_mac open at the end of the segment (a tag pending,
@@ -248,8 +254,30 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
     lo, carry = seg["start"], _f32_bits(0.0)
     local = decode_closed(lo, None)
     rounds = 0
+    while tail_rows is not None:
+        own = _owned(local, seg)
+        tails = do_gather(_header(lo, carry), own[-tail_rows:], device)
+        truth = np.concatenate([t for _, t in tails[:rank]]) if rank else np.zeros((0, REC_FIELDS), np.int32)
+        truth = truth[truth[:, TRIG] < seg["core_start"]]
+        ok = lo == 0 or boundary_check(truth, local, carry, lo, seg["core_start"])     # a decode from sample 0 IS the sequential receiver
+        verdicts = do_gather(_header(int(ok), 0), np.zeros((0, REC_FIELDS), np.int32), device)
+        bad = next((r for r, (h, _) in enumerate(verdicts) if int(h[BURST]) == 0), None)
+        if bad is None:                      # rank 0 is right; rank r agreed with the tails of ranks it just saw agree: all are
+            return own, [t for _, t in tails], rounds
+        rounds += 1
+        if max_rounds is not None and rounds > max_rounds:
+            raise RuntimeError("time sharding did not reconcile in %d rounds" % max_rounds)
+        if bad == rank:
+            rp = resume_point(truth, seg["start"], seg["core_start"])
+            if rp is None:                   # no closed state among the records at hand: only the start of the capture is known
+                lo, carry = 0, _f32_bits(0.0)
+                local = decode_closed(0, None)
+            else:
+                lo, st, front = rp
+                carry = _f32_bits(st["fo_carry"])
+                local = np.concatenate([front, decode_closed(lo, st)])
     while True:
-        allrec = (gather or gather_records)(_header(lo, carry), local, device)
+        allrec = do_gather(_header(lo, carry), local, device)
         owned_all, bad = [], None
 
         def truth_before(core_start, rows):
@@ -265,7 +293,7 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
 
         for r, sr in enumerate(segs):
             hdr, rec = allrec[r]
-            if r > 0:
+            if r > 0 and int(hdr[BURST]) != 0:           # (a decode that started at sample 0 is the sequential receiver)
                 n_front = int(np.searchsorted(rec[:, TRIG], sr["core_start"]))
                 if not boundary_check(truth_before(sr["core_start"], n_front + 64), rec, int(hdr[FREQ]), int(hdr[BURST]), sr["core_start"]):
                     bad = r
@@ -287,7 +315,7 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
                 local = np.concatenate([front, decode_closed(lo, st)])
 
 
-def simulate_ranks(decode, segs, n_samples):
+def simulate_ranks(decode, segs, n_samples, tail_rows=None):
     """All ranks of `reconcile` in one process (threads and a barrier where the all-gather is): what the single-GPU
     tests use.  Returns (every rank's owned records, rounds)."""
     import threading
@@ -302,7 +330,7 @@ def simulate_ranks(decode, segs, n_samples):
             bar.wait()
             return res
         try:
-            out[rank] = reconcile(decode, segs, rank, n_samples, gather=gather, max_rounds=world + 1)
+            out[rank] = reconcile(decode, segs, rank, n_samples, gather=gather, max_rounds=world + 1, tail_rows=tail_rows)
         except Exception as e:        # a failing rank must not leave the others at the barrier
             errs.append(e)
             bar.abort()
@@ -314,4 +342,11 @@ def simulate_ranks(decode, segs, n_samples):
         t.join()
     if errs:
         raise errs[0]
+    if tail_rows is not None:            # every rank's own records (the exchanged tails are only what the checks needed)
+        return [o[0] for o in out], out[0][2]
     return out[0][1], out[0][2]
+
+
+def gather_owned(own, device=None):
+    """Every rank's owned records (for a check of the union against a sequential decode; not part of the receive path)."""
+    return [t for _, t in gather_records(_header(0, 0), own, device)]

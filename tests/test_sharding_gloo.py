@@ -93,6 +93,10 @@ def test_reconcile_cascades_over_many_ranks():
         for world in (3, 5):
             owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=1), S.shard_stream(y.size, world), y.size)
             assert S.same(np.concatenate(owned), truth) and rounds >= 1, (trunc, world, rounds)
+            # the same with only the last 64 owned records of every rank exchanged (fewer than the zone's 230 frames:
+            # a rank whose look-back shows no closed state decodes from the start of the capture)
+            owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=1), S.shard_stream(y.size, world), y.size, tail_rows=64)
+            assert S.same(np.concatenate(owned), truth) and rounds >= 1, (trunc, world, rounds, "tails")
     y, _ = make_capture(O, np.random.default_rng(8), [(4, 600)] * 30, snr_db=28, seed=3, gap=1100, cfo=0.004)
     owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=0), S.shard_stream(y.size, 4), y.size)
     assert S.same(np.concatenate(owned), S.records(O.rx(y, algo=0, want_carrier=False).frames, 0)) and rounds == 0
@@ -122,6 +126,8 @@ def test_reconcile_fuzz_random_traffic():
         for world in (2, 3, 6):
             owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=algo), S.shard_stream(y.size, world), y.size)
             assert S.same(np.concatenate(owned), truth), (seed, world, rounds)
+            owned, rounds = S.simulate_ranks(oracle_segment_decoder(O, y, algo=algo), S.shard_stream(y.size, world), y.size, tail_rows=16)
+            assert S.same(np.concatenate(owned), truth), (seed, world, rounds, "tails")
 
 
 def test_resumed_stream_state_reproduces_the_sequential_receiver():
