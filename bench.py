@@ -569,8 +569,9 @@ def main():
                         n_ += len(meta)
 
                 # untimed warm-up: the arena, the staging buffers and the pinned result mirrors are allocated on first use
-                for fl in (False, True):
-                    hl.rx_push_links_async(blobs[0], off, flush=fl)
+                for k in range(3):                     # three pending pushes: every staging slot is allocated here, not in the timed loop
+                    hl.rx_push_links_async(blobs[k], off, flush=(k == 2))
+                for k in range(3):
                     hl.rx_push_wait()
                     drain()
                 hl.rx_reset()
