@@ -228,7 +228,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp"
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -238,7 +238,10 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """t_begin / t_end (time.time()): keep the samples taken inside the timed region (nvidia-smi needs a few hundred
+        milliseconds to start, so the sampler is launched well before it); all samples if none fall inside."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.p:
             return out
@@ -249,22 +252,29 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 7:
                 continue
             try:
-                sm.append(float(c[0]))
-                mx.append(float(c[1]))
+                row = (float(c[0]), float(c[1]), {nm for k, nm in enumerate(names) if c[3 + k].lower().startswith("active")})
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if c[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            ts = None
+            if len(c) >= 8:
+                try:
+                    ts = datetime.datetime.strptime(c[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    ts = None
+            rows.append((ts,) + row)
+        inside = [r for r in rows if r[0] is not None and t_begin is not None and t_begin - 0.02 <= r[0] <= t_end + 0.02]
+        use = inside or rows
+        if use:
+            reasons = set().union(*[r[3] for r in use])
+            out = {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)), "reasons": sorted(reasons),
+                   "samples": len(use), "samples_inside_timed_region": len(inside)}
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -395,6 +405,7 @@ def main():
     n_samples = n_links * (LEAD + fpl * (flen + GAP))
     h = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=n_samples + 1024, max_frames=n + n_links + 1024,
                  soft_decision=args.soft)
+    sampler = ClockSampler(local) if rank == 0 else None           # started early: nvidia-smi takes a while to produce its first line
     cap, link_off, psdus = build_capture(h, W, torch, n_links, fpl, seed=1000 + rank)
     torch.cuda.synchronize()
 
@@ -406,13 +417,13 @@ def main():
     def step():
         h.rx_batch_dev(cap.data_ptr(), link_off, final=True, fetch=False)
 
-    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
     stage_acc = {}
     barrier()
     t0 = time.perf_counter()
+    wall0 = time.time()
     for _ in range(args.steps):
         step()                      # synchronises its own stream before returning
         for k, v in h.stage_times().items():
@@ -423,7 +434,7 @@ def main():
     # their sum, the host wall clock adds launch/sync gaps -- report the larger (honest) one
     dev_ms = sum(stage_acc.values())
     elapsed = max(wall, dev_ms / 1e3)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall0, time.time()) if sampler else None
     res = h.results()
     st_frames = len(res.frames)
     st_ok = int(res.frames["crc_ok"].sum())
