@@ -126,40 +126,26 @@ WDM_FN void wdm_sincosf(float x, float *s, float *c)
     *c = co;
 }
 
-/* atan of a non-negative argument, result in [0, pi/2] */
-WDM_FN float wdm_atan_pos(float x)
+/* atan2(y, x) in (-pi, pi].  atan2(0,0) = 0.  NaN inputs give NaN.
+ * One division and no branches: with mn = min(|x|,|y|), mx = max(|x|,|y|) the angle of (mx, mn) lies in [0, pi/4];
+ * above tan(pi/8) it is pi/4 + atan((mn - mx)/(mn + mx)), so the argument of the polynomial is formed as a quotient of
+ * sums BEFORE the division (the classic form divides twice: mn/mx, then (q - 1)/(q + 1)); |t| <= tan(pi/8). */
+WDM_FN float wdm_atan2f(float y, float x)
 {
-    float y0, t;
-    if (x > 2.414213562373095f) {        /* tan(3pi/8) */
-        y0 = 1.5707963267948966f;
-        t = -1.0f / x;
-    } else if (x > 0.4142135623730950f) { /* tan(pi/8) */
-        y0 = 0.7853981633974483f;
-        t = (x - 1.0f) / (x + 1.0f);
-    } else {
-        y0 = 0.0f;
-        t = x;
-    }
-    float z = t * t;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const int hi = mn > 0.4142135623730950f * mx;
+    const float num = hi ? mn - mx : mn;
+    const float den = hi ? mn + mx : mx;
+    float t = num / den;
+    if (mx == 0.0f) t = 0.0f;                               /* atan2(0, 0) = 0 */
+    const float z = t * t;
     float p = fmaf(z, 8.05374449538e-2f, -1.38776856032e-1f);
     p = fmaf(p, z, 1.99777106478e-1f);
     p = fmaf(p, z, -3.33329491539e-1f);
-    float y = fmaf(p * z, t, t);
-    return y0 + y;
-}
-
-/* atan2(y, x) in (-pi, pi].  atan2(0,0) = 0.  NaN inputs give NaN. */
-WDM_FN float wdm_atan2f(float y, float x)
-{
-    float ax = fabsf(x), ay = fabsf(y);
-    float r;
-    if (ax == 0.0f && ay == 0.0f) {
-        r = 0.0f;
-    } else if (ax >= ay) {
-        r = wdm_atan_pos(ay / ax);              /* [0, pi/4] */
-    } else {
-        r = 1.5707963267948966f - wdm_atan_pos(ax / ay);
-    }
+    float r = fmaf(p * z, t, t);
+    if (hi) r = 0.7853981633974483f + r;
+    if (ay > ax) r = 1.5707963267948966f - r;
     if (x < 0.0f) r = 3.14159265358979f - r;
     if (y < 0.0f) r = -r;
     if (x != x || y != y) r = x + y;
