@@ -669,8 +669,7 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
     const int n_syms = emitted_symbols(avail, fs, last);
     const float fshort = F.freq_short;
     const float delta = fo - fshort;
-    const cf w1 = crot(delta), w80 = crot(delta * 80.0f);
-    cf r0 = {1.f, 0.f};
+    const cf w1 = crot(delta);
     const int64_t t = F.trigger;
     const int hist = L.hist;
 
@@ -767,9 +766,7 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
             if (n + 1 < n_end) fetch_raw(n + 1, raw);
             // one rotation by delta = freq_long - freq_short: the even sample by exp(j delta j0), the odd one behind
             // it by that times exp(j delta) (oracle: sync_long COPY)
-            // (from the fourth symbol on the even sample's rotation is the previous symbol's advanced by 80 samples)
-            if (PHASE == 0 || n == 3) r0 = crot(delta * (float)j0);
-            else r0 = cmul(r0, w80);
+            const cf r0 = crot(delta * (float)j0);
             const cf r1 = cmul(r0, w1);
             a = (j0 < avail) ? cmul(s0, r0) : cf{0.f, 0.f};
             b = (j0 + 1 < avail) ? cmul(s1, r1) : cf{0.f, 0.f};
@@ -777,15 +774,10 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
         warp_fft64(a, b, lane, tw);
         // a = cur[iA], b = cur[iB] (fftshift)
         {
-            // sampling-offset ramp: bin iA from its angle, bin iB = iA - 32 as that turned back by 32 theta, the square
-            // of lane 16's factor (oracle: frame_equalizer ramp)
             double k = 2 * M_PI * n * 80 * (eps0 + d_er);
-            double phA = k * (iA - 32) / 64;
-            const cf rA = crot((float)phA);
-            const cf r16 = cshfl(rA, 16);
-            const cf rB = wdm_cmulc(rA, cmul(r16, r16));
-            a = cmul(a, rA);
-            b = cmul(b, rB);
+            double phA = k * (iA - 32) / 64, phB = k * (iB - 32) / 64;
+            a = cmul(a, crot((float)phA));
+            b = cmul(b, crot((float)phB));
         }
         cf c11 = cshfl(b, 11), c25 = cshfl(b, 25), c39 = cshfl(a, 7), c53 = cshfl(a, 21);
         const float p = (n >= 2) ? c_tab.polarity[pidx] : 1.f;        // pidx = (n - 2) mod 127, kept as a counter

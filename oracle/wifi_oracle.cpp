@@ -28,12 +28,12 @@
  *  (6) Complex products are the fused sequences of wifi_detmath.h (VOLK's rounding
  *      depends on the SIMD kernel it dispatches to); the running sums of the
  *      front-end are fused multiply-add chains; sync_short's and sync_long's two
- *      derotations are applied as one rotation by freq_long - freq_short (from
- *      the fourth symbol on by recurrence over the symbols); the lower half of
- *      the equalizer's sampling-offset ramp is derived from the upper half.  Each
- *      differs from the literal upstream float sequence by a few 1e-7 relative (a
- *      few 1e-6 at the end of the longest frame), against a 2e-3 tolerance on
- *      equalised points.
+ *      derotations are applied as one rotation by freq_long - freq_short.  Each
+ *      differs from the literal upstream float sequence by a few 1e-7 relative,
+ *      against a 2e-3 tolerance on equalised points.  (Tried and
+ *      dropped: the rotation by recurrence over the symbols and the lower half of
+ *      the sampling-offset ramp derived from the upper half -- 7 % fewer
+ *      instructions in k_demod, no time gained, so the literal forms stay.)
  */
 #include "wifi_oracle.h"
 #include "../include/wifi_detmath.h"
@@ -893,23 +893,15 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
             int R = avail - F.frame_start;
             int E = R <= 0 ? 0 : (R <= 128 ? R : 128 + 64 * ((R - 128) / 80) + std::max(0, ((R - 128) % 80) - 16));
             sy.resize((size_t)E);
-            /* the even sample's rotation: computed from its position for the symbols 0..3 (LTS1, LTS2, SIGNAL, first data
-             * symbol); from the fourth on it is the rotation of the same sample of the symbol before, advanced by the 80
-             * samples between them -- one complex product instead of a sine and a cosine */
-            const cf w80 = crot(delta * 80.0f);
-            cf rot_even[32];
+            cf rot_even = {1.f, 0.f};
             for (int k = 0; k < E; ++k) {
                 int nn = k / 64, m = k % 64;
                 int j = F.frame_start + (nn < 2 ? 64 * nn + m : 128 + 80 * (nn - 2) + 16 + m);
                 int64_t src = B.t + j - 16;
                 cf xs = src >= -(int64_t)cfg.hist ? x[src] : cf{0.f, 0.f};
                 cf rot;
-                if ((m & 1) == 0) {
-                    rot_even[m >> 1] = nn <= 3 ? crot(delta * (float)j) : cmul(rot_even[m >> 1], w80);
-                    rot = rot_even[m >> 1];
-                } else {
-                    rot = cmul(rot_even[m >> 1], w1);
-                }
+                if ((m & 1) == 0) { rot_even = crot(delta * (float)j); rot = rot_even; }
+                else rot = cmul(rot_even, w1);
                 sy[(size_t)k] = cmul(xs, rot);
             }
         }
@@ -938,17 +930,9 @@ static void rx_link(const cf *x, int64_t n, int link, const orc_rx_cfg &cfg, Res
             std::memcpy(tin, &sy[(size_t)nn * 64], sizeof tin);
             fft64(tin, X, false);
             for (int i = 0; i < 64; ++i) cur[i] = X[(i + 32) & 63];
-            {
-                /* sampling-offset ramp exp(j theta (i - 32)): the upper half from its angles, the lower half as the upper
-                 * one turned back by 32 theta, which is the square of bin 48's factor (exp(j 16 theta)) */
-                cf ramp[64];
-                for (int i = 32; i < 64; ++i) {
-                    double ph = 2 * M_PI * nn * 80 * (eps0 + d_er) * (i - 32) / 64;
-                    ramp[i] = crot((float)ph);
-                }
-                const cf sq = cmul(ramp[48], ramp[48]);
-                for (int i = 0; i < 32; ++i) ramp[i] = wdm_cmulc(ramp[i + 32], sq);
-                for (int i = 0; i < 64; ++i) cur[i] = cmul(cur[i], ramp[i]);
+            for (int i = 0; i < 64; ++i) {
+                double ph = 2 * M_PI * nn * 80 * (eps0 + d_er) * (i - 32) / 64;
+                cur[i] = cmul(cur[i], crot((float)ph));
             }
             float p = (nn >= 2) ? t.polarity[(nn - 2) % 127] : 1.f;
             cf pil[4];
