@@ -692,7 +692,7 @@ def main():
     line = {"metric": "rx_msamples_per_s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u8", "data": "synthetic",
             "decoded_mbps": mbps, "frames_per_step": tot_frames, "crc_ok_per_step": tot_ok,
-            "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 13 * args.steps,   # detect, select_spec, select, reserve, frames_init, sync_long, demod x2, signal, plan_fast, plan, pack, viterbi
+            "config": config_dict(args, n_links, fpl), "clocks": clocks, "e2e": e2e, "gpu_launches": 14 * args.steps,   # detect, select_spec, select_fix, select, reserve, frames_init, sync_long, demod x2, signal, plan_fast, plan, pack, viterbi (profiles/r02_ncu_launches.csv)
             "roofline": roof, "roofline_frontend": roof_det, "roofline_stages": roof_stages, "stage_ms": stage_ms, "tx": dict(TX_INFO), "time_sharded": tsh,
             "path_hbm": {"algorithmic_GBps": path_alg / (step_ms * 1e-3) / 1e9, "frac_of_peak": path_alg / (step_ms * 1e-3) / 1e9 / hbm_peak}}
     if not args.no_cpu and world == 1:
