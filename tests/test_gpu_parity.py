@@ -611,6 +611,34 @@ def test_time_sharding_reconciles_adversarial_traffic(O, W, trunc):
         h.close()
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("WIFI_FUZZ_SEEDS", "3"))))
+def test_fuzz_time_sharding_random_traffic(O, W, seed):
+    """Random traffic (gaps from none to a long silence, frames cut short by the next one) cut across 2..6 ranks on the GPU,
+    whole tables and owned tails only: always the sequential oracle's table."""
+    S = W.sharding
+    rng = np.random.default_rng(900 + seed)
+    parts = [np.zeros(int(rng.integers(0, 400)), np.complex64)]
+    for i in range(int(rng.integers(25, 60))):
+        f = O.tx_frame(make_psdu(O, rng, int(rng.integers(30, 500)), seq=i), int(rng.integers(0, 8)), seed=1 + i % 127)
+        if rng.random() < 0.2:
+            f = f[:int(rng.integers(350, f.size))]
+        parts += [f, np.zeros(int(rng.choice([0, 0, 40, 300, 900, 2500, 60000 if i % 17 == 5 else 700])), np.complex64)]
+    x = np.concatenate(parts).astype(np.complex64)
+    y = O.channel(x, gain=0.6, cfo=float(rng.uniform(-0.01, 0.01)), noise_sigma=0.6 * 10 ** (-float(rng.uniform(14, 30)) / 20), seed=seed)
+    algo = int(rng.integers(0, 4))
+    truth = S.records(O.rx(y, algo=algo, want_carrier=False).frames, 0)
+    h = W.Handle(max_samples=y.size + 1024, max_frames=2048, chan_est=algo)
+    try:
+        dec = gpu_segment_decoder(h, y)
+        for world in (2, 3, 6):
+            owned, rounds = S.simulate_ranks(dec, S.shard_stream(y.size, world), y.size)
+            assert S.same(np.concatenate(owned), truth), (seed, world, rounds)
+            owned, rounds = S.simulate_ranks(dec, S.shard_stream(y.size, world), y.size, tail_rows=16)
+            assert S.same(np.concatenate(owned), truth), (seed, world, rounds, "tails")
+    finally:
+        h.close()
+
+
 def test_resumed_stream_state_entry_point_matches_oracle(O, W):
     """wifi_b200_rx_batch_dev_state against the oracle given the same (min_pos, fo_carry, hist), every field and PSDU."""
     S = W.sharding
