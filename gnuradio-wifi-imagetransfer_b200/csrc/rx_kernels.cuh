@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
     const int f = f0 + blockIdx.x * 4 + wib;
     if (f >= n_frames) return;
     const wifi_b200_frame F = frames[f];
-    if (F.burst_len < SYNC_LENGTH + 63) return;
+    if (phase == 1 && F.burst_len < SYNC_LENGTH + 63) return;
     const LinkDesc L = links[F.link];
     const cf *x = iq + L.x_off;
     const bool last = L.is_final && (f == L.frame_first + L.frame_count - 1);
@@ -662,6 +662,10 @@ __global__ void __launch_bounds__(128, DEMOD_MINB) k_demod(const cf *__restrict_
             fo = L.fo_carry;
             for (int g = f - 1; g >= L.frame_first; --g)
                 if (frames[g].found) { fo = frames[g].freq_long; break; }
+        }
+        if (F.burst_len < SYNC_LENGTH + 63) {          // SYNC never completes (end of stream): the record carries the offset in force
+            if (lane == 0 && F.n_syms >= 0) frames[f].freq_long = fo;
+            return;
         }
     }
     const int avail = F.burst_len - SYNC_LENGTH;

@@ -125,6 +125,21 @@ def test_rx_truncated_and_back_to_back(H, O, W):
         assert_frames_equal(H.rx_batch(y, final=final), O.rx(y, algo=3, final=final))
 
 
+def test_short_final_burst_carries_the_frequency_offset(H, O, W):
+    """A capture that ends less than 320 + 63 samples behind its last trigger: sync_long never completes for that burst,
+    and its record carries the frequency offset of the last burst that matched (found by the time-sharding fuzz)."""
+    rng = np.random.default_rng(77)
+    y, _ = make_capture(O, rng, [(3, 120), (5, 200), (2, 90)], snr_db=28, cfo=0.006, gap=400, seed=9)
+    ref_all = O.rx(y, algo=0)
+    t_last = int(ref_all.frames["trigger"][-1])
+    H.set_param(W.wifi_b200.P_CHAN_EST, 0)
+    for cut in (t_last + 60, t_last + 300, t_last + 382, t_last + 383):
+        ref = O.rx(y[:cut], algo=0)
+        assert ref.frames["burst_len"][-1] == cut - t_last and ref.frames["freq_long"][-2] != 0
+        assert_frames_equal(H.rx_batch(y[:cut]), ref)
+        assert_frames_equal(H.rx_batch(y[:cut], final=False), O.rx(y[:cut], algo=0, final=False))
+
+
 def test_rx_multi_link(H, O, W):
     rng = np.random.default_rng(21)
     links, offs = [], [0]
