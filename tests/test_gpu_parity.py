@@ -770,13 +770,21 @@ def test_fuzz_random_captures(O, W, seed):
         x = np.concatenate(parts).astype(np.complex64)
         taps = ((0, 1.0),) if rng.random() < 0.5 else ((0, 1.0), (1, 0.4 * np.exp(1j * rng.uniform(0, 6.28))), (3, 0.2 * np.exp(1j * rng.uniform(0, 6.28))))
         snr = float(rng.uniform(4, 34))
-        links.append(O.channel(x, gain=0.6, cfo=float(rng.uniform(-0.02, 0.02)), noise_sigma=0.6 * 10 ** (-snr / 20), taps=taps, seed=100 * seed + l))
+        yl = O.channel(x, gain=0.6, cfo=float(rng.uniform(-0.02, 0.02)), noise_sigma=0.6 * 10 ** (-snr / 20), taps=taps, seed=100 * seed + l)
+        u = rng.random()
+        if u < 0.3:
+            yl = yl[:int(rng.integers(1, yl.size))]             # the capture ends anywhere: mid-frame, mid-preamble, short final bursts
+        elif u < 0.4:
+            yl = yl[:int(rng.integers(0, 100))]                 # a (nearly) empty link
+        links.append(yl)
         offs.append(offs[-1] + links[-1].size)
     y = np.concatenate(links)
+    final = bool(rng.random() < 0.8)
     h = W.Handle(max_samples=y.size + 1024, max_frames=256, want_carrier=True, chan_est=algo, soft_decision=soft)
+    h.set_param(W.wifi_b200.P_HOST_GROUP_SAMPLES, int(rng.choice([0, 1, 5000])))
     try:
-        res = h.rx_batch(y, np.array(offs, np.uint64))
-        ref = O.rx_links(y, np.array(offs[:-1], np.int64), np.diff(offs).astype(np.int64), algo=algo, soft=soft)
+        res = h.rx_batch(y, np.array(offs, np.uint64), final=final) if y.size else h.rx_batch(np.zeros(0, np.complex64))
+        ref = O.rx_links(y, np.array(offs[:-1], np.int64), np.diff(offs).astype(np.int64), algo=algo, soft=soft, final=final)
         assert_frames_equal(res, ref)
         rows, car = h.rows(carrier=True)
         for i in range(len(ref.frames)):
