@@ -607,6 +607,8 @@ def main():
                                     "unit": "Msamples/s", "links": s_links,
                                     "samples_per_push_per_link": chunk, "pushes": pushes, "pdus": n_pdu,
                                     "realtime_factor_per_20Msps_link": chunk * pushes / t_lib / 20e6,
+                                    # pipeline full (the first push waits for its own copy, the last one also flushes): pushes 2 .. n-1
+                                    "steady_state_realtime_factor": (chunk / 20e6) / (1e-3 * float(np.mean(push_ms[1:-1]))) if len(push_ms) > 2 else None,
                                     "how": "wifi_b200_rx_push_links_async(k+2), rx_push_wait(k), rx_pop per chunk; pre-filled pinned host buffers, one handle; wall time of the whole loop, per-rank figure"}
                 hl.close()
                 del pins
