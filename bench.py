@@ -559,59 +559,77 @@ def main():
             chunk, pushes, s_links = 262144, 6, 100
             link_len = int(link_off[1] - link_off[0])
             if link_len >= chunk * pushes:
-                hl = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=s_links * (chunk + 131072) + 1024,
-                              max_frames=s_links * (chunk // 4096 + 16), soft_decision=args.soft)
-                # every chunk gets its own page-locked buffer, filled BEFORE the timed region (that is the radios' job): the
-                # timed loop is library calls only, back to back, so no copy hides behind untimed host work
-                pins = [torch.empty(2 * s_links * chunk, dtype=torch.float32, pin_memory=True) for _ in range(pushes)]
-                blobs = [p_.numpy().view(np.complex64) for p_ in pins]
                 off = (np.arange(s_links + 1) * chunk).astype(np.uint64)
                 hv = hn.reshape(n_links, link_len)
                 src = np.arange(s_links) % n_links
-                for k in range(pushes):
-                    blobs[k].reshape(s_links, chunk)[:] = hv[src, k * chunk:(k + 1) * chunk]
 
-                def drain():
-                    n_ = 0
-                    while True:
-                        meta, _pd = hl.rx_pop_arrays(cap=8192, copy=False)
-                        if not len(meta):
-                            return n_
-                        n_ += len(meta)
+                def live(wire):
+                    """One handle, `pushes` chunks of every stream; wire = int16 I/Q (the radios' format) instead of complex64."""
+                    hl = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=s_links * (chunk + 131072) + 1024,
+                                  max_frames=s_links * (chunk // 4096 + 16), soft_decision=args.soft)
+                    # every chunk gets its own page-locked buffer, filled BEFORE the timed region (that is the radios' job): the
+                    # timed loop is library calls only, back to back, so no copy hides behind untimed host work
+                    if wire:
+                        pins = [torch.empty(2 * s_links * chunk, dtype=torch.int16, pin_memory=True) for _ in range(pushes)]
+                        blobs = [p_.numpy() for p_ in pins]
+                        for k in range(pushes):
+                            x = hv[src, k * chunk:(k + 1) * chunk].view(np.float32)
+                            blobs[k].reshape(s_links, 2 * chunk)[:] = np.clip(np.rint(x * np.float32(1.0 / SC16_SCALE)), -32768, 32767).astype(np.int16)
+                        push = lambda k, fl: hl.rx_push_links_sc16_async(blobs[k], SC16_SCALE, off, flush=fl)
+                    else:
+                        pins = [torch.empty(2 * s_links * chunk, dtype=torch.float32, pin_memory=True) for _ in range(pushes)]
+                        blobs = [p_.numpy().view(np.complex64) for p_ in pins]
+                        for k in range(pushes):
+                            blobs[k].reshape(s_links, chunk)[:] = hv[src, k * chunk:(k + 1) * chunk]
+                        push = lambda k, fl: hl.rx_push_links_async(blobs[k], off, flush=fl)
 
-                # untimed warm-up: the arena, the staging buffers and the pinned result mirrors are allocated on first use
-                for k in range(3):                     # three pending pushes: every staging slot is allocated here, not in the timed loop
-                    hl.rx_push_links_async(blobs[k], off, flush=(k == 2))
-                for k in range(3):
-                    hl.rx_push_wait()
-                    drain()
-                hl.rx_reset()
-                n_pdu, push_ms, wait_ms, stage_last = 0, [], [], {}
-                barrier()
-                t_start = time.perf_counter()
-                hl.rx_push_links_async(blobs[0], off, flush=False)
-                hl.rx_push_links_async(blobs[1], off, flush=False)                   # two copies queued ahead: the copy engine never idles
-                for k in range(1, pushes + 1):
-                    t0 = time.perf_counter()
-                    if k + 1 < pushes:
-                        hl.rx_push_links_async(blobs[k + 1], off, flush=(k + 1 == pushes - 1))
-                    tw = time.perf_counter()
-                    hl.rx_push_wait()
-                    wait_ms.append(round(1e3 * (time.perf_counter() - tw), 2))
-                    if k == pushes - 1:
-                        stage_last = {kk: round(v, 3) for kk, v in hl.stage_times().items() if v}
-                    n_pdu += drain()
-                    push_ms.append(round(1e3 * (time.perf_counter() - t0), 2))
-                t_lib = time.perf_counter() - t_start
-                e2e["streaming"] = {"value": s_links * chunk * pushes / t_lib / 1e6, "push_ms": push_ms, "wait_ms": wait_ms, "stage_ms_of_one_push": stage_last,
-                                    "unit": "Msamples/s", "links": s_links,
-                                    "samples_per_push_per_link": chunk, "pushes": pushes, "pdus": n_pdu,
-                                    "realtime_factor_per_20Msps_link": chunk * pushes / t_lib / 20e6,
-                                    # pipeline full (the first push waits for its own copy, the last one also flushes): pushes 2 .. n-1
-                                    "steady_state_realtime_factor": (chunk / 20e6) / (1e-3 * float(np.mean(push_ms[1:-1]))) if len(push_ms) > 2 else None,
-                                    "how": "wifi_b200_rx_push_links_async(k+2), rx_push_wait(k), rx_pop per chunk; pre-filled pinned host buffers, one handle; wall time of the whole loop, per-rank figure"}
-                hl.close()
-                del pins
+                    def drain():
+                        n_ = 0
+                        while True:
+                            meta, _pd = hl.rx_pop_arrays(cap=8192, copy=False)
+                            if not len(meta):
+                                return n_
+                            n_ += len(meta)
+
+                    # untimed warm-up: the arena, the staging buffers and the pinned result mirrors are allocated on first use
+                    for k in range(3):                     # three pending pushes: every staging slot is allocated here, not in the timed loop
+                        push(k, k == 2)
+                    for k in range(3):
+                        hl.rx_push_wait()
+                        drain()
+                    hl.rx_reset()
+                    n_pdu, push_ms, wait_ms, stage_last = 0, [], [], {}
+                    barrier()
+                    t_start = time.perf_counter()
+                    push(0, False)
+                    push(1, False)                         # two copies queued ahead: the copy engine never idles
+                    for k in range(1, pushes + 1):
+                        t0 = time.perf_counter()
+                        if k + 1 < pushes:
+                            push(k + 1, k + 1 == pushes - 1)
+                        tw = time.perf_counter()
+                        hl.rx_push_wait()
+                        wait_ms.append(round(1e3 * (time.perf_counter() - tw), 2))
+                        if k == pushes - 1:
+                            stage_last = {kk: round(v, 3) for kk, v in hl.stage_times().items() if v}
+                        n_pdu += drain()
+                        push_ms.append(round(1e3 * (time.perf_counter() - t0), 2))
+                    t_lib = time.perf_counter() - t_start
+                    hl.close()
+                    del pins
+                    return {"value": s_links * chunk * pushes / t_lib / 1e6, "push_ms": push_ms, "wait_ms": wait_ms, "stage_ms_of_one_push": stage_last,
+                            "unit": "Msamples/s", "links": s_links, "format": "sc16" if wire else "fc32", "h2d_bytes_per_push": int(s_links * chunk * (4 if wire else 8)),
+                            "samples_per_push_per_link": chunk, "pushes": pushes, "pdus": n_pdu,
+                            "realtime_factor_per_20Msps_link": chunk * pushes / t_lib / 20e6,
+                            # pipeline full (the first push waits for its own copy, the last one also flushes): pushes 2 .. n-1
+                            "steady_state_realtime_factor": (chunk / 20e6) / (1e-3 * float(np.mean(push_ms[1:-1]))) if len(push_ms) > 2 else None,
+                            "how": "wifi_b200_rx_push_links%s_async(k+2), rx_push_wait(k), rx_pop per chunk; pre-filled pinned host buffers, one handle; wall time of the whole loop, per-rank figure" % ("_sc16" if wire else "")}
+
+                e2e["streaming"] = live(False)
+                try:
+                    e2e["streaming_sc16"] = live(True)
+                except Exception as ex:
+                    e2e["streaming_sc16"] = {"error": repr(ex)}
         except Exception as ex:
             e2e["streaming"] = {"error": repr(ex)}
         h.host_free(hn)

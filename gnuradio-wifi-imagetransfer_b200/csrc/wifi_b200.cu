@@ -232,7 +232,7 @@ struct wifi_b200 {
     std::vector<wifi_b200_frame> s_meta;
     std::vector<uint8_t> s_bytes;
     // asynchronous pushes (wifi_b200_rx_push_links_async): up to A_SLOTS in flight, each with its device staging buffer
-    struct AsyncPush { int slot = 0; int flush = 0; std::vector<uint64_t> off; };
+    struct AsyncPush { int slot = 0; int flush = 0; float sc16_scale = 0.f; std::vector<uint64_t> off; };   // sc16_scale != 0: the slot holds int16 I/Q
     std::vector<AsyncPush> a_pending;
     cf *d_stage[A_SLOTS] = {};
     size_t a_cap[A_SLOTS] = {};
@@ -340,6 +340,18 @@ __global__ void __launch_bounds__(256) k_move_segments(const cf *__restrict__ sr
 {
     const wifi_b200::MoveSeg m = segs[blockIdx.y];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.n; i += (int64_t)gridDim.x * blockDim.x) dst[m.dst + i] = src[m.src + i];
+}
+
+// the same append for a staging buffer in the wire format: x = (float)i16 * scale as k_sc16_to_fc32, converted on the way
+// into the arena (one 4-byte load and one 8-byte store per sample, no intermediate fc32 copy)
+__global__ void __launch_bounds__(256) k_append_sc16(const int16_t *__restrict__ src, cf *__restrict__ dst, const wifi_b200::MoveSeg *__restrict__ segs, float scale)
+{
+    const wifi_b200::MoveSeg m = segs[blockIdx.y];
+    const int *in = reinterpret_cast<const int *>(src) + m.src;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = in[i];
+        dst[m.dst + i] = cf{(float)(int16_t)(w & 0xffff) * scale, (float)(int16_t)(w >> 16) * scale};
+    }
 }
 
 // element-wise evaluation of the numerical contract on the device (tests/test_detmath.py)
@@ -704,7 +716,7 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
         const void *kernels[] = {(const void *)k_detect, (const void *)k_select_spec, (const void *)k_select_fix, (const void *)k_select, (const void *)k_reserve,
                                  (const void *)k_frames_init, (const void *)k_sync_long, (const void *)k_signal, (const void *)k_plan_fast,
                                  (const void *)k_plan, (const void *)k_pack, (const void *)k_viterbi, (const void *)k_viterbi_warp,
-                                 (const void *)k_move_segments, (const void *)k_sc16_to_fc32, (const void *)k_tx, (const void *)k_channel,
+                                 (const void *)k_move_segments, (const void *)k_append_sc16, (const void *)k_sc16_to_fc32, (const void *)k_tx, (const void *)k_channel,
                                  (const void *)k_demod<false, WIFI_EQ_LS, 0>, (const void *)k_demod<false, WIFI_EQ_LS, 1>,
                                  (const void *)k_demod<false, WIFI_EQ_LMS, 0>, (const void *)k_demod<false, WIFI_EQ_LMS, 1>,
                                  (const void *)k_demod<false, WIFI_EQ_COMB, 0>, (const void *)k_demod<false, WIFI_EQ_COMB, 1>,
@@ -1143,8 +1155,9 @@ int wifi_b200_rx_reset(wifi_b200_t *h)
 // makes that a plain DMA), and stay on the device: a run decodes the regions in place, then every link's retained
 // tail (history + held / deferred bursts) slides to the front of its region.
 // dev_src != nullptr: the new samples already sit in device memory (the staging buffer of an asynchronous push, link l at
-// dev_src[link_off[l]]) and are appended by a copy kernel; else they are copied from the host buffer `iq`.
-static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, int n_links, int flush, const cf *dev_src = nullptr)
+// dev_src[link_off[l]]; as int16 I/Q pairs when sc16_scale != 0) and are appended by a copy kernel; else they are copied
+// from the host buffer `iq`.
+static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, int n_links, int flush, const cf *dev_src = nullptr, float sc16_scale = 0.f)
 {
     if (n_links <= 0 || n_links > MAX_LINKS) return WIFI_E_ARG;
     cudaSetDevice(h->device);
@@ -1176,7 +1189,10 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
     if (!app.empty()) {
         CK(cudaMemcpyAsync(h->d_moves, app.data(), app.size() * sizeof(wifi_b200::MoveSeg), cudaMemcpyHostToDevice, h->stream));
         unsigned bx = (unsigned)std::min<int64_t>((newest + 2047) / 2048, 64);
-        k_move_segments<<<dim3(bx ? bx : 1, (unsigned)app.size()), 256, 0, h->stream>>>(dev_src, h->d_stream, h->d_moves);
+        if (sc16_scale != 0.f)
+            k_append_sc16<<<dim3(bx ? bx : 1, (unsigned)app.size()), 256, 0, h->stream>>>(reinterpret_cast<const int16_t *>(dev_src), h->d_stream, h->d_moves, sc16_scale);
+        else
+            k_move_segments<<<dim3(bx ? bx : 1, (unsigned)app.size()), 256, 0, h->stream>>>(dev_src, h->d_stream, h->d_moves);
     }
     h->s_unprocessed += newest;
     // small pushes only buffer: a pipeline run has a fixed cost of about a millisecond (the decoder's latency for the
@@ -1318,7 +1334,7 @@ int wifi_b200_rx_push_links(wifi_b200_t *h, const float *iq, const uint64_t *lin
     return stream_push(h, iq, link_off, n_links, flush);
 }
 
-int wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq, const uint64_t *link_off, int n_links, int flush)
+static int push_async(wifi_b200 *h, const void *iq, size_t bytes_per_sample, float sc16_scale, const uint64_t *link_off, int n_links, int flush)
 {
     if (!h || !link_off || n_links <= 0 || n_links > MAX_LINKS) return WIFI_E_ARG;
     for (int l = 0; l < n_links; ++l)
@@ -1330,7 +1346,7 @@ int wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq, const uint64_
     if (h->a_pending.size() >= A_SLOTS) { h->err = "three asynchronous pushes are already pending: call wifi_b200_rx_push_wait first"; return WIFI_E_OVERFLOW; }
     if (total > h->cfg.max_samples) { h->err = "push larger than max_samples"; return WIFI_E_OVERFLOW; }
     const int slot = h->a_next % A_SLOTS;
-    if ((int64_t)h->a_cap[slot] < total) {
+    if ((int64_t)h->a_cap[slot] < total) {        // slots are sized in fc32 samples: either format fits
         if (h->d_stage[slot]) cudaFree(h->d_stage[slot]);
         h->d_stage[slot] = nullptr;
         h->a_cap[slot] = 0;
@@ -1341,15 +1357,31 @@ int wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq, const uint64_
     wifi_b200::AsyncPush job;
     job.slot = slot;
     job.flush = flush;
+    job.sc16_scale = sc16_scale;
     job.off.resize(n_links + 1);
     for (int l = 0; l <= n_links; ++l) job.off[l] = link_off[l] - link_off[0];
     // one copy for the whole push (the links lie back to back in the caller's buffer), on the copy stream: it runs while
     // the pipeline of the push before it is still decoding
-    if (total) CK(cudaMemcpyAsync(h->d_stage[slot], iq + 2 * link_off[0], (size_t)total * sizeof(cf), cudaMemcpyHostToDevice, h->copy_stream));
+    if (total) CK(cudaMemcpyAsync(h->d_stage[slot], (const char *)iq + bytes_per_sample * link_off[0], (size_t)total * bytes_per_sample, cudaMemcpyHostToDevice, h->copy_stream));
     CK(cudaEventRecord(h->a_ev[slot], h->copy_stream));
     h->a_pending.push_back(std::move(job));
     h->a_next++;
     return WIFI_OK;
+}
+
+int wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq, const uint64_t *link_off, int n_links, int flush)
+{
+    return push_async(h, iq, sizeof(cf), 0.f, link_off, n_links, flush);
+}
+
+int wifi_b200_rx_push_links_sc16_async(wifi_b200_t *h, const int16_t *iq, float scale, const uint64_t *link_off, int n_links, int flush)
+{
+    if (h && scale == 0.f) {
+        std::lock_guard<std::mutex> g(h->mu);
+        h->err = "sc16 scale must not be 0";
+        return WIFI_E_ARG;
+    }
+    return push_async(h, iq, 2 * sizeof(int16_t), scale, link_off, n_links, flush);
 }
 
 int wifi_b200_rx_push_wait(wifi_b200_t *h)
@@ -1361,7 +1393,7 @@ int wifi_b200_rx_push_wait(wifi_b200_t *h)
     wifi_b200::AsyncPush job = std::move(h->a_pending.front());
     h->a_pending.erase(h->a_pending.begin());
     CK(cudaStreamWaitEvent(h->stream, h->a_ev[job.slot], 0));
-    int rc = stream_push(h, nullptr, job.off.data(), (int)job.off.size() - 1, job.flush, h->d_stage[job.slot]);
+    int rc = stream_push(h, nullptr, job.off.data(), (int)job.off.size() - 1, job.flush, h->d_stage[job.slot], job.sc16_scale);
     // the staging buffer may be written by the next asynchronous push only after the append kernel has read it
     cudaStreamSynchronize(h->stream);
     return rc < 0 ? rc : 1;

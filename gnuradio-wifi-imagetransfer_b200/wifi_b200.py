@@ -62,7 +62,7 @@ EXPORTS = [
     "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_dev_state", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_rx_push_links", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
-    "wifi_b200_selftest_detmath", "wifi_b200_alu_peak", "wifi_b200_rx_push_links_async", "wifi_b200_rx_push_wait",
+    "wifi_b200_selftest_detmath", "wifi_b200_alu_peak", "wifi_b200_rx_push_links_async", "wifi_b200_rx_push_links_sc16_async", "wifi_b200_rx_push_wait",
     "wifi_b200_host_alloc", "wifi_b200_host_free",
 ]
 
@@ -109,6 +109,7 @@ def lib():
         L.wifi_b200_rx_push.argtypes = [vp, vp, C.c_size_t, C.c_int]
         L.wifi_b200_rx_push_links.argtypes = [vp, vp, vp, C.c_int, C.c_int]
         L.wifi_b200_rx_push_links_async.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        L.wifi_b200_rx_push_links_sc16_async.argtypes = [vp, vp, C.c_float, vp, C.c_int, C.c_int]
         L.wifi_b200_rx_push_wait.argtypes = [vp]
         L.wifi_b200_rx_pop.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_int)]
         L.wifi_b200_rx_reset.argtypes = [vp]
@@ -357,6 +358,13 @@ class Handle:
         assert isinstance(blob, np.ndarray) and blob.dtype == np.complex64 and blob.flags.c_contiguous
         off = np.ascontiguousarray(link_off, np.uint64)
         self._ck(self._L.wifi_b200_rx_push_links_async(self._h, _p(blob) if blob.size else None, _p(off), off.size - 1, int(flush)))
+
+    def rx_push_links_sc16_async(self, blob16, scale, link_off, flush=False):
+        """The asynchronous push in the wire format: `blob16` is page-locked int16, I/Q interleaved (2 values per sample);
+        link_off counts complex samples.  x = float32(i16) * float32(scale) on the GPU, as rx_batch_sc16."""
+        assert isinstance(blob16, np.ndarray) and blob16.dtype == np.int16 and blob16.flags.c_contiguous
+        off = np.ascontiguousarray(link_off, np.uint64)
+        self._ck(self._L.wifi_b200_rx_push_links_sc16_async(self._h, _p(blob16) if blob16.size else None, C.c_float(scale), _p(off), off.size - 1, int(flush)))
 
     def rx_push_wait(self):
         """Completes the oldest pending asynchronous push (copy done, pipeline run); True if there was one."""

@@ -206,6 +206,11 @@ int  wifi_b200_rx_push_links(wifi_b200_t *h, const float *iq_host, const uint64_
  * the copy of push k + 1 overlaps the decoding of push k.  Results are identical to the synchronous calls. */
 int  wifi_b200_rx_push_links_async(wifi_b200_t *h, const float *iq_host, const uint64_t *link_off, int n_links, int flush);
 int  wifi_b200_rx_push_wait(wifi_b200_t *h);
+/* The same push in the radios' wire format (int16 I/Q pairs, as wifi_b200_rx_batch_sc16: x = (float)i16 * scale, the
+ * conversion UHD's sc16 -> fc32 host converter performs before uhd_usrp_source hands samples to `samp_in`): half the bytes
+ * over PCIe, converted on the GPU while the samples are appended to the streams.  Completed by wifi_b200_rx_push_wait like
+ * the fc32 form; the two forms may be mixed on one handle.  link_off counts complex samples. */
+int  wifi_b200_rx_push_links_sc16_async(wifi_b200_t *h, const int16_t *iq_host, float scale, const uint64_t *link_off, int n_links, int flush);
 
 int  wifi_b200_get_stats(wifi_b200_t *h, wifi_b200_stats *out);
 /* device time (ms) of each pipeline stage in the last rx_batch call; names via wifi_b200_stage_name */

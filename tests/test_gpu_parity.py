@@ -472,6 +472,63 @@ def test_asynchronous_pushes_equal_synchronous_ones(O, W):
     assert sorted(sync) == sorted(want)
 
 
+def test_wire_format_pushes_equal_float_pushes(O, W):
+    """wifi_b200_rx_push_links_sc16_async: int16 I/Q over PCIe, converted while it is appended to the streams.  The frames are
+    those of pushing x = float32(i16) * scale as complex64 (and of the oracle on that capture); the two forms mix freely."""
+    import torch
+    rng = np.random.default_rng(77)
+    n_links, chunk, scale = 4, 5000, np.float32(1.0 / 4096)
+    caps16 = []
+    for l in range(n_links):
+        c = make_capture(O, rng, [(int(rng.integers(0, 8)), int(rng.integers(60, 500))) for _ in range(8)], snr_db=30,
+                         cfo=float(rng.uniform(-0.01, 0.01)), seed=40 + l, lead=int(rng.integers(50, 400)))[0]
+        q = np.clip(np.round(c.view(np.float32) / scale), -32768, 32767).astype(np.int16)          # what an ADC + DDC would deliver
+        caps16.append(q)
+    n_push = max(-(-(q.size // 2) // chunk) for q in caps16)
+    caps16 = [np.concatenate([q, np.zeros(2 * n_push * chunk - q.size, np.int16)]) for q in caps16]
+    capsf = [(q.astype(np.float32) * scale).view(np.complex64) for q in caps16]
+    off = (np.arange(n_links + 1) * chunk).astype(np.uint64)
+
+    def run(wire):
+        h = W.Handle(max_samples=n_links * (1 << 17), max_frames=512)
+        pf = [torch.empty(2 * n_links * chunk, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        p16 = [torch.empty(2 * n_links * chunk, dtype=torch.int16, pin_memory=True) for _ in range(2)]
+        out = []
+
+        def push(k):
+            if wire(k):
+                b = p16[k & 1].numpy()
+                for l in range(n_links):
+                    b[2 * l * chunk:2 * (l + 1) * chunk] = caps16[l][2 * k * chunk:2 * (k + 1) * chunk]
+                h.rx_push_links_sc16_async(b, float(scale), off, flush=(k == n_push - 1))
+            else:
+                b = pf[k & 1].numpy().view(np.complex64)
+                for l in range(n_links):
+                    b[l * chunk:(l + 1) * chunk] = capsf[l][k * chunk:(k + 1) * chunk]
+                h.rx_push_links_async(b, off, flush=(k == n_push - 1))
+
+        push(0)
+        for k in range(1, n_push + 1):
+            if k < n_push:
+                push(k)
+            assert h.rx_push_wait()
+            out += h.rx_pop(cap=512)
+        with pytest.raises(W.WifiB200Error):
+            h.rx_push_links_sc16_async(p16[0].numpy(), 0.0, off)           # scale 0 is refused
+        h.close()
+        return [(int(f["link"]), int(f["trigger"]), float(f["freq_long"]), float(f["snr"]), d) for f, d in out]
+
+    as_float, as_wire, mixed = run(lambda k: False), run(lambda k: True), run(lambda k: k % 3 != 1)
+    assert as_float == as_wire == mixed and len(as_float) >= 24
+    want = []
+    for l, c in enumerate(capsf):
+        r = O.rx(c, algo=0, want_carrier=False)
+        want += [(l, int(f["trigger"]), float(f["freq_long"]), float(f["snr"]), r.psdu(i)[:-4]) for i, f in enumerate(r.frames) if f["crc_ok"]]
+    a_, b_ = sorted(as_wire), sorted(want)
+    assert [x[:3] + x[4:] for x in a_] == [x[:3] + x[4:] for x in b_]                # stream, trigger, frequency offset, bytes
+    assert np.allclose([x[3] for x in a_], [x[3] for x in b_], rtol=1e-9, atol=1e-9)  # snr: double log10, libm vs device
+
+
 def test_loopback_epsilon_is_the_channel_models_frequency_offset(O, W):
     """channel_model(frequency_offset = epsilon * freq / 10e6) is cycles per sample (IRS_tranceiver.py:284,434): with the
     slider at its end stop (20e-6) the receiver must report 2 pi * 0.01178 = 0.074 rad/sample, not a 2e7 times smaller one."""
