@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include "rx_kernels.cuh"
@@ -229,8 +230,16 @@ struct wifi_b200 {
     int64_t group_samples = 0;     // WIFI_P_HOST_GROUP_SAMPLES: samples per link group of the host-input batch calls (0: 128 MB of host bytes)
     int64_t s_batch = 0;           // WIFI_P_STREAM_BATCH: a push only buffers until this many new samples per link wait (0: every push)
     int64_t s_unprocessed = 0;     // samples appended to the fullest link since the last pipeline run
+    // results waiting for wifi_b200_rx_pop: the frames of the newest runs stay in the page-locked PSDU mirror they arrived
+    // in (one block per run, two mirrors used in turn); a block whose mirror the next run needs is spilled into the
+    // packed queue (s_meta / s_bytes), which is always older than every block
+    struct StreamBlock { uint8_t *buf = nullptr; std::vector<wifi_b200_frame> meta; size_t next = 0; };
     std::vector<wifi_b200_frame> s_meta;
     std::vector<uint8_t> s_bytes;
+    std::deque<StreamBlock> s_blocks;
+    uint8_t *h_psdu_alt = nullptr;         // pinned, allocated by the first streaming run
+    int view_kind = 0;                     // wifi_b200_rx_pop_view handed out: 1 = the packed queue, 2 = the front block
+    size_t view_n = 0, view_bytes = 0;
     // asynchronous pushes (wifi_b200_rx_push_links_async): up to A_SLOTS in flight, each with its device staging buffer
     struct AsyncPush { int slot = 0; int flush = 0; float sc16_scale = 0.f; std::vector<uint64_t> off; };   // sc16_scale != 0: the slot holds int16 I/Q
     std::vector<AsyncPush> a_pending;
@@ -283,6 +292,7 @@ void free_all(wifi_b200 *h)
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->h_frames) cudaFreeHost(h->h_frames);
     if (h->h_psdu) cudaFreeHost(h->h_psdu);
+    if (h->h_psdu_alt) cudaFreeHost(h->h_psdu_alt);
     if (h->h_iq) cudaFreeHost(h->h_iq);
     for (int i = 0; i <= ST_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
@@ -412,8 +422,43 @@ struct H2dPlan {
 // stream while group g is decoded, and the results of group g travel back on a third stream while group g + 1 is
 // decoded -- one cudaMemcpyAsync per group and direction.  Frame records, rows and PSDU slots of the groups follow each
 // other in link order, so the result is the same table as from one pass over all links.
+// ---- queued streaming results (see wifi_b200::StreamBlock) ----
+void release_view(wifi_b200 *h)
+{
+    if (h->view_kind == 1) {
+        h->s_meta.erase(h->s_meta.begin(), h->s_meta.begin() + h->view_n);
+        h->s_bytes.erase(h->s_bytes.begin(), h->s_bytes.begin() + h->view_bytes);
+    } else if (h->view_kind == 2 && !h->s_blocks.empty()) {
+        h->s_blocks.pop_front();
+    }
+    h->view_kind = 0;
+}
+
+void spill_front_block(wifi_b200 *h)
+{
+    wifi_b200::StreamBlock &b = h->s_blocks.front();
+    for (size_t i = b.next; i < b.meta.size(); ++i) {
+        const wifi_b200_frame &f = b.meta[i];
+        const uint8_t *p = b.buf + f.psdu_off;
+        h->s_bytes.insert(h->s_bytes.end(), p, p + (f.length - 4));
+        h->s_meta.push_back(f);
+    }
+    h->s_blocks.pop_front();
+}
+
+// `buf` is about to be overwritten: the blocks that live in it, and the older ones in front of them, move to the packed queue
+void spill_blocks_on(wifi_b200 *h, const uint8_t *buf)
+{
+    release_view(h);
+    size_t last = 0;
+    for (size_t i = 0; i < h->s_blocks.size(); ++i)
+        if (h->s_blocks[i].buf == buf) last = i + 1;
+    for (size_t i = 0; i < last; ++i) spill_front_block(h);
+}
+
 int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullptr)
 {
+    spill_blocks_on(h, h->h_psdu);
     const int n_links = (int)h->h_links.size();
     int64_t total_tiles = 0, total = 0;
     for (auto &L : h->h_links) {
@@ -608,6 +653,7 @@ int fetch_frames(wifi_b200 *h)
 int fetch_psdus(wifi_b200 *h)
 {
     if (h->psdu_mirror || h->n_jobs == 0) return WIFI_OK;
+    spill_blocks_on(h, h->h_psdu);
     CK(cudaMemcpyAsync(h->h_psdu, h->d_psdu, (size_t)h->n_jobs * PSDU_STRIDE, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->psdu_mirror = true;
@@ -1147,6 +1193,8 @@ int wifi_b200_rx_reset(wifi_b200_t *h)
     h->s_cap = 0;
     h->s_unprocessed = 0;
     h->s_meta.clear(); h->s_bytes.clear();
+    h->s_blocks.clear();
+    h->view_kind = 0;
     return WIFI_OK;
 }
 
@@ -1247,6 +1295,7 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
     for (int64_t i = 0; i < h->n_frames; ++i)
         if (h->h_frames[i].n_syms < 0) has_held[h->h_frames[i].link] = 1;
     std::vector<int64_t> keep(n_links, -1);
+    wifi_b200::StreamBlock blk;
     h->stats.samples += h->n_samples;             // samples this run looked at (a held burst is looked at again)
     for (int64_t i = 0; i < h->n_frames; ++i) {
         wifi_b200_frame f = h->h_frames[i];
@@ -1260,10 +1309,23 @@ static int stream_push(wifi_b200 *h, const float *iq, const uint64_t *link_off, 
         S.prev_trigger = f.trigger + S.abs0;
         S.fo_carry = f.freq_long;
         if (!f.crc_ok) continue;
-        const uint8_t *p = h->h_psdu + f.psdu_off;
-        h->s_bytes.insert(h->s_bytes.end(), p, p + (f.length - 4));
         f.trigger += S.abs0;
-        h->s_meta.push_back(f);
+        blk.meta.push_back(f);                    // psdu_off: offset of the PSDU in this run's mirror
+    }
+    if (!blk.meta.empty()) {
+        // the PSDUs stay where the copy engine put them; the next run writes into the other mirror
+        if (!h->h_psdu_alt && cudaMallocHost(&h->h_psdu_alt, (size_t)h->cfg.max_frames * PSDU_STRIDE) != cudaSuccess) {
+            cudaGetLastError();
+            h->h_psdu_alt = nullptr;
+        }
+        blk.buf = h->h_psdu;
+        h->s_blocks.push_back(std::move(blk));
+        if (h->h_psdu_alt) {
+            std::swap(h->h_psdu, h->h_psdu_alt);
+            h->psdu_mirror = false;               // h_psdu no longer holds the last run's PSDUs
+        } else {
+            spill_blocks_on(h, h->h_psdu);        // no second mirror: packed copy, as a pageable queue
+        }
     }
     std::vector<wifi_b200::MoveSeg> moves;         // [0, nm): arena -> scratch, [nm, 2 nm): scratch -> front of the region
     std::vector<wifi_b200::MoveSeg> back;
@@ -1403,6 +1465,7 @@ int wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *ps
 {
     if (!h || !n_out) return WIFI_E_ARG;
     std::lock_guard<std::mutex> g(h->mu);
+    release_view(h);
     int k = 0;
     size_t used = 0, consumed_bytes = 0;
     while (k < (int)h->s_meta.size() && k < cap) {
@@ -1416,9 +1479,53 @@ int wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *ps
         consumed_bytes += nb;
         ++k;
     }
+    const bool queue_empty = k == (int)h->s_meta.size();
     h->s_meta.erase(h->s_meta.begin(), h->s_meta.begin() + k);
     h->s_bytes.erase(h->s_bytes.begin(), h->s_bytes.begin() + consumed_bytes);
+    bool full = !queue_empty;
+    while (!full && !h->s_blocks.empty()) {        // then the runs whose PSDUs still sit in their mirror, oldest first
+        wifi_b200::StreamBlock &b = h->s_blocks.front();
+        while (b.next < b.meta.size()) {
+            wifi_b200_frame f = b.meta[b.next];
+            size_t nb = (size_t)(f.length - 4);
+            if (k >= cap || used + nb > psdu_cap) { full = true; break; }
+            if (psdu_buf) memcpy(psdu_buf + used, b.buf + f.psdu_off, nb);
+            f.psdu_off = (int64_t)used;
+            if (meta) meta[k] = f;
+            used += nb;
+            ++k;
+            ++b.next;
+        }
+        if (!full) h->s_blocks.pop_front();
+    }
     *n_out = k;
+    return WIFI_OK;
+}
+
+int wifi_b200_rx_pop_view(wifi_b200_t *h, const wifi_b200_frame **meta, const uint8_t **psdu_bytes, size_t *n_bytes, int *n_out)
+{
+    if (!h || !meta || !psdu_bytes || !n_bytes || !n_out) return WIFI_E_ARG;
+    std::lock_guard<std::mutex> g(h->mu);
+    release_view(h);
+    *meta = nullptr; *psdu_bytes = nullptr; *n_bytes = 0; *n_out = 0;
+    if (!h->s_meta.empty()) {
+        size_t used = 0;
+        for (auto &f : h->s_meta) { f.psdu_off = (int64_t)used; used += (size_t)(f.length - 4); }
+        *meta = h->s_meta.data();
+        *psdu_bytes = h->s_bytes.data();
+        *n_bytes = used;
+        *n_out = (int)h->s_meta.size();
+        h->view_kind = 1;
+        h->view_n = h->s_meta.size();
+        h->view_bytes = used;
+    } else if (!h->s_blocks.empty()) {
+        wifi_b200::StreamBlock &b = h->s_blocks.front();
+        *meta = b.meta.data() + b.next;
+        *psdu_bytes = b.buf;
+        *n_bytes = (size_t)h->cfg.max_frames * PSDU_STRIDE;
+        *n_out = (int)(b.meta.size() - b.next);
+        h->view_kind = 2;
+    }
     return WIFI_OK;
 }
 

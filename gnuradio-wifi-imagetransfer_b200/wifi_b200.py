@@ -14,6 +14,7 @@ FRAME_DTYPE = np.dtype([
     ("crc_ok", "<i4"), ("snr", "<f8"), ("row_off", "<i8"), ("psdu_off", "<i8"),
 ], align=True)
 PSDU_STRIDE = 1536
+vp_t = C.c_void_p
 
 ENCODINGS = ("BPSK_1_2", "BPSK_3_4", "QPSK_1_2", "QPSK_3_4", "QAM16_1_2", "QAM16_3_4", "QAM64_2_3", "QAM64_3_4")
 EQUALIZERS = ("LS", "LMS", "COMB", "STA")
@@ -62,7 +63,7 @@ EXPORTS = [
     "wifi_b200_tx_symbols", "wifi_b200_channel_dev", "wifi_b200_channel", "wifi_b200_rx_batch", "wifi_b200_rx_batch_dev", "wifi_b200_rx_batch_dev_state", "wifi_b200_rx_batch_sc16", "wifi_b200_rx_counts",
     "wifi_b200_rx_frames", "wifi_b200_rx_rows", "wifi_b200_rx_psdus", "wifi_b200_rx_soft", "wifi_b200_rx_flags", "wifi_b200_rx_push",
     "wifi_b200_rx_pop", "wifi_b200_rx_reset", "wifi_b200_rx_push_links", "wifi_b200_get_stats", "wifi_b200_stage_times", "wifi_b200_stage_name",
-    "wifi_b200_selftest_detmath", "wifi_b200_alu_peak", "wifi_b200_rx_push_links_async", "wifi_b200_rx_push_links_sc16_async", "wifi_b200_rx_push_wait",
+    "wifi_b200_selftest_detmath", "wifi_b200_alu_peak", "wifi_b200_rx_push_links_async", "wifi_b200_rx_push_links_sc16_async", "wifi_b200_rx_push_wait", "wifi_b200_rx_pop_view",
     "wifi_b200_host_alloc", "wifi_b200_host_free",
 ]
 
@@ -112,6 +113,7 @@ def lib():
         L.wifi_b200_rx_push_links_sc16_async.argtypes = [vp, vp, C.c_float, vp, C.c_int, C.c_int]
         L.wifi_b200_rx_push_wait.argtypes = [vp]
         L.wifi_b200_rx_pop.argtypes = [vp, vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_int)]
+        L.wifi_b200_rx_pop_view.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         L.wifi_b200_rx_reset.argtypes = [vp]
         L.wifi_b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.wifi_b200_stage_times.argtypes = [vp, vp, C.c_int]
@@ -382,9 +384,19 @@ class Handle:
         return out
 
     def rx_pop_arrays(self, cap=4096, copy=True):
-        """Bulk form of rx_pop for many live links: (frame records, PSDU bytes back to back); record i's PSDU is
-        blob[rec["psdu_off"] : rec["psdu_off"] + rec["length"] - 4].  No per-frame Python objects.  copy=False returns
-        views of the wrapper's receive buffers, valid until the next rx_pop_arrays call."""
+        """Bulk form of rx_pop for many live links: (frame records, PSDU bytes); record i's PSDU is
+        blob[rec["psdu_off"] : rec["psdu_off"] + rec["length"] - 4].  No per-frame Python objects.  copy=True packs up to
+        `cap` frames back to back into fresh arrays; copy=False returns views of the library's own (page-locked) result
+        buffers -- the frames of ONE pipeline run per call, `cap` ignored, valid until the next call on this handle
+        (wifi_b200_rx_pop_view).  Call until no records come back."""
+        if not copy:
+            pm, pb, nb, n = vp_t(), vp_t(), C.c_size_t(), C.c_int()
+            self._ck(self._L.wifi_b200_rx_pop_view(self._h, C.byref(pm), C.byref(pb), C.byref(nb), C.byref(n)))
+            if not n.value:
+                return np.zeros(0, FRAME_DTYPE), np.zeros(0, np.uint8)
+            meta = np.frombuffer((C.c_char * (n.value * FRAME_DTYPE.itemsize)).from_address(pm.value), FRAME_DTYPE)
+            blob = np.frombuffer((C.c_char * nb.value).from_address(pb.value), np.uint8) if nb.value else np.zeros(0, np.uint8)
+            return meta, blob
         if getattr(self, "_pop_meta", None) is None or self._pop_meta.size < cap:
             self._pop_meta = np.zeros(cap, FRAME_DTYPE)
             self._pop_buf = np.zeros(cap * 1528, np.uint8)
@@ -392,8 +404,6 @@ class Handle:
         self._ck(self._L.wifi_b200_rx_pop(self._h, _p(self._pop_meta), cap, _p(self._pop_buf), self._pop_buf.size, C.byref(n)))
         k = n.value
         used = int(self._pop_meta["psdu_off"][k - 1] + self._pop_meta["length"][k - 1] - 4) if k else 0
-        if not copy:
-            return self._pop_meta[:k], self._pop_buf[:used]
         return self._pop_meta[:k].copy(), self._pop_buf[:used].copy()
 
     def rx_reset(self):

@@ -188,6 +188,12 @@ int  wifi_b200_rx_push(wifi_b200_t *h, const float *iq_host, size_t n, int flush
 /* pops CRC-ok frames in stream order; psdu_buf receives PSDUs without FCS back to back,
  * meta[i].psdu_off is the offset into psdu_buf, meta[i].length-4 the size; trigger is absolute */
 int  wifi_b200_rx_pop(wifi_b200_t *h, wifi_b200_frame *meta, int cap, uint8_t *psdu_buf, size_t psdu_cap, int *n_frames);
+/* The same frames without a copy: *meta points at *n_frames records and *psdu_bytes at the (page-locked) buffer the copy
+ * engine delivered their PSDUs into; record i's PSDU is (*psdu_bytes)[meta[i].psdu_off .. + meta[i].length - 4) (the
+ * offsets are NOT back to back), *n_bytes is the extent of that buffer.  One call returns the results of one pipeline
+ * run (the oldest not yet popped; call until *n_frames == 0).  The pointers stay valid until the next call on this
+ * handle, which is also when the frames leave the queue. */
+int  wifi_b200_rx_pop_view(wifi_b200_t *h, const wifi_b200_frame **meta, const uint8_t **psdu_bytes, size_t *n_bytes, int *n_frames);
 int  wifi_b200_rx_reset(wifi_b200_t *h);
 /* The same for n_links continuous streams at once (many live channels on one GPU share one pipeline run): link l
  * receives iq_host[link_off[l] .. link_off[l+1]) new complex samples (possibly none).  The number of links is fixed by
