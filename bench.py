@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-time-shard", action="store_true", help="skip the time-sharded section (one capture cut into overlapping segments across the ranks)")
     ap.add_argument("--ts-frames", type=int, default=151552, help="frames of the single-link capture the time-sharded section cuts across the ranks (the same at every N: strong scaling)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--viterbi-form", type=int, default=0, help="pin the Viterbi kernel form of the main handle (WIFI_P_VITERBI_FORM: 1 warp, 2 four lanes, 3 thread per trellis; 0 = by frame count)")
     ap.add_argument("--cpu-frames", type=int, default=8192, help="frames of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -405,6 +406,8 @@ def main():
     n_samples = n_links * (LEAD + fpl * (flen + GAP))
     h = W.Handle(device=local, chan_est=args.algo, encoding=ENC, max_samples=n_samples + 1024, max_frames=n + n_links + 1024,
                  soft_decision=args.soft)
+    if args.viterbi_form:
+        h.set_param(W.wifi_b200.P_VITERBI_FORM, args.viterbi_form)
     sampler = ClockSampler(local) if rank == 0 else None           # started early: nvidia-smi takes a while to produce its first line
     cap, link_off, psdus = build_capture(h, W, torch, n_links, fpl, seed=1000 + rank)
     torch.cuda.synchronize()

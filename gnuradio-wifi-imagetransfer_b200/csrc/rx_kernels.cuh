@@ -1300,6 +1300,77 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     frames[J.frame].crc_ok = sink.crc_ok();
 }
 
+// ------------------------------------------------------------------ R6a-c, four lanes per trellis (middle-sized calls)
+// VitQuad (viterbi.cuh): a quarter of the butterflies per lane and two quad exchanges per four steps.  A call with a few
+// thousand frames (a streaming run of a hundred links, a link group of a host batch) has one warp per scheduler or
+// less in the one-trellis-per-thread kernel and pays that kernel's full ~1.7 ms latency; here the same frames make four
+// times the warps, each with a quarter of the dependent work.  Chunk 0 (6 steps) runs as two erased steps + 6: from
+// all-zero metrics an erased step leaves the metrics zero and every path's decision bit set, so masking bits 7, 6 of
+// the path bytes afterwards gives exactly the 6-step bytes.
+__global__ void __launch_bounds__(VQ_BLOCK) k_viterbi_quad(const JobDesc *__restrict__ jobs, int f0, int n_frames, const uint32_t *__restrict__ vit_in,
+                                                          uint32_t *__restrict__ psdu, wifi_b200_frame *frames)
+{
+    __shared__ uint32_t s_ring[VQ_FRAMES * VQ_RSTRIDE];
+    __shared__ uint32_t s_crc[256];
+    __shared__ uint16_t s_scr[128];
+    __shared__ uint2 s_bm[16];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += VQ_BLOCK) s_crc[i] = c_tab.crc_tab[i];
+    for (int i = tid; i < 128; i += VQ_BLOCK) s_scr[i] = c_tab.scr_tab[i];
+    if (tid < 16) { uint32_t T, E; VitCore::branch((uint32_t)tid, T, E); s_bm[tid] = make_uint2(T, E); }
+    __syncthreads();
+    const int job = f0 + blockIdx.x * VQ_FRAMES + (tid >> 2);
+    // the quads of a warp stay together (full-mask shuffles): a quad without a frame, or with a shorter one, runs along
+    // on zeros and keeps its results to itself
+    JobDesc J;
+    J.n_sym = 0;
+    if (job < n_frames) J = jobs[job];
+    const bool active = job < n_frames && J.n_sym != 0;
+    if (!__any_sync(0xffffffffu, active)) return;
+    const int enc = active ? J.enc : 0;
+    const int punct = c_tab.mcs[enc].punct;
+    const int ntb = punct == 0 ? 5 : (punct == 1 ? 9 : 10);
+    const int nw = active ? (J.n_sym * c_tab.mcs[enc].n_dbps + 7) >> 3 : 0;
+    const uint32_t *in = vit_in + (int64_t)(active ? job : f0) * VIT_MAXW;
+    const int L = active ? J.len : 0;
+    const int last_chunk = active ? L + 1 + ntb : 0;
+    const int trips = __reduce_max_sync(0xffffffffu, last_chunk);
+    uint32_t *ring = s_ring + (tid >> 2) * VQ_RSTRIDE;
+    VitQuad v;
+    v.init(tid & 31);
+    uint32_t prev = 0 < nw ? in[0] : 0u;
+    v.step4<0>(s_bm, 0xau, 0xau, prev & 0xfu, (prev >> 4) & 0xfu);
+    v.step4<4>(s_bm, (prev >> 8) & 0xfu, (prev >> 12) & 0xfu, (prev >> 16) & 0xfu, (prev >> 20) & 0xfu);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.p[i] &= 0x3f3f3f3fu;
+    int slot = 1 % ntb;
+    v.trace_begin(ring, slot, ntb, true);
+    PsduSink sink;
+    sink.init(psdu + (int64_t)(active ? job : f0) * (PSDU_STRIDE / 4), L, s_crc, s_scr);
+    sink.writer = active && (tid & 3) == 0;
+    uint32_t next = 1 < nw ? in[1] : 0u;
+    VitCore::Trace tr;
+    tr.bs = 0; tr.sl = slot; tr.left = 0;
+#pragma unroll 1
+    for (int chunk = 1; chunk <= trips; ++chunk) {
+        const uint32_t bits = __funnelshift_r(prev, next, 24);
+        prev = next;
+        next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
+        VitQuad::trace_hops<3>(tr, ring, ntb);
+        v.step4<0>(s_bm, bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
+        VitQuad::trace_hops<3>(tr, ring, ntb);
+        v.step4<4>(s_bm, (bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
+        VitQuad::trace_hops<3>(tr, ring, ntb);
+        // the traceback of chunk - 1 is complete (ntb - 1 <= 9 hops): its byte, if that chunk has one and is this frame's
+        if (chunk - 1 >= ntb && chunk - 1 <= last_chunk) sink.push(VitQuad::ring_byte(ring, tr.sl, tr.bs), chunk - 1 - ntb);
+        slot = (slot + 1 == ntb) ? 0 : slot + 1;
+        tr = v.trace_begin(ring, slot, ntb, (chunk & 3) == 0);
+    }
+    VitQuad::trace_hops<9>(tr, ring, ntb);
+    if (trips == last_chunk && last_chunk >= ntb) sink.push(VitQuad::ring_byte(ring, tr.sl, tr.bs), last_chunk - ntb);
+    if (sink.writer) frames[J.frame].crc_ok = sink.crc_ok();
+}
+
 // ------------------------------------------------------------------ R6a-c, low-latency form for small batches
 // One trellis per WARP: lane l owns states l and l + 32 -- exactly the two inputs of butterfly l -- and the survivors
 // 2l, 2l + 1 travel to their new owners by shuffle (state n lives in lane n % 32).  Per-frame latency is a fraction of

@@ -303,6 +303,182 @@ struct VitCore {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same decoder with one trellis spread over FOUR lanes (a "quad"), for calls that hold too few frames to fill the
+// machine with one thread per trellis (a 1528-byte frame is 12312 dependent trellis steps; one warp per scheduler runs
+// them in ~1.7 ms however idle the GPU is).  Lane g of a quad owns the natural metric words {g, g+4, g+8, g+12} (and
+// the path words), i.e. local word i <-> natural word g + 4i.  In VitCore::step4's schedule that ownership makes
+//   step A (natural, pairs word j with j+8)        local: j = g and j = g + 4
+//   step B (stride 2, pairs S[j] with S[j+4])      local
+//   step C (stride 4, pairs Q[4j+o], Q[4(j+2)+o])  one exchange with lane g ^ 2 (two metric + two path words each way)
+//   step D (stride 8, pairs S[o], S[8+o])          one exchange with lane g ^ 1
+//   the 4x4 byte transpose back to natural order   local, and lands on the ownership step A needs
+// so four trellis steps cost a quarter of the butterflies plus 8 shuffles per lane.  Which butterflies a lane computes
+// depends on g, so the branch selectors are per-lane registers (set up once) instead of immediates.  The eight quads of
+// a warp run in lock step (full-mask shuffles): the kernel gives them one trip count.
+// Results are those of VitCore bit for bit: same metrics, same tie rule, same path bytes, same first-best-state search.
+#define VQ_BLOCK 64                      // threads per block: 16 quads
+#define VQ_FRAMES (VQ_BLOCK / 4)
+#define VQ_RSTRIDE (VIT_NTB_MAX * 16 + 4) // ring words per frame; 164 = 4 (mod 32): the 8 quads x 4 lanes of a warp hit 32 banks
+
+struct VitQuad {
+    uint32_t m[4], p[4];
+    uint32_t selA0, selA1, selB0, selB1, selC0, selC1, selD0, selD1;
+    uint32_t keyc[4];                    // state labels (63 - state) of local word i, for the best-state keys
+    int g;
+    bool hiC, hiD;
+
+    static __device__ __forceinline__ uint32_t sel4(int k0, int k1, int k2, int k3)
+    {
+        const int k[4] = {k0, k1, k2, k3};
+        uint32_t s = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t A = __popc((2u * k[b]) & 0x6du) & 1u, B = __popc((2u * k[b]) & 0x4fu) & 1u;
+            s |= (2 * A + B) << (4 * b);
+        }
+        return s;
+    }
+
+    __device__ __forceinline__ void init(int lane_in_warp)
+    {
+        g = lane_in_warp & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { m[i] = 0; p[i] = 0; keyc[i] = 0x3c3d3e3fu - 0x04040404u * (uint32_t)(g + 4 * i); }
+        selA0 = sel4(4 * g, 4 * g + 1, 4 * g + 2, 4 * g + 3);
+        selA1 = sel4(4 * (g + 4), 4 * (g + 4) + 1, 4 * (g + 4) + 2, 4 * (g + 4) + 3);
+        selB0 = sel4(8 * g, 8 * g + 2, 8 * g + 4, 8 * g + 6);
+        selB1 = sel4(8 * g + 1, 8 * g + 3, 8 * g + 5, 8 * g + 7);
+        hiC = (g >> 1) != 0;
+        { const int j = g & 1, o = hiC ? 2 : 0;
+          selC0 = sel4(16 * j + o, 16 * j + 4 + o, 16 * j + 8 + o, 16 * j + 12 + o);
+          selC1 = sel4(16 * j + o + 1, 16 * j + 5 + o, 16 * j + 9 + o, 16 * j + 13 + o); }
+        hiD = (g & 1) != 0;
+        { const int o = (g >> 1) * 4 + (g & 1) * 2;
+          selD0 = sel4(o, 8 + o, 16 + o, 24 + o);
+          selD1 = sel4(o + 1, 9 + o, 17 + o, 25 + o); }
+    }
+
+    template <uint32_t BIT>
+    static __device__ __forceinline__ void bfly(uint32_t T, uint32_t E, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t plo, uint32_t phi,
+                                                uint32_t &v0, uint32_t &v1, uint32_t &q0, uint32_t &q1)
+    {
+        const uint32_t svm = prmt(T, 0u, sel), sv = E - svm;
+        const uint32_t m0 = lo + sv, m1 = hi + svm, m2 = lo + svm, m3 = hi + sv;
+        const uint32_t k0 = prmt(m0 + 0x7f7f7f7fu - m1, 0u, 0xba98u);
+        const uint32_t k1 = prmt(m2 + 0x7f7f7f7fu - m3, 0u, 0xba98u);
+        v0 = (m0 & k0) | (m1 & ~k0);
+        v1 = (m2 & k1) | (m3 & ~k1);
+        const uint32_t pb = phi + BIT;
+        q0 = (plo & k0) | (pb & ~k0);
+        q1 = (plo & k1) | (pb & ~k1);
+    }
+
+    // the lane that computes the "upper" two pairs keeps x[2], x[3] as the hi inputs and receives its partner's as lo;
+    // the other keeps x[0], x[1] as lo and receives hi
+    __device__ __forceinline__ void exchange(const uint32_t (&x)[4], bool high, int lane_xor, uint32_t &lo_a, uint32_t &hi_a, uint32_t &lo_b, uint32_t &hi_b) const
+    {
+        const uint32_t ra = __shfl_xor_sync(0xffffffffu, high ? x[0] : x[2], lane_xor);
+        const uint32_t rb = __shfl_xor_sync(0xffffffffu, high ? x[1] : x[3], lane_xor);
+        lo_a = high ? ra : x[0]; hi_a = high ? x[2] : ra;
+        lo_b = high ? rb : x[1]; hi_b = high ? x[3] : rb;
+    }
+
+    template <int S0>
+    __device__ __forceinline__ void step4(const uint2 *bm, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
+    {
+        constexpr uint32_t B0 = 0x01010101u << (7 - S0), B1 = B0 >> 1, B2 = B0 >> 2, B3 = B0 >> 3;
+        uint32_t T, E;
+        uint32_t s[4], sp[4], q[4], qp[4];
+        // A: pairs j = g -> S[g], S[8+g]; j = g + 4 -> S[g+4], S[12+g]      (s[i] <-> S[g + 4i])
+        { const uint2 te = bm[n0]; T = te.x; E = te.y; }
+        bfly<B0>(T, E, selA0, m[0], m[2], p[0], p[2], s[0], s[2], sp[0], sp[2]);
+        bfly<B0>(T, E, selA1, m[1], m[3], p[1], p[3], s[1], s[3], sp[1], sp[3]);
+        // B: even pair j = g: (S[g], S[g+4]) -> Q[4g], Q[4g+1]; odd pair: (S[8+g], S[12+g]) -> Q[4g+2], Q[4g+3]
+        { const uint2 te = bm[n1]; T = te.x; E = te.y; }
+        bfly<B1>(T, E, selB0, s[0], s[1], sp[0], sp[1], q[0], q[1], qp[0], qp[1]);
+        bfly<B1>(T, E, selB1, s[2], s[3], sp[2], sp[3], q[2], q[3], qp[2], qp[3]);
+        // C: lanes j and j + 2 share pairs (j, o): the lower lane takes o = 0, 1, the upper one o = 2, 3
+        { const uint2 te = bm[n2]; T = te.x; E = te.y; }
+        {
+            uint32_t la, ha, lb, hb, pla, pha, plb, phb;
+            exchange(q, hiC, 2, la, ha, lb, hb);
+            exchange(qp, hiC, 2, pla, pha, plb, phb);
+            bfly<B2>(T, E, selC0, la, ha, pla, pha, s[0], s[1], sp[0], sp[1]);
+            bfly<B2>(T, E, selC1, lb, hb, plb, phb, s[2], s[3], sp[2], sp[3]);
+        }
+        // now lane 0: S[0..3], lane 2: S[4..7], lane 1: S[8..11], lane 3: S[12..15].  D: pairs (S[o], S[8+o]): lanes g, g ^ 1
+        { const uint2 te = bm[n3]; T = te.x; E = te.y; }
+        {
+            uint32_t la, ha, lb, hb, pla, pha, plb, phb;
+            exchange(s, hiD, 1, la, ha, lb, hb);
+            exchange(sp, hiD, 1, pla, pha, plb, phb);
+            bfly<B3>(T, E, selD0, la, ha, pla, pha, q[0], q[1], qp[0], qp[1]);
+            bfly<B3>(T, E, selD1, lb, hb, plb, phb, q[2], q[3], qp[2], qp[3]);
+        }
+        // lane g holds Q[4g .. 4g+3]: the transpose of VitCore::step4, group g -> natural words g, g+4, g+8, g+12
+        uint32_t t0 = prmt(q[0], q[1], 0x5140u), t1 = prmt(q[0], q[1], 0x7362u);
+        uint32_t t2 = prmt(q[2], q[3], 0x5140u), t3 = prmt(q[2], q[3], 0x7362u);
+        m[0] = prmt(t0, t2, 0x5410u); m[1] = prmt(t0, t2, 0x7632u); m[2] = prmt(t1, t3, 0x5410u); m[3] = prmt(t1, t3, 0x7632u);
+        t0 = prmt(qp[0], qp[1], 0x5140u); t1 = prmt(qp[0], qp[1], 0x7362u);
+        t2 = prmt(qp[2], qp[3], 0x5140u); t3 = prmt(qp[2], qp[3], 0x7362u);
+        p[0] = prmt(t0, t2, 0x5410u); p[1] = prmt(t0, t2, 0x7632u); p[2] = prmt(t1, t3, 0x5410u); p[3] = prmt(t1, t3, 0x7632u);
+    }
+
+    // ring: this frame's VIT_NTB_MAX x 16 words (natural order).  All four lanes follow the traceback (same addresses:
+    // broadcast reads), so no lane waits for another's result.
+    __device__ __forceinline__ VitCore::Trace trace_begin(uint32_t *ring, int slot, int ntb, bool renorm)
+    {
+        __syncwarp();                                        // the quad is done reading the slot this snapshot replaces
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ring[slot * 16 + g + 4 * i] = p[i];
+        uint32_t key[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            key[2 * i] = prmt(m[i], keyc[i], 0x1504u);
+            key[2 * i + 1] = prmt(m[i], keyc[i], 0x3726u);
+        }
+#pragma unroll
+        for (int n = 4; n >= 1; n >>= 1)
+#pragma unroll
+            for (int i = 0; i < n; ++i) key[i] = __vmaxu2(key[i], key[i + n]);
+        uint32_t kbest = max(key[0] & 0xffffu, key[0] >> 16);
+        kbest = max(kbest, __shfl_xor_sync(0xffffffffu, kbest, 1));
+        kbest = max(kbest, __shfl_xor_sync(0xffffffffu, kbest, 2));  // (also orders the snapshot stores before the quad's reads)
+        __syncwarp();
+        VitCore::Trace t;
+        t.bs = 63 - (int)(kbest & 0xffu);
+        t.sl = slot;
+        t.left = ntb - 1;
+        if (renorm) {
+            const uint32_t mx = kbest >> 8;
+            const uint32_t minw = (mx > 12u ? mx - 12u : 0u) * 0x01010101u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[i] -= minw;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = 0;
+        return t;
+    }
+    static __device__ __forceinline__ uint32_t ring_byte(const uint32_t *ring, int sl, int bs)
+    {
+        return reinterpret_cast<const uint8_t *>(ring)[sl * 64 + bs];
+    }
+    template <int N>
+    static __device__ __forceinline__ void trace_hops(VitCore::Trace &t, const uint32_t *ring, int ntb)
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool go = t.left > 0;
+            const int nb = (int)(ring_byte(ring, t.sl, t.bs) >> 2);
+            const int ns = (t.sl == 0) ? ntb - 1 : t.sl - 1;
+            t.bs = go ? nb : t.bs;
+            t.sl = go ? ns : t.sl;
+            t.left -= go ? 1 : 0;
+        }
+    }
+};
+
 // descramble + CRC-32 + PSDU word assembly shared by the hard and soft decoders
 // ([UPSTREAM] decode_mac.cc descramble(), boost::crc_32_type).  push() takes the traceback byte c
 // (MSB = earliest bit) of decoded byte index m.

@@ -148,12 +148,19 @@ enum { ST_H2D = 0, ST_DETECT, ST_SELECT, ST_SYNC_LONG, ST_DEMOD_HEAD, ST_SIGNAL,
 const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "demod_head", "signal", "demod_data", "plan", "pack", "viterbi", "d2h"};
 
 #define MAX_LINKS 16384
+// Which Viterbi kernel decodes a call's (or a link group's) frames, by their number -- measured on 1528-byte 64-QAM 3/4
+// frames (tools/exp_viterbi_forms.sh): one trellis per warp 0.68 ms up to 592 frames, 0.87 at 1184, 1.45 at
+// 2368; per four lanes 0.93 ms flat up to 4736, 1.38 at 9472, 2.54 at 18944; per thread 1.72-1.78 ms up to 18944, 3.11 at 37888.
 #ifndef VW_SWITCH
-#define VW_SWITCH 2368          // frames per call up to which the warp-per-frame Viterbi is used (148 SMs x 16 warps; measured crossover ~2700)
+#define VW_SWITCH 1280          // up to here one trellis per warp
+#endif
+#ifndef VQ_SWITCH
+#define VQ_SWITCH 12288         // up to here one trellis per four lanes; above, one per thread
 #endif
 #define DET_SMEM DET_SMEM_BYTES
 
 } // namespace
+
 
 #define A_SLOTS 3                // asynchronous pushes that may be pending at once (device staging buffers)
 struct wifi_b200 {
@@ -247,6 +254,7 @@ struct wifi_b200 {
     size_t a_cap[A_SLOTS] = {};
     cudaEvent_t a_ev[A_SLOTS] = {};
     int a_next = 0;
+    int viterbi_form = 0;          // WIFI_P_VITERBI_FORM
 };
 
 namespace {
@@ -586,7 +594,10 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
                 k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in, h->d_frames);
                 if (timed) mark(h, ST_VITERBI);
                 // a handful of frames (streaming runs, small link groups): one trellis per warp, a third of the latency; else one per thread
-                if (nf <= VW_SWITCH) k_viterbi_warp<<<(unsigned)((nf + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
+                // (WIFI_P_VITERBI_FORM pins one form: the three are the same decoder, bit for bit)
+                const int form = h->viterbi_form ? h->viterbi_form : (nf <= VW_SWITCH ? 1 : (nf <= VQ_SWITCH ? 2 : 3));
+                if (form == 1) k_viterbi_warp<<<(unsigned)((nf + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
+                else if (form == 2) k_viterbi_quad<<<(unsigned)((nf + VQ_FRAMES - 1) / VQ_FRAMES), VQ_BLOCK, 0, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
                 else k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, vit_smem, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
             } else {
                 k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in, h->d_frames);
@@ -762,7 +773,7 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
         const void *kernels[] = {(const void *)k_detect, (const void *)k_select_spec, (const void *)k_select_fix, (const void *)k_select, (const void *)k_reserve,
                                  (const void *)k_frames_init, (const void *)k_sync_long, (const void *)k_signal, (const void *)k_plan_fast,
                                  (const void *)k_plan, (const void *)k_pack, (const void *)k_viterbi, (const void *)k_viterbi_warp,
-                                 (const void *)k_move_segments, (const void *)k_append_sc16, (const void *)k_sc16_to_fc32, (const void *)k_tx, (const void *)k_channel,
+                                 (const void *)k_move_segments, (const void *)k_viterbi_quad, (const void *)k_append_sc16, (const void *)k_sc16_to_fc32, (const void *)k_tx, (const void *)k_channel,
                                  (const void *)k_demod<false, WIFI_EQ_LS, 0>, (const void *)k_demod<false, WIFI_EQ_LS, 1>,
                                  (const void *)k_demod<false, WIFI_EQ_LMS, 0>, (const void *)k_demod<false, WIFI_EQ_LMS, 1>,
                                  (const void *)k_demod<false, WIFI_EQ_COMB, 0>, (const void *)k_demod<false, WIFI_EQ_COMB, 1>,
@@ -823,6 +834,7 @@ int wifi_b200_set_param(wifi_b200_t *h, int id, double v)
     case WIFI_P_SOFT_DECISION: h->cfg.soft_decision = v != 0; break;
     case WIFI_P_STREAM_BATCH: if (v < 0 || v > (double)h->cfg.max_samples / 2) return WIFI_E_ARG; h->s_batch = (int64_t)v; break;
     case WIFI_P_HOST_GROUP_SAMPLES: if (v < 0) return WIFI_E_ARG; h->group_samples = (int64_t)v; break;
+    case WIFI_P_VITERBI_FORM: if (v != 0 && v != 1 && v != 2 && v != 3) return WIFI_E_ARG; h->viterbi_form = (int)v; break;
     case WIFI_P_WANT_CARRIER:
         if (v != 0 && !h->d_carrier) {
             cudaSetDevice(h->device);
@@ -850,6 +862,7 @@ double wifi_b200_get_param(wifi_b200_t *h, int id)
     case WIFI_P_SOFT_DECISION: return h->cfg.soft_decision;
     case WIFI_P_STREAM_BATCH: return (double)h->s_batch;
     case WIFI_P_HOST_GROUP_SAMPLES: return (double)h->group_samples;
+    case WIFI_P_VITERBI_FORM: return h->viterbi_form;
     default: return NAN;
     }
 }

@@ -18,7 +18,7 @@ vp_t = C.c_void_p
 
 ENCODINGS = ("BPSK_1_2", "BPSK_3_4", "QPSK_1_2", "QPSK_3_4", "QAM16_1_2", "QAM16_3_4", "QAM64_2_3", "QAM64_3_4")
 EQUALIZERS = ("LS", "LMS", "COMB", "STA")
-P_BANDWIDTH, P_FREQUENCY, P_SENSITIVITY, P_CHAN_EST, P_ENCODING, P_MIN_PLATEAU, P_WANT_CARRIER, P_SOFT_DECISION, P_STREAM_BATCH, P_HOST_GROUP_SAMPLES = range(10)
+P_BANDWIDTH, P_FREQUENCY, P_SENSITIVITY, P_CHAN_EST, P_ENCODING, P_MIN_PLATEAU, P_WANT_CARRIER, P_SOFT_DECISION, P_STREAM_BATCH, P_HOST_GROUP_SAMPLES, P_VITERBI_FORM = range(11)
 E_ARG, E_TOO_LARGE, E_CUDA, E_NOMEM, E_OVERFLOW, E_NODEVICE = -1, -2, -3, -4, -5, -6
 
 

@@ -60,7 +60,11 @@ enum { WIFI_P_BANDWIDTH = 0, WIFI_P_FREQUENCY = 1, WIFI_P_SENSITIVITY = 2, WIFI_
        /* host-input batch calls (rx_batch, rx_batch_sc16) process the links in groups so that the copy of one group overlaps
         * the decoding of the previous one; a group is closed when it holds this many samples (0 = about 128 MB of host
         * bytes, the default).  Results do not depend on it. */
-       WIFI_P_HOST_GROUP_SAMPLES = 9 };
+       WIFI_P_HOST_GROUP_SAMPLES = 9,
+       /* which form of the hard-decision Viterbi kernel decodes a call's frames: 0 = by frame count (default), 1 = one
+        * trellis per warp (a handful of frames), 2 = per four lanes (a few thousand), 3 = per thread (tens of thousands).
+        * The three are the same decoder and give identical bytes; the id exists for tests and measurements. */
+       WIFI_P_VITERBI_FORM = 10 };
 
 typedef struct wifi_b200_cfg {
     double bandwidth;      /* Hz, hier default 10e6 (wifi_phy_hier.grc:92)                        */

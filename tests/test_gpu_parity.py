@@ -76,6 +76,40 @@ def test_rx_all_mcs(H, O, W, algo):
     assert sum(ref.frames["crc_ok"]) >= 9   # the capture is decodable
 
 
+@pytest.mark.parametrize("form", [1, 2, 3])
+def test_viterbi_kernel_forms_are_one_decoder(O, W, form):
+    """One trellis per warp, per four lanes and per thread (WIFI_P_VITERBI_FORM): every MCS and traceback depth, lengths that
+    differ inside a warp, frames that fail their FCS at a marginal SNR, several links -- the same bytes as the oracle's decoder."""
+    rng = np.random.default_rng(4242)
+    caps = []
+    for l in range(3):
+        specs = [(int(rng.integers(0, 8)), int(rng.integers(20, 1529))) for _ in range(14)] + [(l, 1), (7 - l, 1528)]
+        caps.append(make_capture(O, rng, specs, snr_db=[30, 19, 13][l], cfo=float(rng.uniform(-0.01, 0.01)), seed=300 + l, gap=600)[0])
+    off = np.concatenate([[0], np.cumsum([c.size for c in caps])]).astype(np.uint64)
+    h = W.Handle(max_samples=1 << 22, max_frames=512)
+    try:
+        h.set_param(W.wifi_b200.P_VITERBI_FORM, form)
+        assert h.get_param(W.wifi_b200.P_VITERBI_FORM) == form
+        res = h.rx_batch(np.concatenate(caps), link_off=off)
+        k = 0
+        n_bad = 0
+        for l, c in enumerate(caps):
+            ref = O.rx(c, algo=0, want_carrier=False)
+            for i in range(len(ref.frames)):
+                g = res.frames[k + i]
+                assert int(g["link"]) == l and int(g["trigger"]) == int(ref.frames[i]["trigger"])
+                assert int(g["decoded"]) == int(ref.frames[i]["decoded"]) and int(g["crc_ok"]) == int(ref.frames[i]["crc_ok"]), (l, i)
+                if ref.frames[i]["decoded"]:
+                    assert res.psdu(k + i) == ref.psdu(i), (l, i)
+                    n_bad += not ref.frames[i]["crc_ok"]
+            k += len(ref.frames)
+        assert k == len(res.frames) >= 40 and n_bad >= 3
+        with pytest.raises(W.WifiB200Error):
+            h.set_param(W.wifi_b200.P_VITERBI_FORM, 4)
+    finally:
+        h.close()
+
+
 def test_flags_match_frontend(H, O, W):
     rng = np.random.default_rng(5)
     y, _ = make_capture(O, rng, [(2, 100), (5, 300)], snr_db=15, cfo=-0.02)
