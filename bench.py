@@ -157,6 +157,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
     segs = S.shard_stream(n_total, world)
     dev = torch.device("cuda", local)
     decode_ms = [0.0]
+    last_stage = {}
 
     problems = []
 
@@ -170,7 +171,10 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
                 state = np.zeros(1, W.wifi_b200.LINK_STATE_DTYPE)
                 state["min_pos"], state["fo_carry"], state["hist"] = st["min_pos"], st["fo_carry"], st["hist"]
                 h.rx_batch_dev_state(cap.data_ptr(), off, state, final=final, fetch=False)
-            decode_ms[0] += sum(h.stage_times().values())
+            st_ = h.stage_times()
+            last_stage.clear()
+            last_stage.update({k: round(v, 3) for k, v in st_.items() if v})
+            decode_ms[0] += sum(st_.values())
             return h.frames()                                                    # 96 bytes per trigger; PSDUs stay on the device
         except Exception as ex:
             problems.append(repr(ex))
@@ -221,10 +225,10 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
     t_sh, dec_sh, t_one = [float(v) for v in tv.tolist()]
     return {"capture": "one link, %d frames, %d samples (%.2f GB), the same on every rank" % (fpl, n_total, n_total * 8 / 1e9),
             "ranks": world, "overlap_samples": S.OVERLAP, "sharded_ms": 1e3 * t_sh, "sharded_decode_device_ms": dec_sh,
-            "single_gpu_ms": 1e3 * t_one, "single_gpu_stage_ms": one_stage, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
+            "sharded_stage_ms_rank0_last_decode": dict(last_stage), "single_gpu_ms": 1e3 * t_one, "single_gpu_stage_ms": one_stage, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
             "value_msamples_per_s": n_total / t_sh / 1e6, "frames_owned_total": int(cnt[0]), "crc_ok_total": int(cnt[1]),
             "re_decode_rounds": rounds, "union_equals_single_gpu_table": equal, "problems": problems or None, "scaling": "strong",
-            "collective": "per round two NCCL all_gathers: the last 512 owned frame records of every rank (96 bytes each), then the ranks' verdicts; + one counter all_reduce" if world > 1 else "none (one rank)",
+            "collective": "per round two NCCL all_gathers of fixed-size buffers: the last 512 owned frame records of every rank (96 bytes each), then the ranks' verdicts; + one counter all_reduce" if world > 1 else "none (one rank)",
             "timing": "wall clock around sharding.reconcile (decode, record all-gather, join check), barrier + synchronize on both sides, max over ranks, mean of %d; the union check against rank 0's whole-capture decode runs outside it" % reps}
 
 

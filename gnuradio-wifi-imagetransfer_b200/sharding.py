@@ -185,15 +185,34 @@ def resume_point(truth, seg_start, core_start):
     return start, {"min_pos": int(f2[TRIG]) - start, "fo_carry": _bits_f32(f1[FREQ]), "hist": min(HIST, start)}, t[idx[-1]:idx[-1] + 1]
 
 
-def gather_records(hdr, rec, device=None):
+def gather_records(hdr, rec, device=None, fixed_rows=None):
     """All ranks' (header, record table) pairs (NCCL all_gather of the padded int32 tables on GPUs, gloo on CPU); list
-    indexed by rank.  The header row says where a rank's decode started and the frequency offset it started with."""
+    indexed by rank.  The header row says where a rank's decode started and the frequency offset it started with.
+    fixed_rows = K: every rank sends at most K rows, so the buffers have a known size and the row count travels in the
+    header (column FOUND) -- ONE collective and one copy back instead of a count exchange first."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [(hdr, rec)]
     world = dist.get_world_size()
     rec = np.ascontiguousarray(rec, np.int32)
+    if fixed_rows is not None:
+        assert len(rec) <= fixed_rows
+        mine = np.zeros((fixed_rows + 1, REC_FIELDS), np.int32)
+        mine[0] = hdr
+        mine[0, FOUND] = len(rec)
+        mine[1:1 + len(rec)] = rec
+        buf = torch.from_numpy(mine).to(device) if device is not None else torch.from_numpy(mine)
+        everyone = torch.empty((world,) + tuple(buf.shape), dtype=torch.int32, device=buf.device)
+        dist.all_gather_into_tensor(everyone, buf)
+        a = everyone.cpu().numpy()
+        out = []
+        for r in range(world):
+            c = int(a[r, 0, FOUND])
+            h = a[r, 0].copy()
+            h[FOUND] = 0
+            out.append((h, a[r, 1:1 + c]))
+        return out
     n = torch.tensor([len(rec)], dtype=torch.int64, device=device)
     counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(counts, n)
@@ -256,11 +275,11 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
     rounds = 0
     while tail_rows is not None:
         own = _owned(local, seg)
-        tails = do_gather(_header(lo, carry), own[-tail_rows:], device)
+        tails = do_gather(_header(lo, carry), own[-tail_rows:], device, tail_rows)
         truth = np.concatenate([t for _, t in tails[:rank]]) if rank else np.zeros((0, REC_FIELDS), np.int32)
         truth = truth[truth[:, TRIG] < seg["core_start"]]
         ok = lo == 0 or boundary_check(truth, local, carry, lo, seg["core_start"])     # a decode from sample 0 IS the sequential receiver
-        verdicts = do_gather(_header(int(ok), 0), np.zeros((0, REC_FIELDS), np.int32), device)
+        verdicts = do_gather(_header(int(ok), 0), np.zeros((0, REC_FIELDS), np.int32), device, 0)
         bad = next((r for r, (h, _) in enumerate(verdicts) if int(h[BURST]) == 0), None)
         if bad is None:                      # rank 0 is right; rank r agreed with the tails of ranks it just saw agree: all are
             return own, [t for _, t in tails], rounds
@@ -323,7 +342,7 @@ def simulate_ranks(decode, segs, n_samples, tail_rows=None):
     slots, out, bar, errs = [None] * world, [None] * world, threading.Barrier(world), []
 
     def run(rank):
-        def gather(hdr, rec, device=None):
+        def gather(hdr, rec, device=None, fixed_rows=None):
             slots[rank] = (hdr, rec)
             bar.wait()
             res = list(slots)
