@@ -1107,7 +1107,8 @@ __device__ void plan_sequential(PlanState &S, int f0, int f1, wifi_b200_frame *f
 // Fast path: one thread per frame.  A "regular" frame forms its own job and a SIGNAL-less frame forms
 // none, whatever surrounds them -- unless some frame of the link is irregular (SIGNAL ok but no rows,
 // too few rows, or an oversize tag), in which case the link is flagged and k_plan replays the exact
-// sequential state machine over it.
+// sequential state machine over it, from its first irregular frame on (everything in front of that frame is regular or
+// SIGNAL-less, which leaves decode_mac's state closed: the fast path's answer stands there).
 __global__ void __launch_bounds__(128) k_plan_fast(wifi_b200_frame *frames, int f0, int n_frames, JobDesc *jobs, int *pack_list, int *n_pack,
                                                     int *link_dirty, int soft)
 {
@@ -1118,7 +1119,7 @@ __global__ void __launch_bounds__(128) k_plan_fast(wifi_b200_frame *frames, int 
     jobs[fi].n_sym = 0;
     if (!sig) return;
     const bool regular = nrows > 0 && fsym <= WIFI_MAX_SYM && len <= WIFI_MAX_PSDU && nrows >= fsym;
-    if (!regular) { link_dirty[F->link] = 1; return; }
+    if (!regular) { atomicMax(&link_dirty[F->link], 0x7fffffff - fi); return; }   // records the link's FIRST irregular frame
     JobDesc J;
     J.frame = fi; J.enc = enc; J.len = len; J.n_sym = fsym; J.n_seg = 1;
     J.seg_row[0] = (int32_t)F->row_off; J.seg_cnt[0] = fsym;
@@ -1141,12 +1142,16 @@ __global__ void __launch_bounds__(128) k_plan(const LinkDesc *__restrict__ links
 {
     int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (l >= n_links) return;
-    if (!link_dirty[l]) return;          // every frame of the link was regular or SIGNAL-less: k_plan_fast is exact
+    const int dirty = link_dirty[l];
+    if (!dirty) return;                  // every frame of the link was regular or SIGNAL-less: k_plan_fast is exact
     const LinkDesc L = links[l];
     PlanState S;
     S.cur = -1; S.copied = 0; S.need = 0; S.pending = -1; S.J.n_seg = 0;
     const int fend = L.frame_first + L.frame_count;
-    for (int f0 = L.frame_first; f0 < fend; f0 += 32) {
+    // start at the group of 32 that holds the first irregular frame: no tag is pending and no collection open in front of
+    // it, which is the state above (a long stream cut at an arbitrary sample has ONE irregular frame, its last)
+    const int fstart = L.frame_first + (((0x7fffffff - dirty) - L.frame_first) & ~31);
+    for (int f0 = fstart; f0 < fend; f0 += 32) {
         int fi = f0 + lane;
         bool valid = fi < fend;
         int sig = 0, nrows = 0, fsym = 0, len = 0, enc = 0;

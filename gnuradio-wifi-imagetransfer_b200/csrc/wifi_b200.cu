@@ -168,6 +168,9 @@ struct wifi_b200 {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // host input / results of one link group while another is decoded
+    cudaStream_t aux_stream = nullptr;     // the Viterbi launch of the frames beyond whole waves, beside the main one
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int sm_count = 148;
     std::vector<cudaEvent_t> ev_h2d, ev_done;
     std::mutex mu;
     std::string err;
@@ -292,7 +295,10 @@ void free_all(wifi_b200 *h)
     // nothing of this handle may still be reading a caller's buffer or writing a pinned mirror when the memory goes away
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
+    if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int k = 0; k < A_SLOTS; ++k) if (h->a_ev[k]) cudaEventDestroy(h->a_ev[k]);
     void *ptrs[] = {h->d_stage[0], h->d_stage[1], h->d_stage[2], h->d_stream, h->d_moves, h->d_sc16, h->d_iq, h->d_flags, h->d_links, h->d_frames, h->d_states, h->d_rows, h->d_carrier, h->d_jobs, h->d_vit_in,
                     h->d_psdu, h->d_depunct, h->d_counters, h->d_summary, h->d_trig_tmp, h->d_pack_list, h->d_link_dirty, h->d_spec_trig, h->d_spec_cnt, h->d_spec_trig2, h->d_spec_cnt2, h->d_soft, h->d_vit_soft_in, h->d_txblob, h->d_txdesc, h->d_txsym, h->d_txiq, h->d_segs};
@@ -307,6 +313,7 @@ void free_all(wifi_b200 *h)
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -593,12 +600,31 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
             if (!soft) {
                 k_pack<<<dim3(7, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_rows, h->d_depunct, h->d_vit_in, h->d_frames);
                 if (timed) mark(h, ST_VITERBI);
-                // a handful of frames (streaming runs, small link groups): one trellis per warp, a third of the latency; else one per thread
-                // (WIFI_P_VITERBI_FORM pins one form: the three are the same decoder, bit for bit)
-                const int form = h->viterbi_form ? h->viterbi_form : (nf <= VW_SWITCH ? 1 : (nf <= VQ_SWITCH ? 2 : 3));
-                if (form == 1) k_viterbi_warp<<<(unsigned)((nf + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
-                else if (form == 2) k_viterbi_quad<<<(unsigned)((nf + VQ_FRAMES - 1) / VQ_FRAMES), VQ_BLOCK, 0, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
-                else k_viterbi<<<(unsigned)((nf + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, vit_smem, s>>>(h->d_jobs, f0, fe, h->d_vit_in, h->d_psdu, h->d_frames);
+                // by frame count: one trellis per warp, per four lanes, per thread (WIFI_P_VITERBI_FORM pins one form: the
+                // three are the same decoder, bit for bit)
+                auto launch_viterbi = [&](cudaStream_t st, int a, int b) {
+                    const int64_t n = b - a;
+                    const int form = h->viterbi_form ? h->viterbi_form : (n <= VW_SWITCH ? 1 : (n <= VQ_SWITCH ? 2 : 3));
+                    if (form == 1) k_viterbi_warp<<<(unsigned)((n + VW_WARPS - 1) / VW_WARPS), 32 * VW_WARPS, 0, st>>>(h->d_jobs, a, b, h->d_vit_in, h->d_psdu, h->d_frames);
+                    else if (form == 2) k_viterbi_quad<<<(unsigned)((n + VQ_FRAMES - 1) / VQ_FRAMES), VQ_BLOCK, 0, st>>>(h->d_jobs, a, b, h->d_vit_in, h->d_psdu, h->d_frames);
+                    else k_viterbi<<<(unsigned)((n + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, vit_smem, st>>>(h->d_jobs, a, b, h->d_vit_in, h->d_psdu, h->d_frames);
+                };
+                // The per-thread kernel runs in whole waves of sm_count x 4 blocks x 64 frames, and a wave takes ~1.7 ms
+                // however few blocks it holds: the frames beyond the last whole wave (a handful, when a long stream is cut
+                // into wave-sized segments with an overlap) go to their own launch on a second stream, in the form their
+                // number calls for, and run beside the main grid instead of after it.
+                const int64_t wave = (int64_t)h->sm_count * 4 * VIT_BLOCK;
+                const int64_t rem = nf % wave;
+                if (h->viterbi_form || nf < wave || rem == 0) {
+                    launch_viterbi(s, f0, fe);
+                } else {
+                    CK(cudaEventRecord(h->ev_fork, s));
+                    CK(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+                    launch_viterbi(h->aux_stream, fe - (int)rem, fe);
+                    launch_viterbi(s, f0, fe - (int)rem);
+                    CK(cudaEventRecord(h->ev_join, h->aux_stream));
+                    CK(cudaStreamWaitEvent(s, h->ev_join, 0));
+                }
             } else {
                 k_pack_soft<<<dim3(25, 148), 256, 0, s>>>(h->d_jobs, h->d_pack_list, h->d_counters + 1, h->d_soft, h->d_depunct, h->d_vit_soft_in, h->d_frames);
                 if (timed) mark(h, ST_VITERBI);
@@ -647,6 +673,7 @@ int run_rx_host(wifi_b200 *h, const H2dPlan &plan)
     if (rc != WIFI_OK) {
         cudaStreamSynchronize(h->copy_stream);
         cudaStreamSynchronize(h->d2h_stream);
+        cudaStreamSynchronize(h->aux_stream);
         cudaStreamSynchronize(h->stream);
     }
     return rc;
@@ -765,6 +792,10 @@ int wifi_b200_create(const wifi_b200_cfg *cfg_in, wifi_b200_t **out)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
     if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(WIFI_E_CUDA);
+    if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess || h->sm_count <= 0) h->sm_count = 148;
     for (int i = 0; i <= ST_COUNT; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) return fail(WIFI_E_CUDA);
     if (upload_tables(h) != WIFI_OK) return fail(WIFI_E_CUDA);
     if (cudaFuncSetAttribute(k_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, DET_SMEM) != cudaSuccess) return fail(WIFI_E_CUDA);

@@ -208,3 +208,30 @@ def test_config4_soft_decisions_over_the_ladder(O, W):
     assert (per[True] <= per[False] + 0.08).all(), (per[False], per[True])
     # (a 4 dB grid does not sample every column's waterfall: BPSK 3/4 falls between 2 and 6 dB)
     assert sum((per[False][e] - per[True][e]).max() >= 0.3 for e in range(len(mcs))) >= 2, (per[False], per[True])
+
+
+@pytest.mark.parametrize("fpp", [4760, 5000])
+def test_frames_beyond_whole_viterbi_waves_are_decoded_beside_them(W, fpp):
+    """A call with more frames than one wave of the per-thread Viterbi kernel (148 SMs x 4 blocks x 64 = 37888) decodes
+    the whole waves with that kernel and the remainder (192 frames: one trellis per warp; 2112: per four lanes) in a
+    second launch beside it.  Same frame table and the same PSDU bytes as ONE launch of the per-thread kernel over all."""
+    import hashlib
+    rng = np.random.default_rng(fpp)
+    pay = [rng.integers(0, 256, int(rng.integers(20, 70)), dtype=np.uint8).tobytes() for _ in range(997)]
+    h = W.Handle(chan_est=0, max_samples=1 << 28, max_frames=8 * fpp + 4096)
+    try:
+        cap, link_off, _, _ = build_ladder(W, h, pay, list(range(8)), [14.0], fpp)        # marginal SNR for the upper MCS: failing frames too
+        tables, stores = [], []
+        for form in (0, 3):
+            h.set_param(W.wifi_b200.P_VITERBI_FORM, form)
+            res = h.rx_batch_dev(cap.data_ptr(), link_off, final=True, fetch=True)
+            assert len(res.frames) >= 8 * fpp - 50 and len(res.frames) % 37888 not in (0,)
+            tables.append(res.frames.copy())
+            stores.append(hashlib.sha256(b"".join(res.psdu(i) for i in np.nonzero(res.frames["decoded"])[0])).hexdigest())
+        differing = [k for k in tables[0].dtype.names if not np.array_equal(tables[0][k], tables[1][k], equal_nan=True)]
+        assert not differing, [(k, np.nonzero(tables[0][k] != tables[1][k])[0][:8]) for k in differing]
+        assert stores[0] == stores[1]
+        ok = tables[0]["crc_ok"].sum()
+        assert 0.5 * 8 * fpp < ok < 8 * fpp - 100, ok
+    finally:
+        h.close()
