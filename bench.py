@@ -187,13 +187,15 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
 
     reps, warm = 5, 2
     own = owned_all = None
+    phases = {}
     rounds = 0
     for it in range(warm + reps):
         if it == warm:
             barrier()
             decode_ms[0] = 0.0
+            phases.clear()
             t0 = time.perf_counter()
-        own, _tails, rounds = S.reconcile(decode, segs, rank, n_total, device=dev if world > 1 else None, max_rounds=world + 2, tail_rows=512)
+        own, _tails, rounds = S.reconcile(decode, segs, rank, n_total, device=dev if world > 1 else None, max_rounds=world + 2, tail_rows=512, trace=phases)
     barrier()
     t_sh = (time.perf_counter() - t0) / reps
     dec_sh = decode_ms[0] / reps
@@ -225,7 +227,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
     t_sh, dec_sh, t_one = [float(v) for v in tv.tolist()]
     return {"capture": "one link, %d frames, %d samples (%.2f GB), the same on every rank" % (fpl, n_total, n_total * 8 / 1e9),
             "ranks": world, "overlap_samples": S.OVERLAP, "sharded_ms": 1e3 * t_sh, "sharded_decode_device_ms": dec_sh,
-            "sharded_stage_ms_rank0_last_decode": dict(last_stage), "single_gpu_ms": 1e3 * t_one, "single_gpu_stage_ms": one_stage, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
+            "sharded_stage_ms_rank0_last_decode": dict(last_stage), "sharded_wall_ms_by_phase_rank0": {k: round(1e3 * v / reps, 3) for k, v in phases.items()}, "single_gpu_ms": 1e3 * t_one, "single_gpu_stage_ms": one_stage, "speedup_over_single_gpu": t_one / t_sh if t_sh else None,
             "value_msamples_per_s": n_total / t_sh / 1e6, "frames_owned_total": int(cnt[0]), "crc_ok_total": int(cnt[1]),
             "re_decode_rounds": rounds, "union_equals_single_gpu_table": equal, "problems": problems or None, "scaling": "strong",
             "collective": "per round two NCCL all_gathers of fixed-size buffers: the last 512 owned frame records of every rank (96 bytes each), then the ranks' verdicts; + one counter all_reduce" if world > 1 else "none (one rank)",

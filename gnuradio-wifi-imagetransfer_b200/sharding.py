@@ -6,6 +6,8 @@ all-gather of the per-segment frame records with which every rank checks that it
 the sequential receiver's state before its core region began (`reconcile`); a rank whose check
 fails decodes again from a point where that state is known (NCCL over NVLink on GPUs, gloo in the
 CPU tests)."""
+import time
+
 import numpy as np
 
 # sync_short MAX_SAMPLES + sync_long window + FFT + MIN_GAP look-back + window warm-up (SURVEY 8e)
@@ -243,7 +245,7 @@ def _owned(rec, seg):
     return rec[a:b]
 
 
-def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gather=None, tail_rows=None):
+def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gather=None, tail_rows=None, trace=None):
     """Time-sharded receive with an exact result.  `decode(lo, end, state, final)` runs this rank's receiver over
     samples [lo, end) of the capture -- state None: a stream start at lo; else the wifi_b200_link_state fields, with
     state["hist"] samples of history in front of lo (the callee reads them from lo - hist) -- and returns its frame
@@ -259,6 +261,12 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
     seg = segs[rank]
     do_gather = gather or gather_records
 
+    def lap(key, t0):
+        # trace: a dict that receives the wall time (s) this rank spent per phase (decode, exchange, check); tail mode only
+        if trace is not None:
+            trace[key] = trace.get(key, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     def decode_closed(lo, st):
         """Decode [lo, end); while a frame this rank owns leaves decode_mac open at the end of the segment (a tag pending,
         a collection short of symbols: state the sequential receiver keeps for as long as it takes), decode further."""
@@ -271,15 +279,20 @@ def reconcile(decode, segs, rank, n_samples, device=None, max_rounds=None, gathe
             end, grow = min(n_samples, end + grow), 2 * grow
 
     lo, carry = seg["start"], _f32_bits(0.0)
+    t_ = time.perf_counter()
     local = decode_closed(lo, None)
+    t_ = lap("decode", t_)
     rounds = 0
     while tail_rows is not None:
         own = _owned(local, seg)
         tails = do_gather(_header(lo, carry), own[-tail_rows:], device, tail_rows)
+        t_ = lap("exchange", t_)
         truth = np.concatenate([t for _, t in tails[:rank]]) if rank else np.zeros((0, REC_FIELDS), np.int32)
         truth = truth[truth[:, TRIG] < seg["core_start"]]
         ok = lo == 0 or boundary_check(truth, local, carry, lo, seg["core_start"])     # a decode from sample 0 IS the sequential receiver
+        t_ = lap("check", t_)
         verdicts = do_gather(_header(int(ok), 0), np.zeros((0, REC_FIELDS), np.int32), device, 0)
+        t_ = lap("exchange", t_)
         bad = next((r for r, (h, _) in enumerate(verdicts) if int(h[BURST]) == 0), None)
         if bad is None:                      # rank 0 is right; rank r agreed with the tails of ranks it just saw agree: all are
             return own, [t for _, t in tails], rounds
