@@ -175,7 +175,7 @@ def run_time_sharded(W, torch, dist, args, rank, world, local):
             last_stage.clear()
             last_stage.update({k: round(v, 3) for k, v in st_.items() if v})
             decode_ms[0] += sum(st_.values())
-            return h.frames()                                                    # 96 bytes per trigger; PSDUs stay on the device
+            return h.frames(reuse=True)                                          # 96 bytes per trigger; PSDUs stay on the device
         except Exception as ex:
             problems.append(repr(ex))
             return np.zeros(0, W.wifi_b200.FRAME_DTYPE)

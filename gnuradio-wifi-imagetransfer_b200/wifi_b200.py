@@ -309,12 +309,19 @@ class Handle:
             self._ck(self._L.wifi_b200_rx_psdus(self._h, _p(store), store.size))
         return RxResult(frames, store)
 
-    def frames(self):
-        """The frame table of the last rx call alone (96 bytes per trigger; the PSDU store stays on the device)."""
-        c = self.counts()
-        frames = np.zeros(c["n_frames"], FRAME_DTYPE)
-        if c["n_frames"]:
-            self._ck(self._L.wifi_b200_rx_frames(self._h, _p(frames), frames.size))
+    def frames(self, reuse=False):
+        """The frame table of the last rx call alone (96 bytes per trigger; the PSDU store stays on the device).
+        reuse=True returns a view of a buffer the wrapper keeps (no fresh pages to fault in for a large table): valid until
+        the next frames(reuse=True)."""
+        n = self.counts()["n_frames"]
+        if reuse:
+            if getattr(self, "_frames_buf", None) is None or self._frames_buf.size < n:
+                self._frames_buf = np.empty(max(n, 1024), FRAME_DTYPE)
+            frames = self._frames_buf[:n]
+        else:
+            frames = np.zeros(n, FRAME_DTYPE)
+        if n:
+            self._ck(self._L.wifi_b200_rx_frames(self._h, _p(frames), n))
         return frames
 
     def rows(self, carrier=False):
