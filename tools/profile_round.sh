@@ -17,3 +17,9 @@ ncu --metrics smsp__inst_executed.sum,smsp__inst_executed_pipe_alu.sum,smsp__ins
 ncu --set full --clock-control none --import-source on -k 'regex:k_viterbi|k_demod|k_detect|k_sync_long' -s 10 -c 5 -f \
     -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 ls -la gpurun_out/${TAG}_*
+# the middle-sized-call Viterbi (one trellis per four lanes): 4736 frames in one call
+CMDQ="python bench.py --links 32 --frames-per-link 148 --steps 2 --warmup 1 --no-e2e --no-cpu --no-time-shard"
+$CMDQ > gpurun_out/${TAG}_quad_plain.json 2> gpurun_out/${TAG}_quad_plain.err && \
+ncu --set full --clock-control none --import-source on -k 'regex:k_viterbi_quad' -c 1 -s 2 -f \
+    -o gpurun_out/${TAG}_full_quad $CMDQ > gpurun_out/${TAG}_ncu4.log 2>&1
+ls -la gpurun_out/${TAG}_*
