@@ -157,6 +157,7 @@ const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "de
 #ifndef VQ_SWITCH
 #define VQ_SWITCH 12288         // up to here one trellis per four lanes; above, one per thread
 #endif
+#define VQ_SPLIT_MAX 4736        // frames beyond a step of the per-thread kernel's staircase that get their own launch (run_rx)
 #define DET_SMEM DET_SMEM_BYTES
 
 } // namespace
@@ -609,12 +610,13 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
                     else if (form == 2) k_viterbi_quad<<<(unsigned)((n + VQ_FRAMES - 1) / VQ_FRAMES), VQ_BLOCK, 0, st>>>(h->d_jobs, a, b, h->d_vit_in, h->d_psdu, h->d_frames);
                     else k_viterbi<<<(unsigned)((n + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, vit_smem, st>>>(h->d_jobs, a, b, h->d_vit_in, h->d_psdu, h->d_frames);
                 };
-                // The per-thread kernel runs in whole waves of sm_count x 4 blocks x 64 frames, and a wave takes ~1.7 ms
-                // however few blocks it holds: the frames beyond the last whole wave (a handful, when a long stream is cut
-                // into wave-sized segments with an overlap) go to their own launch on a second stream, in the form their
-                // number calls for, and run beside the main grid instead of after it.
-                const int64_t wave = (int64_t)h->sm_count * 4 * VIT_BLOCK;
-                const int64_t rem = nf % wave;
+                // The per-thread kernel's time is a staircase: 1.79 ms while every scheduler holds at most one of its warps
+                // (sm_count x 2 blocks x 64 = 18944 frames), 3.1 ms up to two (37888), and so on -- 18951 frames cost what
+                // 37888 do.  A few frames beyond a step (a long stream cut into step-sized segments with an overlap) therefore
+                // go to their own launch on a second stream, in the form their number calls for, beside the main grid.
+                const int64_t wave = (int64_t)h->sm_count * 2 * VIT_BLOCK;
+                int64_t rem = nf % wave;
+                if (rem > VQ_SPLIT_MAX) rem = 0;           // a large remainder competes for the same pipes: no gain
                 if (h->viterbi_form || nf < wave || rem == 0) {
                     launch_viterbi(s, f0, fe);
                 } else {
