@@ -1252,11 +1252,11 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     uint32_t *ring = vsm;                                   // VIT_NTB_MAX*16*VIT_BLOCK words
     uint32_t *s_crc = vsm + VIT_NTB_MAX * 16 * VIT_BLOCK;   // 256
     uint16_t *s_scr = (uint16_t *)(s_crc + 256);            // 128
-    uint2 *s_bm = (uint2 *)(s_crc + 256 + 64);              // 16 branch-word pairs
+    uint4 *s_bm = (uint4 *)(s_crc + 256 + 64);              // 16 branch-word triples (VitCoreH::branch)
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += VIT_BLOCK) s_crc[i] = c_tab.crc_tab[i];
     for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
-    if (tid < 16) { uint32_t T, E; VitCore::branch((uint32_t)tid, T, E); s_bm[tid] = make_uint2(T, E); }
+    if (tid < 16) s_bm[tid] = VitCoreH::branch((uint32_t)tid);
     __syncthreads();
     const int job = f0 + blockIdx.x * VIT_BLOCK + tid;
     if (job >= n_frames) return;
@@ -1269,13 +1269,15 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     uint32_t *out = psdu + (int64_t)job * (PSDU_STRIDE / 4);
     const int L = J.len;
     const int last_chunk = L + 1 + ntb;   // chunk whose traceback yields PSDU byte L-1
-    VitCore v;
+    VitCoreH v;
     v.init();
     uint32_t prev = in[0];
-#pragma unroll 1
-    for (int k = 0; k < 6; ++k) v.step((prev >> (4 * k)) & 0xfu);
+    // chunk 0 has 6 steps: two erased steps in front of them leave the all-zero metrics as they are and set bits 0, 1 of
+    // every path byte, which trace_begin masks off (keep = 0xfc)
+    v.step4<0>(s_bm, 0xau, 0xau, prev & 0xfu, (prev >> 4) & 0xfu);
+    v.step4<4>(s_bm, (prev >> 8) & 0xfu, (prev >> 12) & 0xfu, (prev >> 16) & 0xfu, (prev >> 20) & 0xfu);
     int slot = 1 % ntb;
-    v.end_chunk(ring, slot, ntb, tid);
+    v.trace_begin(ring, slot, ntb, tid, true, 0xfcu);
     PsduSink sink;
     sink.init(out, L, s_crc, s_scr);
     uint32_t next = 1 < nw ? in[1] : 0u;
@@ -1288,19 +1290,19 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
         uint32_t bits = __funnelshift_r(prev, next, 24);
         prev = next;
         next = (chunk + 1 < nw) ? in[chunk + 1] : 0u;
-        VitCore::trace_hops<3>(tr, ring, ntb, tid);
+        VitCoreH::trace_hops<3>(tr, ring, ntb, tid);
         v.step4<0>(s_bm, bits & 0xfu, (bits >> 4) & 0xfu, (bits >> 8) & 0xfu, (bits >> 12) & 0xfu);
-        VitCore::trace_hops<3>(tr, ring, ntb, tid);
+        VitCoreH::trace_hops<3>(tr, ring, ntb, tid);
         v.step4<4>(s_bm, (bits >> 16) & 0xfu, (bits >> 20) & 0xfu, (bits >> 24) & 0xfu, bits >> 28);
-        VitCore::trace_hops<3>(tr, ring, ntb, tid);
-        if (pending && chunk - 1 >= ntb) sink.push(VitCore::trace_finish(tr, ring, tid), chunk - 1 - ntb);
+        VitCoreH::trace_hops<3>(tr, ring, ntb, tid);
+        if (pending && chunk - 1 >= ntb) sink.push(VitCoreH::trace_finish(tr, ring, tid), chunk - 1 - ntb);
         slot = (slot + 1 == ntb) ? 0 : slot + 1;
         tr = v.trace_begin(ring, slot, ntb, tid, (chunk & 3) == 0);
         pending = true;
     }
     if (pending && last_chunk >= ntb) {
-        VitCore::trace_hops<9>(tr, ring, ntb, tid);
-        sink.push(VitCore::trace_finish(tr, ring, tid), last_chunk - ntb);
+        VitCoreH::trace_hops<9>(tr, ring, ntb, tid);
+        sink.push(VitCoreH::trace_finish(tr, ring, tid), last_chunk - ntb);
     }
     frames[J.frame].crc_ok = sink.crc_ok();
 }

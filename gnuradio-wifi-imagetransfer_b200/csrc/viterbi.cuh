@@ -1,18 +1,20 @@
-// viterbi.cuh -- K=7 (133,171) hard-decision Viterbi decoder, one trellis per thread.
+// viterbi.cuh -- K=7 (133,171) hard-decision Viterbi decoder.
 //
 // Restates [UPSTREAM] gr-ieee802-11 lib/viterbi_decoder/{base,viterbi_decoder_generic}.cc
 // (instance wifi_phy_hier.grc:533-549 decode_mac, and :550-569 frame_equalizer for SIGNAL):
 // 8-bit agreement metrics, tie -> predecessor k+32, per-state 8-bit path registers, a
 // traceback over `ntb` stored path snapshots every 8 trellis steps (first after 6).
 //
-// B200 mapping: the 64 path metrics of one frame live in 16 registers (4 states per
-// register, one byte each) and the 64 path registers in 16 more, so an add-compare-select
-// for 4 butterflies is a handful of 32-bit integer ops: IADD for the four candidate
-// metrics, one IADD3 + one PRMT (sign-replicate) for the byte-wise "m0 > m1" masks, LOP3
-// for the selects and PRMT for the state interleave.  Metrics never exceed 12+16 (spread
-// bound of the code + growth over one 8-step chunk), so bytes cannot carry into each
-// other.  Path snapshots go to shared memory, word-interleaved across the block's
-// threads (bank = thread id, conflict free).
+// Three forms of the same decoder, chosen by the number of frames in a call (wifi_b200.cu):
+//   VitCoreH  one trellis per THREAD (k_viterbi), metric and path byte of a state in one halfword, two states per
+//             register: the add-compare-select of four new states is two VIADDMNMX.U16x2 + two adds (round 2);
+//   VitQuad   one trellis per FOUR lanes (k_viterbi_quad), byte-packed metrics as VitCore, two quad exchanges per 4 steps;
+//   (k_viterbi_warp, rx_kernels.cuh: one trellis per warp.)
+// VitCore is the byte-packed per-thread form of round 1 -- 64 path metrics in 16 registers (4 states per register, one
+// byte each), 64 path bytes in 16 more; IADD for the candidate metrics, IADD3 + PRMT (sign-replicate) for the byte-wise
+// "m0 > m1" masks, LOP3 selects -- which k_signal and VitQuad still use.  Metrics never exceed 12 + 4 * 16 (spread
+// bound of the code + growth between renormalisations), so bytes cannot carry into each other.  Path snapshots go to
+// shared memory, word-interleaved across the block's threads (bank = thread id, conflict free).
 #pragma once
 #include "wifi_common.cuh"
 
@@ -47,6 +49,18 @@ __host__ __device__ constexpr uint32_t vit_sel4(int k0, int k1, int k2, int k3)
     for (int b = 0; b < 4; ++b) {
         uint32_t A = vit_par((2 * k[b]) & 0x6d), B = vit_par((2 * k[b]) & 0x4f);
         s |= (2 * A + B) << (4 * b);
+    }
+    return s;
+}
+
+// selector picking, for two butterflies k0 (low halfword) and k1 (high), halfword (2A+B) of a (Tlo, Thi) register pair
+__host__ __device__ constexpr uint32_t vit_sel2(int k0, int k1)
+{
+    const int k[2] = {k0, k1};
+    uint32_t s = 0;
+    for (int b = 0; b < 2; ++b) {
+        uint32_t idx = 2 * vit_par((2 * k[b]) & 0x6d) + vit_par((2 * k[b]) & 0x4f);
+        s |= ((2 * idx) | ((2 * idx + 1) << 4)) << (8 * b);
     }
     return s;
 }
@@ -300,6 +314,154 @@ struct VitCore {
 #pragma unroll
         for (int i = 0; i < 16; ++i) P[i] = 0;
         return c;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// VitCoreH: the per-thread decoder with metric and path byte of a state in ONE halfword, two states per register:
+//     halfword = metric << 8 | path byte,   the decision of step s of a chunk at bit s of the path byte (ascending).
+// The candidate that comes from state k + 32 carries the step's decision bit, and every later bit of both candidates'
+// path bytes is still zero, so among equal metrics it is the larger halfword: ONE packed 16-bit maximum performs the
+// compare, upstream's tie rule (-> k + 32) and the selection of metric and path together -- VIADDMNMX.U16x2 even adds
+// one candidate's branch metric on the way.  An add-compare-select of two butterflies (four new states) is two
+// alu-pipe instructions + two adds (which ptxas places on the fma pipe), against 8.5 + 5 for four butterflies in the
+// byte-packed form (compare word, sign-replicating permute, two selects per output word).  Same 32 registers of state.
+// Path bytes are therefore bit-reversed with respect to upstream's shift register (decision of step s at bit 7 - s):
+// the traceback reverses the byte it follows (one BREV per hop), and the output byte is reversed once.
+// Metrics stay below 12 + 4 * 16 = 76 between renormalisations (every fourth chunk), so 8 bits hold them.
+struct VitCoreH {
+    uint32_t X[32];                      // natural order: word j = states 2j (low halfword), 2j + 1 (high)
+
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) X[i] = 0;
+    }
+    // per-step branch words: halfword p = 2A + B of (Tlo | Thi) = disagreements with the expected pair (A, B), << 8;
+    // Ew = symbols present (not erased) << 8 in both halfwords
+    static __device__ __forceinline__ uint4 branch(uint32_t nib)
+    {
+        const uint32_t s0 = nib & 3u, s1 = (nib >> 2) & 3u;
+        const uint32_t e0 = s0 != 2u, e1 = s1 != 2u;
+        uint32_t t[4];
+#pragma unroll
+        for (uint32_t p = 0; p < 4; ++p) t[p] = ((e0 & (s0 ^ (p >> 1))) + (e1 & (s1 ^ (p & 1u)))) << 8;
+        return make_uint4(t[0] | (t[1] << 16), t[2] | (t[3] << 16), ((e0 + e1) << 8) * 0x00010001u, 0u);
+    }
+    // a + b as a multiply-add by one: ptxas then keeps register-register adds as IMAD.IADD (fma pipe) where it would
+    // place part of the plain adds on the alu pipe (VIADD) -- the pipe this kernel is bound by
+    static __device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b)
+    {
+        uint32_t d;
+        asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    // two packed butterflies k0 (low halfword), k1 (high): lo = old states k, hi = old states k + 32;
+    // v0 = survivors of the new states 2k, v1 of 2k + 1.  BITW: this step's decision bit in both path bytes.
+    // Measured alternatives (tools/ab.sh, 37888 frames, this form 2.34 ms): separate add + VIMNMX 3.08 ms (the adds
+    // load the fma pipe, whose IMADs issue at half rate too); one permute + three adds shared by the complementary
+    // selector pair (sel ^ 0x6666, T[3 - p] = E - T[p]) saves 67 instructions per chunk and costs 2 %; the + BITW as a
+    // true IMAD (multiplier in a register) instead of the VIADD ptxas makes of an immediate add, 2.41 ms.
+    template <uint32_t BITW>
+    static __device__ __forceinline__ void bfly(uint32_t Tlo, uint32_t Thi, uint32_t Ew, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t &v0, uint32_t &v1)
+    {
+        const uint32_t svm = prmt(Tlo, Thi, sel), sv = fadd(Ew, 0u - svm);
+        v0 = __viaddmax_u16x2(lo, sv, fadd(hi, fadd(svm, BITW)));
+        v1 = __viaddmax_u16x2(lo, svm, fadd(hi, fadd(sv, BITW)));
+    }
+    // Four steps, one re-layout (the schedule of VitCoreSoft::step4: stride inside a word 1 -> 2 -> 4 -> 8 -> 16, then a
+    // halfword transpose per word pair).  bm: 16-entry shared-memory table of branch() indexed by the 4-bit symbol pair.
+    template <int S0>
+    __device__ __forceinline__ void step4(const uint4 *bm, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
+    {
+        constexpr uint32_t B0 = 0x00010001u << S0, B1 = B0 << 1, B2 = B0 << 2, B3 = B0 << 3;
+        uint32_t S[32], Q[32];
+        uint4 te;
+        // A: natural, pair j: k = 2j + b -> S[j] = {4j, 4j+2}, S[16+j] = {4j+1, 4j+3}
+        te = bm[n0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bfly<B0>(te.x, te.y, te.z, vit_sel2(2 * j, 2 * j + 1), X[j], X[j + 16], S[j], S[16 + j]);
+        // B: stride 2.  even pair j: k = 4j + 2b ; odd pair j: k = 4j + 2b + 1 -> Q[4j + o] = {8j + o, 8j + 4 + o}
+        te = bm[n1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            bfly<B1>(te.x, te.y, te.z, vit_sel2(4 * j, 4 * j + 2), S[j], S[j + 8], Q[4 * j], Q[4 * j + 1]);
+            bfly<B1>(te.x, te.y, te.z, vit_sel2(4 * j + 1, 4 * j + 3), S[16 + j], S[24 + j], Q[4 * j + 2], Q[4 * j + 3]);
+        }
+        // C: stride 4.  pair (j, o): k = 8j + 4b + o -> S[8j + o'] = {16j + o', 16j + 8 + o'}, o' = 2o, 2o+1
+        te = bm[n2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                bfly<B2>(te.x, te.y, te.z, vit_sel2(8 * j + o, 8 * j + 4 + o), Q[4 * j + o], Q[4 * (j + 4) + o], S[8 * j + 2 * o], S[8 * j + 2 * o + 1]);
+        // D: stride 8.  pair (j, o'): k = 16j + 8b + o' -> Q[16j + o''] = {32j + o'', 32j + 16 + o''}, o'' = 2o', 2o'+1
+        te = bm[n3];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                bfly<B3>(te.x, te.y, te.z, vit_sel2(16 * j + o, 16 * j + 8 + o), S[8 * j + o], S[8 * (j + 2) + o], Q[16 * j + 2 * o], Q[16 * j + 2 * o + 1]);
+        // stride 16 -> natural: natural word w = {2w, 2w+1}; Q[16j + e], Q[16j + e + 1] (e even) hold them in the same lane
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+                X[(32 * j + e) >> 1] = prmt(Q[16 * j + e], Q[16 * j + e + 1], 0x5410u);
+                X[(32 * j + 16 + e) >> 1] = prmt(Q[16 * j + e], Q[16 * j + e + 1], 0x7632u);
+            }
+    }
+    // end of a chunk: snapshot the path bytes (ring slot `slot`, byte = state, as VitCore's ring), first best state,
+    // optional renormalisation, path bytes cleared.  keep: mask applied to the path bytes first (0xff; 0xfc after the
+    // 6-step first chunk, which runs as two erased steps + 6).
+    __device__ __forceinline__ VitCore::Trace trace_begin(uint32_t *ring, int slot, int ntb, int tid, bool renorm, uint32_t keep = 0xffu)
+    {
+        const uint32_t keepw = 0xff00ff00u | keep | (keep << 16);
+#pragma unroll
+        for (int w = 0; w < 16; ++w) ring[(slot * 16 + w) * VIT_BLOCK + tid] = prmt(X[2 * w] & keepw, X[2 * w + 1] & keepw, 0x6420u);
+        // path bytes cleared; keys (metric << 8) | (63 - state) -- the largest key is the largest metric at the smallest
+        // state -- are the cleared words plus the state labels (an add: fma pipe, where a permute would be alu)
+        uint32_t key[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            X[j] &= 0xff00ff00u;
+            key[j] = fadd(X[j], (uint32_t)(63 - 2 * j) | ((uint32_t)(62 - 2 * j) << 16));
+        }
+#pragma unroll
+        for (int n = 16; n >= 1; n >>= 1)
+#pragma unroll
+            for (int i = 0; i < n; ++i) key[i] = __vmaxu2(key[i], key[i + n]);
+        const uint32_t kbest = max(key[0] & 0xffffu, key[0] >> 16);
+        VitCore::Trace t;
+        t.bs = 63 - (int)(kbest & 0xffu);
+        t.sl = slot;
+        t.left = ntb - 1;
+        if (renorm) {
+            const uint32_t mx = kbest >> 8;
+            const uint32_t nminw = 0u - (mx > 12u ? ((mx - 12u) << 8) * 0x00010001u : 0u);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) X[i] = fadd(X[i], nminw);
+        }
+        return t;
+    }
+    // ring bytes hold the decisions in ascending bit order: the state eight steps back is the byte reversed, >> 2
+    template <int N>
+    static __device__ __forceinline__ void trace_hops(VitCore::Trace &t, const uint32_t *ring, int ntb, int tid)
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool go = t.left > 0;
+            const int nb = (int)(__brev(VitCore::ring_byte(ring, t.sl, t.bs, tid)) >> 26);
+            const int ns = (t.sl == 0) ? ntb - 1 : t.sl - 1;
+            t.bs = go ? nb : t.bs;
+            t.sl = go ? ns : t.sl;
+            t.left -= go ? 1 : 0;
+        }
+    }
+    // the chunk's output byte in upstream's bit order (MSB = earliest decision)
+    static __device__ __forceinline__ uint32_t trace_finish(const VitCore::Trace &t, const uint32_t *ring, int tid)
+    {
+        return __brev(VitCore::ring_byte(ring, t.sl, t.bs, tid)) >> 24;
     }
 };
 
