@@ -149,13 +149,14 @@ const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "de
 
 #define MAX_LINKS 16384
 // Which Viterbi kernel decodes a call's (or a link group's) frames, by their number -- measured on 1528-byte 64-QAM 3/4
-// frames (tools/exp_viterbi_forms.sh): one trellis per warp 0.68 ms up to 592 frames, 0.87 at 1184, 1.45 at
-// 2368; per four lanes 0.93 ms flat up to 4736, 1.38 at 9472, 2.54 at 18944; per thread 1.72-1.78 ms up to 18944, 3.11 at 37888.
+// frames (tools/exp_viterbi_forms.sh, profiles/r02_viterbi_forms_sweep.txt): one trellis per warp 0.68 ms up
+// to 592 frames, 0.87 at 1184, 1.45 at 2368; per four lanes 0.93 ms flat up to 4736, 1.38 at 9472, 2.54 at 18944; per
+// thread 1.43-1.50 ms up to 18944, 2.34 at 37888.
 #ifndef VW_SWITCH
 #define VW_SWITCH 1280          // up to here one trellis per warp
 #endif
 #ifndef VQ_SWITCH
-#define VQ_SWITCH 12288         // up to here one trellis per four lanes; above, one per thread
+#define VQ_SWITCH 10240         // up to here one trellis per four lanes; above, one per thread
 #endif
 #define VQ_SPLIT_MAX 4736        // frames beyond a step of the per-thread kernel's staircase that get their own launch (run_rx)
 #define DET_SMEM DET_SMEM_BYTES
@@ -610,8 +611,8 @@ int run_rx(wifi_b200 *h, const cf *iq, bool mirror, const H2dPlan *plan = nullpt
                     else if (form == 2) k_viterbi_quad<<<(unsigned)((n + VQ_FRAMES - 1) / VQ_FRAMES), VQ_BLOCK, 0, st>>>(h->d_jobs, a, b, h->d_vit_in, h->d_psdu, h->d_frames);
                     else k_viterbi<<<(unsigned)((n + VIT_BLOCK - 1) / VIT_BLOCK), VIT_BLOCK, vit_smem, st>>>(h->d_jobs, a, b, h->d_vit_in, h->d_psdu, h->d_frames);
                 };
-                // The per-thread kernel's time is a staircase: 1.79 ms while every scheduler holds at most one of its warps
-                // (sm_count x 2 blocks x 64 = 18944 frames), 3.1 ms up to two (37888), and so on -- 18951 frames cost what
+                // The per-thread kernel's time is a staircase: 1.5 ms while every scheduler holds at most one of its warps
+                // (sm_count x 2 blocks x 64 = 18944 frames), 2.3 ms up to two (37888), and so on -- 18951 frames cost what
                 // 37888 do.  A few frames beyond a step (a long stream cut into step-sized segments with an overlap) therefore
                 // go to their own launch on a second stream, in the form their number calls for, beside the main grid.
                 const int64_t wave = (int64_t)h->sm_count * 2 * VIT_BLOCK;
