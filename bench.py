@@ -694,7 +694,7 @@ def main():
                 "instruction_count_source": "committed ncu (%s): smsp__inst_executed_pipe_alu.sum per decoded frame" % pipe.get("source", "profiles/"),
                 "alu_warp_inst_per_launch": alu_inst, "ms_per_launch": vit_ms,
                 "algorithmic_bytes_per_launch": vit_alg_bytes, "hbm_frac_for_reference": vit_alg_bytes / (vit_ms * 1e-3) / 1e9 / hbm_peak,
-                "note": "one trellis per thread, 64 byte-packed path metrics in 16 registers; %.2f Tint-op/s algorithmic (256 int-op per decoded bit, four states per 32-bit word)" % (
+                "note": "one trellis per thread, metric and path byte of a state in one halfword, add-compare-select by VIADDMNMX.U16x2 (alu pipe 73 %%, fma pipe 32 %%, issue 72 %% in ncu); %.2f Tint-op/s algorithmic (256 int-op per decoded bit)" % (
                     dec_bits * 256 / (vit_ms * 1e-3) / 1e12)}
     else:
         roof = {"kernel": "k_viterbi", "bound": "alu", "achieved": None, "peak": alu_peak / 1e9, "unit": "Gwarp-inst/s", "frac": None, "traffic": None,
