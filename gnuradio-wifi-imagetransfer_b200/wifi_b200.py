@@ -193,6 +193,10 @@ class Handle:
             raise WifiB200Error(rc, self._L.wifi_b200_strerror(rc).decode())
         self._h = h
         self.max_frames = int(max_frames) if max_frames else int(max_samples) // 1000 + 64
+        # test hook: WIFI_B200_VITERBI_FORM=1|2|3 pins the Viterbi kernel form of every handle (the three forms are one decoder:
+        # the whole GPU suite must pass under each)
+        if os.environ.get("WIFI_B200_VITERBI_FORM"):
+            self.set_param(P_VITERBI_FORM, int(os.environ["WIFI_B200_VITERBI_FORM"]))
 
     def close(self):
         if getattr(self, "_h", None):
