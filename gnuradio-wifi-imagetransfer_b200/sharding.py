@@ -206,9 +206,9 @@ def gather_records(hdr, rec, device=None, fixed_rows=None):
         mine[0, FOUND] = len(rec)
         mine[1:1 + len(rec)] = rec
         buf = torch.from_numpy(mine).to(device) if device is not None else torch.from_numpy(mine)
-        everyone = torch.empty((world,) + tuple(buf.shape), dtype=torch.int32, device=buf.device)
+        everyone = torch.empty((world * buf.shape[0], buf.shape[1]), dtype=torch.int32, device=buf.device)    # rank r's rows at [r * (K + 1), ...): the layout gloo accepts too
         dist.all_gather_into_tensor(everyone, buf)
-        a = everyone.cpu().numpy()
+        a = everyone.cpu().numpy().reshape(world, buf.shape[0], buf.shape[1])
         out = []
         for r in range(world):
             c = int(a[r, 0, FOUND])

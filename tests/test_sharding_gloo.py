@@ -31,15 +31,21 @@ def _worker(rank, world, port, kind, out_dir):
         ref = S.stats_vector(total, sum(c.size for c in caps))
     else:
         from util import adversarial_stream, oracle_segment_decoder
+        tails = kind.startswith("tail")          # the form bench.py runs: only the last owned records travel, in fixed-size buffers
         if kind == "stream":
             y, _ = make_capture(O, rng, [(2, 400)] * 40, snr_db=30, seed=9, gap=900)
         else:
-            y = adversarial_stream(O, trunc=int(kind[3:]))
+            y = adversarial_stream(O, trunc=int(kind[4:] if tails else kind[3:]))
         seg = S.shard_stream(y.size, world, overlap=S.OVERLAP)[rank]
         full = O.rx(y, algo=0, want_carrier=False).frames
         # every rank decodes its segment, the frame records are all-gathered (gloo here, NCCL on the GPUs), every rank
         # checks that it joined the sequential receiver's state and decodes again from a known state if it did not
-        own, owned_all, rounds = S.reconcile(oracle_segment_decoder(O, y, algo=0), S.shard_stream(y.size, world), rank, y.size)
+        trace = {}
+        own, owned_all, rounds = S.reconcile(oracle_segment_decoder(O, y, algo=0), S.shard_stream(y.size, world), rank, y.size,
+                                             tail_rows=64 if tails else None, trace=trace)
+        if tails:
+            assert all(len(t) <= 64 for t in owned_all) and {"decode", "exchange", "check"} <= set(trace)
+            owned_all = S.gather_owned(own)
         assert S.same(np.concatenate(owned_all), S.records(full.copy(), 0)), (kind, rank)
         assert (rounds >= 1) == (kind != "stream"), (kind, rounds)      # idle gaps: joined at once; adversarial: one more pass
         frames = np.zeros(len(own), full.dtype)
@@ -72,7 +78,7 @@ def test_overlapping_segments_dedup_to_the_sequential_frame_set(tmp_path):
 
 def test_back_to_back_traffic_without_idle_gaps_still_reconciles(tmp_path):
     """Trigger chains that never merge (adv500) and a decode_mac tag pending across more than the overlap (adv641)."""
-    for kind in ("adv500", "adv641"):
+    for kind in ("adv500", "adv641", "tail500", "tail641"):
         _run(kind, tmp_path)
         t = np.sort(np.concatenate([np.load(tmp_path / "trig0.npy"), np.load(tmp_path / "trig1.npy")]))
         assert np.array_equal(t, np.load(tmp_path / "trig_full.npy"))
