@@ -1252,11 +1252,11 @@ __global__ void __launch_bounds__(VIT_BLOCK) k_viterbi(const JobDesc *__restrict
     uint32_t *ring = vsm;                                   // VIT_NTB_MAX*16*VIT_BLOCK words
     uint32_t *s_crc = vsm + VIT_NTB_MAX * 16 * VIT_BLOCK;   // 256
     uint16_t *s_scr = (uint16_t *)(s_crc + 256);            // 128
-    uint4 *s_bm = (uint4 *)(s_crc + 256 + 64);              // 16 branch-word triples (VitCoreH::branch)
+    uint4 *s_bm = (uint4 *)(s_crc + 256 + 64);              // branch-word table [8 steps][4 selectors][16 symbol pairs] (VitCoreH::table_entry)
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += VIT_BLOCK) s_crc[i] = c_tab.crc_tab[i];
     for (int i = tid; i < 128; i += VIT_BLOCK) s_scr[i] = c_tab.scr_tab[i];
-    if (tid < 16) s_bm[tid] = VitCoreH::branch((uint32_t)tid);
+    for (int i = tid; i < 512; i += VIT_BLOCK) s_bm[i] = VitCoreH::table_entry(i >> 6, (i >> 4) & 3, (uint32_t)(i & 15));
     __syncthreads();
     const int job = f0 + blockIdx.x * VIT_BLOCK + tid;
     if (job >= n_frames) return;

@@ -356,59 +356,69 @@ struct VitCoreH {
         asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
         return d;
     }
-    // two packed butterflies k0 (low halfword), k1 (high): lo = old states k, hi = old states k + 32;
-    // v0 = survivors of the new states 2k, v1 of 2k + 1.  BITW: this step's decision bit in both path bytes.
-    // Measured alternatives (tools/ab.sh, 37888 frames, this form 2.34 ms): separate add + VIMNMX 3.08 ms (the adds
-    // load the fma pipe, whose IMADs issue at half rate too); one permute + three adds shared by the complementary
-    // selector pair (sel ^ 0x6666, T[3 - p] = E - T[p]) saves 67 instructions per chunk and costs 2 %; the + BITW as a
-    // true IMAD (multiplier in a register) instead of the VIADD ptxas makes of an immediate add, 2.41 ms.
-    template <uint32_t BITW>
-    static __device__ __forceinline__ void bfly(uint32_t Tlo, uint32_t Thi, uint32_t Ew, uint32_t sel, uint32_t lo, uint32_t hi, uint32_t &v0, uint32_t &v1)
+    // ---- branch words from a table ----
+    // Every stage of the four-step schedule (the one of VitCoreSoft::step4: stride inside a word 1 -> 2 -> 4 -> 8 -> 16,
+    // then a halfword transpose per word pair) uses exactly four selectors (two complementary pairs), distinguished by the
+    // expected pair of their low-halfword butterfly (c = 2A + B of k0); the high halfword's is c ^ 1 in stage A, 3 - c in
+    // stages B and C, c in stage D.  table[s][c][nibble] = (svm, sv, svm + BIT_s, sv + BIT_s) for step s of a chunk:
+    // one LDS.128 replaces the permute and the three adds per selector and step (the lsu pipe is idle, the alu pipe is
+    // not): 2.33 -> 2.14 ms per 37888 frames.  Measured alternatives of the add-compare-select itself (tools/ab.sh):
+    // separate add + VIMNMX instead of the fused VIADDMNMX 3.08 ms (the adds load the fma pipe, whose IMADs issue at
+    // half rate too); plain `+` instead of fadd() 2.55 ms (ptxas places a third of the adds on the alu pipe).
+    // two packed butterflies k0 (low halfword), k1 (high): lo = old states k, hi = old states k + 32; v0 = survivors of
+    // the new states 2k, v1 of 2k + 1; e = the table entry of their selector.
+    static __device__ __forceinline__ uint4 table_entry(int s, int c, uint32_t nib)
     {
-        const uint32_t svm = prmt(Tlo, Thi, sel), sv = fadd(Ew, 0u - svm);
-        v0 = __viaddmax_u16x2(lo, sv, fadd(hi, fadd(svm, BITW)));
-        v1 = __viaddmax_u16x2(lo, svm, fadd(hi, fadd(sv, BITW)));
+        const int st = s & 3;
+        const int c1 = st == 0 ? (c ^ 1) : (st == 3 ? c : 3 - c);
+        const uint32_t sel = (uint32_t)((2 * c) | ((2 * c + 1) << 4)) | ((uint32_t)((2 * c1) | ((2 * c1 + 1) << 4)) << 8);
+        const uint4 b = branch(nib);
+        const uint32_t svm = prmt(b.x, b.y, sel), sv = b.z - svm, bit = 0x00010001u << s;
+        return make_uint4(svm, sv, svm + bit, sv + bit);
     }
-    // Four steps, one re-layout (the schedule of VitCoreSoft::step4: stride inside a word 1 -> 2 -> 4 -> 8 -> 16, then a
-    // halfword transpose per word pair).  bm: 16-entry shared-memory table of branch() indexed by the 4-bit symbol pair.
-    template <int S0>
-    __device__ __forceinline__ void step4(const uint4 *bm, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
+    static __device__ __forceinline__ void bflyt(const uint4 e, uint32_t lo, uint32_t hi, uint32_t &v0, uint32_t &v1)
     {
-        constexpr uint32_t B0 = 0x00010001u << S0, B1 = B0 << 1, B2 = B0 << 2, B3 = B0 << 3;
+        v0 = __viaddmax_u16x2(lo, e.y, fadd(hi, e.z));
+        v1 = __viaddmax_u16x2(lo, e.x, fadd(hi, e.w));
+    }
+    static __host__ __device__ constexpr int selc(uint32_t sel) { return (int)((sel & 0xfu) >> 1); }
+    // bt: the table, uint4 [8][4][16]
+    template <int S0>
+    __device__ __forceinline__ void step4(const uint4 *bt, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3)
+    {
         uint32_t S[32], Q[32];
-        uint4 te;
-        // A: natural, pair j: k = 2j + b -> S[j] = {4j, 4j+2}, S[16+j] = {4j+1, 4j+3}
-        te = bm[n0];
+        uint4 e[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bfly<B0>(te.x, te.y, te.z, vit_sel2(2 * j, 2 * j + 1), X[j], X[j + 16], S[j], S[16 + j]);
-        // B: stride 2.  even pair j: k = 4j + 2b ; odd pair j: k = 4j + 2b + 1 -> Q[4j + o] = {8j + o, 8j + 4 + o}
-        te = bm[n1];
+        for (int c = 0; c < 4; ++c) e[c] = bt[((S0 + 0) * 4 + c) * 16 + n0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bflyt(e[selc(vit_sel2(2 * j, 2 * j + 1))], X[j], X[j + 16], S[j], S[16 + j]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[c] = bt[((S0 + 1) * 4 + c) * 16 + n1];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            bfly<B1>(te.x, te.y, te.z, vit_sel2(4 * j, 4 * j + 2), S[j], S[j + 8], Q[4 * j], Q[4 * j + 1]);
-            bfly<B1>(te.x, te.y, te.z, vit_sel2(4 * j + 1, 4 * j + 3), S[16 + j], S[24 + j], Q[4 * j + 2], Q[4 * j + 3]);
+            bflyt(e[selc(vit_sel2(4 * j, 4 * j + 2))], S[j], S[j + 8], Q[4 * j], Q[4 * j + 1]);
+            bflyt(e[selc(vit_sel2(4 * j + 1, 4 * j + 3))], S[16 + j], S[24 + j], Q[4 * j + 2], Q[4 * j + 3]);
         }
-        // C: stride 4.  pair (j, o): k = 8j + 4b + o -> S[8j + o'] = {16j + o', 16j + 8 + o'}, o' = 2o, 2o+1
-        te = bm[n2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[c] = bt[((S0 + 2) * 4 + c) * 16 + n2];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int o = 0; o < 4; ++o)
-                bfly<B2>(te.x, te.y, te.z, vit_sel2(8 * j + o, 8 * j + 4 + o), Q[4 * j + o], Q[4 * (j + 4) + o], S[8 * j + 2 * o], S[8 * j + 2 * o + 1]);
-        // D: stride 8.  pair (j, o'): k = 16j + 8b + o' -> Q[16j + o''] = {32j + o'', 32j + 16 + o''}, o'' = 2o', 2o'+1
-        te = bm[n3];
+                bflyt(e[selc(vit_sel2(8 * j + o, 8 * j + 4 + o))], Q[4 * j + o], Q[4 * (j + 4) + o], S[8 * j + 2 * o], S[8 * j + 2 * o + 1]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[c] = bt[((S0 + 3) * 4 + c) * 16 + n3];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int o = 0; o < 8; ++o)
-                bfly<B3>(te.x, te.y, te.z, vit_sel2(16 * j + o, 16 * j + 8 + o), S[8 * j + o], S[8 * (j + 2) + o], Q[16 * j + 2 * o], Q[16 * j + 2 * o + 1]);
-        // stride 16 -> natural: natural word w = {2w, 2w+1}; Q[16j + e], Q[16j + e + 1] (e even) hold them in the same lane
+                bflyt(e[selc(vit_sel2(16 * j + o, 16 * j + 8 + o))], S[8 * j + o], S[8 * (j + 2) + o], Q[16 * j + 2 * o], Q[16 * j + 2 * o + 1]);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-                X[(32 * j + e) >> 1] = prmt(Q[16 * j + e], Q[16 * j + e + 1], 0x5410u);
-                X[(32 * j + 16 + e) >> 1] = prmt(Q[16 * j + e], Q[16 * j + e + 1], 0x7632u);
+            for (int e2 = 0; e2 < 16; e2 += 2) {
+                X[(32 * j + e2) >> 1] = prmt(Q[16 * j + e2], Q[16 * j + e2 + 1], 0x5410u);
+                X[(32 * j + 16 + e2) >> 1] = prmt(Q[16 * j + e2], Q[16 * j + e2 + 1], 0x7632u);
             }
     }
     // end of a chunk: snapshot the path bytes (ring slot `slot`, byte = state, as VitCore's ring), first best state,
