@@ -151,7 +151,7 @@ const char *STAGE_NAMES[ST_COUNT] = {"h2d", "detect", "select", "sync_long", "de
 // Which Viterbi kernel decodes a call's (or a link group's) frames, by their number -- measured on 1528-byte 64-QAM 3/4
 // frames (tools/exp_viterbi_forms.sh, profiles/r02_viterbi_forms_sweep.txt): one trellis per warp 0.68 ms up
 // to 592 frames, 0.87 at 1184, 1.45 at 2368; per four lanes 0.93 ms flat up to 4736, 1.38 at 9472, 2.54 at 18944; per
-// thread 1.43-1.50 ms up to 18944, 2.34 at 37888.
+// thread 1.43-1.50 ms up to 18944, 2.34 at 37888 (measured before that kernel's branch-word table: 2.14 at 37888 now).
 #ifndef VW_SWITCH
 #define VW_SWITCH 1280          // up to here one trellis per warp
 #endif
